@@ -1,0 +1,190 @@
+// af_device.cuh -- device helpers shared by the kernels: bit-exact reference arithmetic
+// (downmix, cubic interpolation, frame energy, VAD step) and the register FFT.
+#pragma once
+#include "af_common.cuh"
+
+namespace af {
+
+// ------------------------------------------------------------------------------------------
+// Downmix: AudioFrame::to_mono (capture.rs:30-42).  Sequential sum from 0.0, one division.
+// Frames outside [0, n_in) read as 0 (the resampler's zero history / flush padding,
+// resampler.rs:150-158).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float load_mono(const void *__restrict__ data, uint64_t n_samples, uint32_t n_in,
+                                           uint32_t channels, uint32_t format, int idx)
+{
+    if (idx < 0 || (uint32_t)idx >= n_in) return 0.0f;
+    if (channels == 1) {
+        if (format == FMT_F32) return __ldg(reinterpret_cast<const float *>(data) + idx);
+        return (float)__ldg(reinterpret_cast<const short *>(data) + idx) * (1.0f / 32768.0f);
+    }
+    const uint64_t base = (uint64_t)idx * channels;
+    if (channels == 2 && base + 2 <= n_samples) {
+        float l, r;
+        if (format == FMT_F32) {
+            const float2 v = __ldg(reinterpret_cast<const float2 *>(data) + idx);
+            l = v.x; r = v.y;
+        } else {
+            const short2 v = __ldg(reinterpret_cast<const short2 *>(data) + idx);
+            l = (float)v.x * (1.0f / 32768.0f); r = (float)v.y * (1.0f / 32768.0f);
+        }
+        return __fmul_rn(__fadd_rn(__fadd_rn(0.0f, l), r), 0.5f);   // x / 2 == x * 0.5 exactly
+    }
+    uint32_t m = channels;
+    if (base + m > n_samples) m = (uint32_t)(n_samples - base);     // trailing partial frame
+    float sum = 0.0f;
+    for (uint32_t c = 0; c < m; ++c) {
+        float v = format == FMT_F32 ? __ldg(reinterpret_cast<const float *>(data) + base + c)
+                                    : (float)__ldg(reinterpret_cast<const short *>(data) + base + c) * (1.0f / 32768.0f);
+        sum = __fadd_rn(sum, v);
+    }
+    return __fdiv_rn(sum, (float)channels);
+}
+
+// ------------------------------------------------------------------------------------------
+// rubato 0.16.2 interp_cubic (points at -1, 0, 1, 2), evaluated with the exact operation
+// order of the Rust source and no FMA contraction.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float interp_cubic(float x, float y0, float y1, float y2, float y3)
+{
+    const float c13 = 1.0f / 3.0f, c16 = 1.0f / 6.0f;
+    const float a0 = y1;
+    const float a1 = __fsub_rn(__fadd_rn(__fsub_rn(__fmul_rn(-c13, y0), __fmul_rn(0.5f, y1)), y2), __fmul_rn(c16, y3));
+    const float a2 = __fsub_rn(__fmul_rn(0.5f, __fadd_rn(y0, y2)), y1);
+    const float a3 = __fadd_rn(__fmul_rn(0.5f, __fsub_rn(y1, y2)), __fmul_rn(c16, __fsub_rn(y3, y0)));
+    const float x2 = __fmul_rn(x, x);
+    const float x3 = __fmul_rn(x2, x);
+    return __fadd_rn(__fadd_rn(__fadd_rn(a0, __fmul_rn(a1, x)), __fmul_rn(a2, x2)), __fmul_rn(a3, x3));
+}
+
+// Position of output n of the reference resampler in input-sample units:
+//   P_n = -4 + (n + 1) * p / q          (last_index = -4, one step of p/q per output)
+// returned as k = floor(P_n) and rem = (P_n - k) * q, computed exactly in integers.
+__host__ __device__ __forceinline__ void resample_pos(uint64_t n, uint32_t p, uint32_t q, long long *k, uint32_t *rem)
+{
+    const uint64_t num = (n + 1) * (uint64_t)p + 4ull * q;   // shifted by +8q to stay non-negative
+    *k = (long long)(num / q) - 8;
+    *rem = (uint32_t)(num % q);
+}
+
+// One resampled sample, given the exact integer position (k, rem) and the stream tables.
+//   RS_EXACT: q is a power of two (or 1) -> the f64 recurrence of the reference is exact and
+//             frac = rem / q.
+//   RS_TABLE: frac comes from the host-run f64 recurrence; when the exact position is an integer
+//             the recurrence may sit one ulp below it, which shows as frac ~ 1 and k - 1.
+__device__ __forceinline__ float resample_one(const void *__restrict__ data, uint64_t n_samples, uint32_t n_in,
+                                              uint32_t channels, uint32_t format, uint32_t mode, float inv_q,
+                                              const float *__restrict__ frac_tab, uint32_t n, int k, uint32_t rem)
+{
+    float frac;
+    if (mode == RS_TABLE) {
+        frac = __ldg(frac_tab + n);
+        if (rem == 0 && frac >= 0.5f) k -= 1;
+    } else {
+        frac = (float)rem * inv_q;
+    }
+    const float y0 = load_mono(data, n_samples, n_in, channels, format, k - 1);
+    const float y1 = load_mono(data, n_samples, n_in, channels, format, k);
+    const float y2 = load_mono(data, n_samples, n_in, channels, format, k + 1);
+    const float y3 = load_mono(data, n_samples, n_in, channels, format, k + 2);
+    return interp_cubic(frac, y0, y1, y2, y3);
+}
+
+// ------------------------------------------------------------------------------------------
+// VAD arithmetic (vad.rs:101-153), one frame step on a precomputed mean-square energy.
+// The dB comparison `20*log10(e) > threshold_db` is replaced by `e >= e_min` where e_min is the
+// smallest f32 that satisfies it under the host libm (NaN when none does); see DESIGN.md.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int vad_step(VadState &v, const VadParams &pr, float energy)
+{
+    const float sm = __fadd_rn(__fmul_rn(pr.alpha, energy), __fmul_rn(__fsub_rn(1.0f, pr.alpha), v.smoothed));
+    v.smoothed = sm;
+    const float det = pr.alpha > 0.0f ? sm : energy;
+    const bool is_speech = det >= pr.e_min;
+    if (v.state == 0) {                       // Silence
+        if (is_speech) { v.speech_frames = 1; v.silence_frames = 0; v.state = 1; }
+    } else if (v.state == 1) {                // Speech
+        if (is_speech) { v.speech_frames += 1; v.silence_frames = 0; }
+        else {
+            v.silence_frames += 1;
+            if (v.silence_frames >= pr.silence_timeout) {
+                v.state = v.speech_frames >= pr.min_speech ? 2 : 0;
+                v.speech_frames = 0;
+            }
+        }
+    } else {                                  // Ending -> Silence, unconditionally
+        v.state = 0;
+        v.silence_frames = 0;
+    }
+    return v.state;
+}
+
+// ------------------------------------------------------------------------------------------
+// Register FFT building blocks (forward transform, e^{-i...}).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fft4(float &r0, float &i0, float &r1, float &i1, float &r2, float &i2, float &r3,
+                                     float &i3)
+{
+    const float t0r = r0 + r2, t0i = i0 + i2, t1r = r0 - r2, t1i = i0 - i2;
+    const float t2r = r1 + r3, t2i = i1 + i3, t3r = r1 - r3, t3i = i1 - i3;
+    r0 = t0r + t2r; i0 = t0i + t2i;
+    r2 = t0r - t2r; i2 = t0i - t2i;
+    r1 = t1r + t3i; i1 = t1i - t3r;     // t1 - i t3
+    r3 = t1r - t3i; i3 = t1i + t3r;     // t1 + i t3
+}
+// same with input 3 known to be zero
+__device__ __forceinline__ void fft4_z3(float &r0, float &i0, float &r1, float &i1, float &r2, float &i2, float &r3,
+                                        float &i3)
+{
+    const float t0r = r0 + r2, t0i = i0 + i2, t1r = r0 - r2, t1i = i0 - i2;
+    const float ur = r1, ui = i1;
+    r0 = t0r + ur; i0 = t0i + ui;
+    r2 = t0r - ur; i2 = t0i - ui;
+    r1 = t1r + ui; i1 = t1i - ur;
+    r3 = t1r - ui; i3 = t1i + ur;
+}
+
+#define AF_CMUL(ar, ai, wr, wi)                       \
+    do {                                              \
+        const float _tr = (ar) * (wr) - (ai) * (wi);  \
+        const float _ti = (ar) * (wi) + (ai) * (wr);  \
+        (ar) = _tr; (ai) = _ti;                       \
+    } while (0)
+
+// In-register 16-point FFT, 4x4 decomposition n = 4a + b, k = c + 4d.
+// Input x[n] natural order; output X[k] is left in slot 4*(k&3) + (k>>2).
+// PRUNED: inputs 13, 14, 15 are known zeros (a 400-sample window in a 512-point transform).
+template <bool PRUNED>
+__device__ __forceinline__ void fft16(float (&xr)[16], float (&xi)[16])
+{
+    constexpr float C1 = 0.92387953251128674f;   // cos(pi/8)
+    constexpr float S1 = 0.38268343236508977f;   // sin(pi/8)
+    constexpr float R = 0.70710678118654752f;
+    fft4(xr[0], xi[0], xr[4], xi[4], xr[8], xi[8], xr[12], xi[12]);
+    if (PRUNED) {
+        fft4_z3(xr[1], xi[1], xr[5], xi[5], xr[9], xi[9], xr[13], xi[13]);
+        fft4_z3(xr[2], xi[2], xr[6], xi[6], xr[10], xi[10], xr[14], xi[14]);
+        fft4_z3(xr[3], xi[3], xr[7], xi[7], xr[11], xi[11], xr[15], xi[15]);
+    } else {
+        fft4(xr[1], xi[1], xr[5], xi[5], xr[9], xi[9], xr[13], xi[13]);
+        fft4(xr[2], xi[2], xr[6], xi[6], xr[10], xi[10], xr[14], xi[14]);
+        fft4(xr[3], xi[3], xr[7], xi[7], xr[11], xi[11], xr[15], xi[15]);
+    }
+    // slot 4c + b holds Y[b][c]; multiply by W16^(b c)
+    AF_CMUL(xr[5], xi[5], C1, -S1);          // b=1 c=1 : W^1
+    AF_CMUL(xr[9], xi[9], R, -R);            // b=1 c=2 : W^2
+    AF_CMUL(xr[13], xi[13], S1, -C1);        // b=1 c=3 : W^3
+    AF_CMUL(xr[6], xi[6], R, -R);            // b=2 c=1 : W^2
+    { const float t = xr[10]; xr[10] = xi[10]; xi[10] = -t; }   // b=2 c=2 : W^4 = -i
+    AF_CMUL(xr[14], xi[14], -R, -R);         // b=2 c=3 : W^6
+    AF_CMUL(xr[7], xi[7], S1, -C1);          // b=3 c=1 : W^3
+    AF_CMUL(xr[11], xi[11], -R, -R);         // b=3 c=2 : W^6
+    AF_CMUL(xr[15], xi[15], -C1, S1);        // b=3 c=3 : W^9
+    fft4(xr[0], xi[0], xr[1], xi[1], xr[2], xi[2], xr[3], xi[3]);
+    fft4(xr[4], xi[4], xr[5], xi[5], xr[6], xi[6], xr[7], xi[7]);
+    fft4(xr[8], xi[8], xr[9], xi[9], xr[10], xi[10], xr[11], xi[11]);
+    fft4(xr[12], xi[12], xr[13], xi[13], xr[14], xi[14], xr[15], xi[15]);
+}
+__host__ __device__ constexpr int fft16_slot(int k) { return 4 * (k & 3) + (k >> 2); }
+
+}  // namespace af

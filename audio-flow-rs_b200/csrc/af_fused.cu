@@ -1,0 +1,302 @@
+// af_fused.cu -- the fused hot-path kernel for sm_100a:
+//   K1 downmix + cubic (rubato FastFixedIn) resample  -> 16 kHz tile in shared memory
+//   K2 Hann window + 512-point real FFT (packed 256-point complex, 16x16 in registers,
+//      one half-warp per frame, transposed through shared memory, Hermitian split by shuffles)
+//   K3 sparse banded mel projection + log
+//   K4 (energy part) bit-exact sequential mean-square per frame on a dedicated VAD warp
+// Replaces capture.rs:30-42, resampler.rs:71-93/132-166 (+ rubato) and the O(len) part of
+// vad.rs:157-168; the STFT/mel stages are spec-defined.  The sequential EMA/state
+// machine of vad.rs:101-153 runs in af_vad_scan_kernel (af_kernels.cu).
+#include "af_device.cuh"
+#include "af_launch.h"
+
+namespace af {
+
+struct FusedSmem {
+    float ybuf[YBUF_FLOATS];                         // padded 16 kHz samples of the current step
+    float scr[16 * SCR_FLOATS_PER_FRAME];            // per half-warp transpose scratch / output stage
+    float pbuf[PBUF_FLOATS];                         // 4*|X[k]|^2, [bin][frame]
+    FftTables fft;
+    MelTables mel;
+    StreamDev stream;                                // descriptor of the tile's stream
+    int tile_k;                                      // floor(position) of the tile's first output
+    uint32_t tile_rem;                               // and its remainder (numerator units)
+    uint32_t inc_k, inc_rem;                         // position increment for FUSED_THREADS outputs
+};
+
+// ---- phase 1: resample the 16 kHz samples [base + i_begin, base + YLEN) of the stream into ybuf ----
+__device__ __forceinline__ void resample_step(FusedSmem &sm, const StreamDev &s, uint32_t tile_off, uint32_t base,
+                                              int i_begin, float inv_q)
+{
+    const int tid = threadIdx.x;
+    int i = i_begin + tid;
+    if (s.mode == RS_PASSTHROUGH) {
+        for (; i < YLEN; i += FUSED_THREADS) {
+            const uint32_t n = base + i;
+            float v = 0.0f;
+            if (n < s.n_out) v = load_mono(s.data, s.n_samples, s.n_in, s.channels, s.format, (int)n);
+            sm.ybuf[ypad(i)] = v;
+        }
+        return;
+    }
+    // exact integer position of this thread's first output, relative to the tile start
+    uint32_t a = sm.tile_rem + (tile_off + (uint32_t)i) * s.p;
+    uint32_t dk, rem;
+    if (s.q == 1) { dk = a; rem = 0; }
+    else { dk = a / s.q; rem = a - dk * s.q; }
+    int k = sm.tile_k + (int)dk;
+    const uint32_t inc_k = sm.inc_k, inc_rem = sm.inc_rem, q = s.q;
+    for (; i < YLEN; i += FUSED_THREADS) {
+        const uint32_t n = base + i;
+        float v = 0.0f;
+        if (n < s.n_out)
+            v = resample_one(s.data, s.n_samples, s.n_in, s.channels, s.format, s.mode, inv_q, s.frac, n, k, rem);
+        sm.ybuf[ypad(i)] = v;
+        k += (int)inc_k;
+        rem += inc_rem;
+        if (rem >= q) { rem -= q; k += 1; }
+    }
+}
+
+// ---- phase 2a: one frame per half-warp: window, packed real FFT, power -> pbuf[bin][q] ----
+__device__ __forceinline__ void fft_frame(FusedSmem &sm, float *__restrict__ scr, int q, int l, int lane)
+{
+    float xr[16], xi[16];
+    const float *yb = sm.ybuf + 180 * q + 2 * l;      // ypad(160 q + 32 n1 + 2 l) = 180 q + 36 n1 + 2 l
+    const float *wb = sm.fft.window + 2 * l;
+#pragma unroll
+    for (int n1 = 0; n1 < 12; ++n1) {
+        const float2 v = *reinterpret_cast<const float2 *>(yb + 36 * n1);
+        const float2 w = *reinterpret_cast<const float2 *>(wb + 32 * n1);
+        xr[n1] = __fmul_rn(v.x, w.x);
+        xi[n1] = __fmul_rn(v.y, w.y);
+    }
+    {
+        float2 v = make_float2(0.0f, 0.0f), w = make_float2(0.0f, 0.0f);
+        if (l < 8) {                                   // samples 384 + 2l (+1) < 400
+            v = *reinterpret_cast<const float2 *>(yb + 36 * 12);
+            w = *reinterpret_cast<const float2 *>(wb + 32 * 12);
+        }
+        xr[12] = __fmul_rn(v.x, w.x);
+        xi[12] = __fmul_rn(v.y, w.y);
+    }
+#pragma unroll
+    for (int n1 = 13; n1 < 16; ++n1) { xr[n1] = 0.0f; xi[n1] = 0.0f; }
+
+    // pass 1: 16-point FFT over n1 (this lane is n2 = l), twiddle W256^(l k1), transposed store
+    fft16<true>(xr, xi);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+        float ar = xr[fft16_slot(k1)], ai = xi[fft16_slot(k1)];
+        if (k1 > 0) {
+            const float2 w = sm.fft.tw1[k1 * 16 + l];
+            AF_CMUL(ar, ai, w.x, w.y);
+        }
+        *reinterpret_cast<float2 *>(scr + (k1 * SCR_ROW + l) * 2) = make_float2(ar, ai);
+    }
+    __syncwarp();
+    // pass 2: this lane is k1 = l; read its row (all n2), 16-point FFT over n2
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float4 v = *reinterpret_cast<const float4 *>(scr + (l * SCR_ROW + 2 * u) * 2);
+        xr[2 * u] = v.x; xi[2 * u] = v.y; xr[2 * u + 1] = v.z; xi[2 * u + 1] = v.w;
+    }
+    __syncwarp();
+    fft16<false>(xr, xi);
+    // Z[l + 16 k2] is in slot(k2).  Hermitian split: pair k = l + 16 r with 256 - k, which lives in
+    // lane (16 - l) & 15 at k2 = 15 - r (lane 0 pairs with itself at k2 = (16 - r) & 15).
+    const int src = ((16 - l) & 15) | (lane & 16);
+    float *pb = sm.pbuf + q;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const float zr = xr[fft16_slot(r)], zi = xi[fft16_slot(r)];
+        float pr = __shfl_sync(0xffffffffu, xr[fft16_slot(15 - r)], src);
+        float pi = __shfl_sync(0xffffffffu, xi[fft16_slot(15 - r)], src);
+        if (l == 0) { pr = xr[fft16_slot((16 - r) & 15)]; pi = xi[fft16_slot((16 - r) & 15)]; }
+        const int k = l + 16 * r;
+        const float2 w = sm.fft.tw2[k];
+        const float e2r = zr + pr, e2i = zi - pi;      // 2E = Z[k] + conj(Z[256-k])
+        const float o2r = zi + pi, o2i = pr - zr;      // 2O = -i (Z[k] - conj(Z[256-k]))
+        const float tr = w.x * o2r - w.y * o2i;
+        const float ti = w.x * o2i + w.y * o2r;
+        const float ar = e2r + tr, ai = e2i + ti;      // 2 X[k]
+        const float br = e2r - tr, bi = e2i - ti;      // 2 conj(X[256-k])
+        pb[k * PB_ROW] = ar * ar + ai * ai;
+        pb[(256 - k) * PB_ROW] = br * br + bi * bi;
+    }
+    if (l == 0) {                                       // k = 128 pairs with itself
+        const float zr = xr[fft16_slot(8)], zi = xi[fft16_slot(8)];
+        pb[128 * PB_ROW] = 4.0f * (zr * zr + zi * zi);
+    }
+}
+
+// ---- phase 2b: VAD warp, lane = frame: calculate_energy (vad.rs:157-168), strictly sequential ----
+__device__ __forceinline__ float frame_energy_smem(const float *__restrict__ ybuf, int q)
+{
+    const float4 *yp = reinterpret_cast<const float4 *>(ybuf) + 45 * q;   // ypad(160 q) / 4
+    float sum = 0.0f;
+#pragma unroll 4
+    for (int s8 = 0; s8 < 12; ++s8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 v = yp[9 * s8 + j];            // 8 float4 of data + 1 of padding per 32 samples
+            sum = __fadd_rn(sum, __fmul_rn(v.x, v.x));
+            sum = __fadd_rn(sum, __fmul_rn(v.y, v.y));
+            sum = __fadd_rn(sum, __fmul_rn(v.z, v.z));
+            sum = __fadd_rn(sum, __fmul_rn(v.w, v.w));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                       // samples 384..399
+        const float4 v = yp[9 * 12 + j];
+        sum = __fadd_rn(sum, __fmul_rn(v.x, v.x));
+        sum = __fadd_rn(sum, __fmul_rn(v.y, v.y));
+        sum = __fadd_rn(sum, __fmul_rn(v.z, v.z));
+        sum = __fadd_rn(sum, __fmul_rn(v.w, v.w));
+    }
+    return __fdiv_rn(sum, (float)WIN);
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int l = lane & 15, half = lane >> 4;
+    const uint32_t M = P.n_mels;
+
+    // constant tables -> shared memory (once per CTA)
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(P.fft);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&sm.fft);
+        for (int i = tid; i < (int)(sizeof(FftTables) / 4); i += FUSED_THREADS) dst[i] = src[i];
+        if (M) {
+            const uint32_t *ms = reinterpret_cast<const uint32_t *>(P.mel);
+            uint32_t *md = reinterpret_cast<uint32_t *>(&sm.mel);
+            for (int i = tid; i < (int)(sizeof(MelTables) / 4); i += FUSED_THREADS) md[i] = ms[i];
+        }
+    }
+    __syncthreads();
+    const uint32_t pitch = M | 1u;                      // odd row pitch of the log-mel stage
+    float *stage = sm.scr;
+
+    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        const TileDev td = P.tiles[tile];
+        if (tid < (int)(sizeof(StreamDev) / 4))
+            reinterpret_cast<uint32_t *>(&sm.stream)[tid] = reinterpret_cast<const uint32_t *>(P.streams + td.stream)[tid];
+        __syncthreads();
+        const StreamDev &s = sm.stream;
+        const uint32_t n_tile0 = td.tile * TILE_SAMPLES;
+        const uint32_t tile_end = min(n_tile0 + (uint32_t)TILE_SAMPLES, s.n_out);
+        const uint32_t f_tile0 = td.tile * TILE_FRAMES;
+        const uint32_t n_steps = (tile_end - n_tile0 + STEP_SAMPLES - 1) / STEP_SAMPLES;
+        const float inv_q = 1.0f / (float)s.q;
+        if (tid == 0 && s.mode != RS_PASSTHROUGH) {
+            long long k; uint32_t rem;
+            resample_pos(n_tile0, s.p, s.q, &k, &rem);
+            sm.tile_k = (int)k; sm.tile_rem = rem;
+            const uint32_t inc = (uint32_t)FUSED_THREADS * s.p;
+            sm.inc_k = inc / s.q; sm.inc_rem = inc % s.q;
+        }
+        __syncthreads();
+        float *pcm_row = P.pcm ? P.pcm + (uint64_t)td.stream * P.pcm_stride : nullptr;
+        float *lm_row = P.logmel ? P.logmel + (uint64_t)td.stream * P.logmel_stride : nullptr;
+        float *en_row = P.energy ? P.energy + (uint64_t)td.stream * P.energy_stride : nullptr;
+
+        for (uint32_t g = 0; g < n_steps; ++g) {
+            const uint32_t base = n_tile0 + g * STEP_SAMPLES;       // stream index of ybuf sample 0
+            const uint32_t f0 = f_tile0 + g * SF;                   // first frame of the step
+            const int n_valid = f0 < s.n_frames ? (int)min((uint32_t)SF, s.n_frames - f0) : 0;
+
+            // ---- phase 1: resample (first step of a tile also recomputes the 240-sample halo) ----
+            resample_step(sm, s, g * STEP_SAMPLES, base, g == 0 ? 0 : CARRY, inv_q);
+            __syncthreads();
+
+            // ---- phase 2: PCM write-out, FFT (warps 0..7), energies (warp 8) ----
+            if (pcm_row) {
+                const uint32_t own_end = min(base + (uint32_t)STEP_SAMPLES, tile_end);
+                for (uint32_t i4 = tid * 4; base + i4 < own_end; i4 += FUSED_THREADS * 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(sm.ybuf + ypad((int)i4));
+                    const uint32_t n = base + i4;
+                    if (n + 4 <= own_end) {
+                        *reinterpret_cast<float4 *>(pcm_row + n) = v;
+                    } else {
+                        const float e[4] = {v.x, v.y, v.z, v.w};
+                        for (uint32_t c = 0; n + c < own_end; ++c) pcm_row[n + c] = e[c];
+                    }
+                }
+            }
+            if (n_valid > 0) {
+                if (warp < FFT_WARPS) {
+                    if (M) {
+#pragma unroll 1
+                        for (int round = 0; round < 2; ++round) {
+                            const int hw = warp * 2 + half;
+                            const int q = round * 16 + hw;
+                            if (round * 16 + warp * 2 < n_valid)     // warp-uniform: skip fully invalid pairs
+                                fft_frame(sm, sm.scr + hw * SCR_FLOATS_PER_FRAME, q, l, lane);
+                        }
+                    }
+                } else if (P.do_energy && en_row) {
+                    if (lane < n_valid) en_row[f0 + lane] = frame_energy_smem(sm.ybuf, lane);
+                }
+            }
+            __syncthreads();
+
+            // ---- phase 3: carry the 240-sample overlap forward; mel + log into the stage ----
+            if (g + 1 < n_steps && tid < CARRY) sm.ybuf[ypad(tid)] = sm.ybuf[ypad(tid) + ypad(STEP_SAMPLES)];
+            if (M && n_valid > 0) {
+                const int n_items = (int)M * 8;
+                for (int item = tid; item < n_items; item += FUSED_THREADS) {
+                    const int m = item >> 3, fq = item & 7;
+                    if (fq * 4 >= n_valid) continue;
+                    const int lo = sm.mel.lo[m], cnt = sm.mel.cnt[m];
+                    const float *w = sm.mel.w + sm.mel.off[m];
+                    const float *pp = sm.pbuf + lo * PB_ROW + 4 * fq;
+                    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                    for (int j = 0; j < cnt; ++j) {
+                        const float wj = w[j];
+                        const float4 p4 = *reinterpret_cast<const float4 *>(pp + j * PB_ROW);
+                        a0 = fmaf(wj, p4.x, a0); a1 = fmaf(wj, p4.y, a1);
+                        a2 = fmaf(wj, p4.z, a2); a3 = fmaf(wj, p4.w, a3);
+                    }
+                    float *st = stage + (4 * fq) * pitch + m;
+                    st[0] = logf(fmaxf(a0, P.log_floor)) * P.log_scale;
+                    st[pitch] = logf(fmaxf(a1, P.log_floor)) * P.log_scale;
+                    st[2 * pitch] = logf(fmaxf(a2, P.log_floor)) * P.log_scale;
+                    st[3 * pitch] = logf(fmaxf(a3, P.log_floor)) * P.log_scale;
+                }
+            }
+            __syncthreads();
+
+            // ---- phase 4: coalesced copy-out of the step's [n_valid][M] log-mel block ----
+            if (M && n_valid > 0 && lm_row) {
+                float *dst = lm_row + (uint64_t)f0 * M;
+                const int total = n_valid * (int)M;
+                for (int e = tid; e < total; e += FUSED_THREADS) {
+                    const int f = e / (int)M, m = e - f * (int)M;
+                    dst[e] = stage[f * pitch + m];
+                }
+            }
+            // the barrier after the next phase 1 (or the tile prologue) orders stage/pbuf reuse
+        }
+        __syncthreads();
+    }
+}
+
+size_t fused_smem_bytes() { return sizeof(FusedSmem); }
+
+cudaError_t launch_fused(const FusedParams &P, int n_ctas, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(af_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(FusedSmem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    af_fused_kernel<<<n_ctas, FUSED_THREADS, sizeof(FusedSmem), st>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace af

@@ -1,0 +1,50 @@
+// af_launch.h -- host-callable launch wrappers implemented in the .cu files.
+#pragma once
+#include "af_common.cuh"
+
+namespace af {
+
+// one contiguous piece of a mono f32 device signal to resample (compat objects, sessions)
+struct ResampleJob {
+    const float *data;       // mono f32, data[0] is global input index data_base
+    long long data_base;
+    long long n_valid_end;   // global input indices >= this (and < data_base) read as 0
+    unsigned long long n_begin, n_end;   // global output indices [n_begin, n_end)
+    uint32_t p, q, mode;
+    const float *frac;       // RS_TABLE: indexed by global output index
+    float *out;              // out[n - n_begin]
+};
+
+struct EnergyJob {           // generic frame energies over a device signal
+    const float *y;          // row base
+    uint64_t y_stride;       // floats between streams
+    const uint32_t *n_frames;   // per stream (device) or nullptr -> n_frames_all
+    uint32_t n_frames_all;
+    uint32_t frame_len, hop;
+    float *energy; uint64_t energy_stride;
+    uint32_t n_streams;
+};
+
+struct ScanJob {             // EMA + threshold + state machine, one stream per thread
+    const float *energy; uint64_t energy_stride;
+    const uint32_t *n_frames; uint32_t n_frames_all;
+    uint8_t *states; uint64_t states_stride;      // may be nullptr
+    VadState *state_io;      // per stream: initial state in, final state out (nullptr -> fresh)
+    VadState *final_out;     // optional extra copy of the final state (af_vad_final layout)
+    VadParams prm;
+    uint32_t n_streams;
+};
+
+size_t fused_smem_bytes();
+cudaError_t launch_fused(const FusedParams &P, int n_ctas, cudaStream_t st);
+
+cudaError_t launch_to_mono(const float *in, uint64_t n_samples, uint32_t channels, float *out, uint64_t n_frames,
+                           cudaStream_t st);
+cudaError_t launch_resample_jobs(const ResampleJob *jobs_dev, uint32_t n_jobs, uint32_t max_outputs, cudaStream_t st);
+cudaError_t launch_frame_energy(const EnergyJob &job, cudaStream_t st);
+cudaError_t launch_vad_scan(const ScanJob &job, cudaStream_t st);
+cudaError_t launch_pcm16(const float *in, uint64_t n, int16_t *out, cudaStream_t st);
+cudaError_t launch_vad_segments(const uint8_t *states, uint64_t stride, const uint32_t *n_frames, uint32_t n_streams,
+                                uint32_t *seg, uint32_t seg_cap, uint32_t *n_seg, cudaStream_t st);
+
+}  // namespace af

@@ -1,0 +1,1044 @@
+// af_runtime.cu -- the C ABI of libaudioflow_gpu.so (include/audioflow_gpu.h): library context,
+// compat objects mirroring the reference's Rust types, and the batched pipeline host runtime.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/audioflow_gpu.h"
+#include "af_launch.h"
+#include "af_plan.h"
+
+using namespace af;
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define AF_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) return fail(AF_ERR_CUDA, "CUDA error %s at %s:%d: %s", #expr, __FILE__, __LINE__, \
+                                           cudaGetErrorString(_e));                                \
+    } while (0)
+
+struct DevBuf {                       // grow-only device buffer
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct FracTable {                    // device copy of the f32 fractional offsets of one rate pair
+    float *d = nullptr;
+    size_t n = 0;
+    ~FracTable() { if (d) cudaFree(d); }
+};
+
+struct RatePlan {                     // batch-path plan of one (in, out) pair, grown on demand
+    RsRecurrence rec;                 // state after cum.size() - 1 chunks
+    std::vector<uint64_t> cum{0};     // cum[c] = outputs after c chunks (table mode)
+    std::vector<float> frac;          // host copy (table mode)
+    std::shared_ptr<FracTable> dev;   // device copy covering frac.size() entries
+};
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    FftTables *d_fft = nullptr;
+    std::mutex mu;                    // guards the scratch buffers and the plan cache
+    DevBuf scratch_in, scratch_out, scratch_aux, scratch_jobs;
+    std::map<uint64_t, RatePlan> plans;
+    std::string variant = "auto";
+};
+Context g_ctx;
+
+int require_ctx()
+{
+    if (!g_ctx.ready) {
+        int rc = af_init(-1);
+        if (rc != AF_OK) return rc;
+    }
+    return AF_OK;
+}
+
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// exact output length of BatchResampler::process(all) + flush() and (optionally) the frac table
+int plan_rate(uint32_t in_rate, uint32_t out_rate, uint64_t n_in, uint64_t *n_out, uint32_t *mode, uint32_t *p,
+              uint32_t *q, std::shared_ptr<FracTable> *table)
+{
+    if (in_rate == 0 || out_rate == 0) return fail(AF_ERR_INVALID, "sample rate must be positive");
+    RsRecurrence probe;
+    probe.init(in_rate, out_rate);
+    *mode = probe.mode(); *p = probe.p; *q = probe.q;
+    if (probe.passthrough) { *n_out = n_in; return AF_OK; }
+    if (probe.end_idx <= 0)
+        return fail(AF_ERR_RESAMPLING_FAILED, "unsupported resampling ratio %u -> %u (step %.3f exceeds the 128-frame chunk)",
+                    in_rate, out_rate, probe.t);
+    const uint64_t chunks = (n_in + RS_CHUNK - 1) / RS_CHUNK;
+    if (probe.exact) { *n_out = rs_exact_count(probe, chunks); return AF_OK; }
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    RatePlan &pl = g_ctx.plans[((uint64_t)in_rate << 32) | out_rate];
+    if (pl.rec.in_rate == 0) pl.rec.init(in_rate, out_rate);
+    bool grew = false;
+    while (pl.cum.size() - 1 < chunks) {
+        pl.rec.step(&pl.frac);
+        pl.cum.push_back(pl.rec.n_out);
+        grew = true;
+    }
+    *n_out = pl.cum[chunks];
+    if (table) {
+        if (grew || !pl.dev || pl.dev->n < pl.frac.size()) {
+            auto t = std::make_shared<FracTable>();
+            t->n = pl.frac.size();
+            if (t->n) {
+                AF_CUDA(cudaMalloc(&t->d, t->n * sizeof(float)));
+                AF_CUDA(cudaMemcpy(t->d, pl.frac.data(), t->n * sizeof(float), cudaMemcpyHostToDevice));
+            }
+            pl.dev = t;
+        }
+        *table = pl.dev;
+    }
+    return AF_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// library
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+AF_API const char *af_version(void) { return "audioflow-b200 0.1.0 (sm_100a)"; }
+
+AF_API size_t af_last_error(char *buf, size_t cap)
+{
+    if (buf && cap) {
+        size_t n = g_err.size() < cap - 1 ? g_err.size() : cap - 1;
+        memcpy(buf, g_err.data(), n);
+        buf[n] = 0;
+    }
+    return g_err.size();
+}
+
+AF_API int af_device_count(int *count)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    if (count) *count = n;
+    return AF_OK;
+}
+
+AF_API uint64_t af_kernel_launch_count(void) { return g_launches.load(); }
+
+AF_API int af_init(int device)
+{
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        return fail(AF_ERR_NO_DEVICE, "no CUDA device available (%s); libaudioflow_gpu has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0) {
+        if (g_ctx.ready) return AF_OK;
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
+        device = cur;
+    }
+    if (device >= n) return fail(AF_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+    if (g_ctx.ready && g_ctx.device == device) return AF_OK;
+    if (g_ctx.ready) return fail(AF_ERR_INVALID, "already initialised on device %d", g_ctx.device);
+    AF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    AF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(AF_ERR_NO_DEVICE, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU", device, prop.name,
+                    prop.major, prop.minor);
+    g_ctx.sm_count = prop.multiProcessorCount;
+    AF_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    FftTables *h = new FftTables;
+    build_fft_tables(h);
+    cudaError_t ce = cudaMalloc(&g_ctx.d_fft, sizeof(FftTables));
+    if (ce == cudaSuccess) ce = cudaMemcpy(g_ctx.d_fft, h, sizeof(FftTables), cudaMemcpyHostToDevice);
+    delete h;
+    AF_CUDA(ce);
+    g_ctx.device = device;
+    g_ctx.ready = true;
+    return AF_OK;
+}
+
+AF_API int af_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (!g_ctx.ready) return AF_OK;
+    cudaDeviceSynchronize();
+    g_ctx.plans.clear();
+    g_ctx.scratch_in.release(); g_ctx.scratch_out.release(); g_ctx.scratch_aux.release(); g_ctx.scratch_jobs.release();
+    if (g_ctx.d_fft) cudaFree(g_ctx.d_fft);
+    g_ctx.d_fft = nullptr;
+    if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+    g_ctx.stream = nullptr;
+    g_ctx.ready = false;
+    g_ctx.device = -1;
+    return AF_OK;
+}
+
+AF_API int af_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return fail(AF_ERR_INVALID, "null pointer");
+    int rc = require_ctx();
+    if (rc) return rc;
+    AF_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return AF_OK;
+}
+
+AF_API int af_host_free(void *ptr)
+{
+    if (ptr) AF_CUDA(cudaFreeHost(ptr));
+    return AF_OK;
+}
+
+AF_API int af_set_kernel_variant(const char *name)
+{
+    if (!name) return fail(AF_ERR_INVALID, "null variant name");
+    std::string v(name);
+    if (v != "auto" && v != "sync" && v != "tma") return fail(AF_ERR_INVALID, "unknown kernel variant '%s'", name);
+    g_ctx.variant = v;
+    return AF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// AudioFrame::to_mono (capture.rs:30-42)
+// ------------------------------------------------------------------------------------------
+AF_API int af_to_mono(const float *samples, size_t n_samples, uint16_t channels, float *out, size_t out_cap,
+                      size_t *n_out)
+{
+    if (channels == 0) return fail(AF_ERR_INVALID, "channels must be >= 1");
+    if ((!samples || !out) && n_samples) return fail(AF_ERR_INVALID, "null buffer");
+    int rc = require_ctx();
+    if (rc) return rc;
+    const size_t frames = (n_samples + channels - 1) / channels;
+    if (out_cap < frames) return fail(AF_ERR_CAPACITY, "output capacity %zu < %zu frames", out_cap, frames);
+    if (n_out) *n_out = frames;
+    if (frames == 0) return AF_OK;
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    AF_CUDA(g_ctx.scratch_in.reserve(n_samples * sizeof(float)));
+    AF_CUDA(g_ctx.scratch_out.reserve(frames * sizeof(float)));
+    cudaStream_t st = g_ctx.stream;
+    AF_CUDA(cudaMemcpyAsync(g_ctx.scratch_in.p, samples, n_samples * sizeof(float), cudaMemcpyHostToDevice, st));
+    AF_CUDA(launch_to_mono((const float *)g_ctx.scratch_in.p, n_samples, channels, (float *)g_ctx.scratch_out.p, frames, st));
+    count_launch();
+    AF_CUDA(cudaMemcpyAsync(out, g_ctx.scratch_out.p, frames * sizeof(float), cudaMemcpyDeviceToHost, st));
+    AF_CUDA(cudaStreamSynchronize(st));
+    return AF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// AudioResampler / BatchResampler (resampler.rs)
+// ------------------------------------------------------------------------------------------
+struct af_resampler {
+    RsRecurrence rec;
+    float hist[2 * RS_POLY];          // the last 16 input frames (rubato's buffer head)
+    std::vector<float> frac;          // scratch
+    std::vector<float> stage;         // scratch: hist + chunks
+};
+
+static int resampler_run_chunks(af_resampler *r, const float *input, size_t n_chunks, float *out, size_t out_cap,
+                                size_t *n_out)
+{
+    // runs n_chunks complete 128-frame chunks through the GPU; input has n_chunks * 128 frames
+    const uint64_t c0 = r->rec.chunks;
+    const uint64_t n_begin = r->rec.n_out;
+    RsRecurrence saved = r->rec;
+    r->frac.clear();
+    for (size_t c = 0; c < n_chunks; ++c) r->rec.step(r->rec.exact ? nullptr : &r->frac);
+    const uint64_t n_end = r->rec.n_out;
+    const size_t produced = (size_t)(n_end - n_begin);
+    if (produced > out_cap) {
+        r->rec = saved;
+        return fail(AF_ERR_CAPACITY, "output capacity %zu < %zu produced frames", out_cap, produced);
+    }
+    const size_t n_in = n_chunks * RS_CHUNK;
+    r->stage.resize(2 * RS_POLY + n_in);
+    memcpy(r->stage.data(), r->hist, sizeof(r->hist));
+    memcpy(r->stage.data() + 2 * RS_POLY, input, n_in * sizeof(float));
+
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    cudaStream_t st = g_ctx.stream;
+    const size_t in_bytes = r->stage.size() * sizeof(float);
+    const size_t frac_bytes = r->frac.size() * sizeof(float);
+    AF_CUDA(g_ctx.scratch_in.reserve(in_bytes));
+    AF_CUDA(g_ctx.scratch_aux.reserve(frac_bytes + 16));
+    AF_CUDA(g_ctx.scratch_out.reserve(produced * sizeof(float) + 16));
+    AF_CUDA(g_ctx.scratch_jobs.reserve(sizeof(ResampleJob)));
+    AF_CUDA(cudaMemcpyAsync(g_ctx.scratch_in.p, r->stage.data(), in_bytes, cudaMemcpyHostToDevice, st));
+    if (frac_bytes) AF_CUDA(cudaMemcpyAsync(g_ctx.scratch_aux.p, r->frac.data(), frac_bytes, cudaMemcpyHostToDevice, st));
+    ResampleJob job;
+    job.data = (const float *)g_ctx.scratch_in.p;
+    job.data_base = (long long)(c0 * RS_CHUNK) - 2 * RS_POLY;
+    job.n_valid_end = (long long)((c0 + n_chunks) * RS_CHUNK);
+    job.n_begin = n_begin; job.n_end = n_end;
+    job.p = r->rec.p; job.q = r->rec.q; job.mode = r->rec.mode();
+    job.frac = (const float *)g_ctx.scratch_aux.p - n_begin;      // indexed by the global output index
+    job.out = (float *)g_ctx.scratch_out.p;
+    AF_CUDA(cudaMemcpyAsync(g_ctx.scratch_jobs.p, &job, sizeof(job), cudaMemcpyHostToDevice, st));
+    if (produced) {
+        AF_CUDA(launch_resample_jobs((const ResampleJob *)g_ctx.scratch_jobs.p, 1, (uint32_t)produced, st));
+        count_launch();
+        AF_CUDA(cudaMemcpyAsync(out, g_ctx.scratch_out.p, produced * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    AF_CUDA(cudaStreamSynchronize(st));
+    memcpy(r->hist, r->stage.data() + r->stage.size() - 2 * RS_POLY, sizeof(r->hist));
+    *n_out = produced;
+    return AF_OK;
+}
+
+AF_API int af_resampler_create(uint32_t input_rate, uint32_t output_rate, af_resampler **out)
+{
+    if (!out) return fail(AF_ERR_INVALID, "null out pointer");
+    if (input_rate == 0 || output_rate == 0) return fail(AF_ERR_RESAMPLING_FAILED, "sample rates must be positive");
+    int rc = require_ctx();
+    if (rc) return rc;
+    af_resampler *r = new af_resampler;
+    r->rec.init(input_rate, output_rate);
+    memset(r->hist, 0, sizeof(r->hist));
+    if (!r->rec.passthrough && r->rec.end_idx <= 0) {
+        delete r;
+        return fail(AF_ERR_RESAMPLING_FAILED, "unsupported resampling ratio %u -> %u", input_rate, output_rate);
+    }
+    *out = r;
+    return AF_OK;
+}
+
+AF_API void af_resampler_destroy(af_resampler *r) { delete r; }
+AF_API uint32_t af_resampler_input_rate(const af_resampler *r) { return r ? r->rec.in_rate : 0; }
+AF_API uint32_t af_resampler_output_rate(const af_resampler *r) { return r ? r->rec.out_rate : 0; }
+AF_API int af_resampler_needs_resampling(const af_resampler *r) { return r && r->rec.in_rate != r->rec.out_rate; }
+AF_API size_t af_resampler_chunk_size(const af_resampler *r) { return (r && !r->rec.passthrough) ? RS_CHUNK : 0; }
+
+AF_API int af_resampler_process(af_resampler *r, const float *input, size_t n, float *out, size_t out_cap, size_t *n_out)
+{
+    if (!r || !n_out || ((!input || !out) && n)) return fail(AF_ERR_INVALID, "null argument");
+    if (r->rec.passthrough) {                         // resampler.rs:72-75: Ok(input.to_vec())
+        if (out_cap < n) return fail(AF_ERR_CAPACITY, "output capacity %zu < %zu", out_cap, n);
+        memcpy(out, input, n * sizeof(float));
+        *n_out = n;
+        return AF_OK;
+    }
+    if (n < RS_CHUNK)                                 // rubato ResampleError::InsufficientInputBufferSize
+        return fail(AF_ERR_RESAMPLING_FAILED, "Insufficient buffer size %zu for input channel 0, expected %d", n, RS_CHUNK);
+    return resampler_run_chunks(r, input, 1, out, out_cap, n_out);
+}
+
+AF_API size_t af_resample_max_output(uint32_t input_rate, uint32_t output_rate, size_t n_in)
+{
+    if (input_rate == output_rate || input_rate == 0) return n_in;
+    const size_t chunks = (n_in + RS_CHUNK - 1) / RS_CHUNK;
+    const double per = (double)RS_CHUNK * (double)output_rate / (double)input_rate;
+    return (size_t)((double)chunks * per) + chunks + 64;
+}
+
+AF_API int af_resample_output_len(uint32_t input_rate, uint32_t output_rate, size_t n_in, size_t *n_out)
+{
+    if (!n_out) return fail(AF_ERR_INVALID, "null out pointer");
+    uint64_t n = 0; uint32_t mode, p, q;
+    int rc = plan_rate(input_rate, output_rate, n_in, &n, &mode, &p, &q, nullptr);
+    if (rc) return rc;
+    *n_out = (size_t)n;
+    return AF_OK;
+}
+
+struct af_batch_resampler {
+    af_resampler rs;
+    std::vector<float> buffer;        // BatchResampler::buffer (resampler.rs:118): always < 128 frames after process
+};
+
+AF_API int af_batch_resampler_create(uint32_t input_rate, uint32_t output_rate, af_batch_resampler **out)
+{
+    if (!out) return fail(AF_ERR_INVALID, "null out pointer");
+    af_resampler *r = nullptr;
+    int rc = af_resampler_create(input_rate, output_rate, &r);
+    if (rc) return rc;
+    af_batch_resampler *b = new af_batch_resampler;
+    b->rs = *r;
+    delete r;
+    *out = b;
+    return AF_OK;
+}
+AF_API void af_batch_resampler_destroy(af_batch_resampler *b) { delete b; }
+
+AF_API int af_batch_resampler_process(af_batch_resampler *b, const float *input, size_t n, float *out, size_t out_cap,
+                                      size_t *n_out)
+{
+    if (!b || !n_out || ((!input || !out) && n)) return fail(AF_ERR_INVALID, "null argument");
+    *n_out = 0;
+    if (b->rs.rec.passthrough) {                      // documented deviation: the reference never returns here
+        if (out_cap < n) return fail(AF_ERR_CAPACITY, "output capacity %zu < %zu", out_cap, n);
+        memcpy(out, input, n * sizeof(float));
+        *n_out = n;
+        return AF_OK;
+    }
+    b->buffer.insert(b->buffer.end(), input, input + n);
+    const size_t chunks = b->buffer.size() / RS_CHUNK;
+    if (chunks == 0) return AF_OK;
+    int rc = resampler_run_chunks(&b->rs, b->buffer.data(), chunks, out, out_cap, n_out);
+    if (rc) { b->buffer.resize(b->buffer.size() - n); return rc; }
+    b->buffer.erase(b->buffer.begin(), b->buffer.begin() + chunks * RS_CHUNK);
+    return AF_OK;
+}
+
+AF_API int af_batch_resampler_flush(af_batch_resampler *b, float *out, size_t out_cap, size_t *n_out)
+{
+    if (!b || !n_out) return fail(AF_ERR_INVALID, "null argument");
+    *n_out = 0;
+    if (b->buffer.empty()) return AF_OK;
+    if (b->rs.rec.passthrough) { b->buffer.clear(); return AF_OK; }
+    std::vector<float> chunk(RS_CHUNK, 0.0f);         // resampler.rs:156-157: resize(chunk_size, 0.0)
+    memcpy(chunk.data(), b->buffer.data(), b->buffer.size() * sizeof(float));
+    int rc = resampler_run_chunks(&b->rs, chunk.data(), 1, out, out_cap, n_out);
+    if (rc) return rc;
+    b->buffer.clear();
+    return AF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// VoiceActivityDetector (vad.rs)
+// ------------------------------------------------------------------------------------------
+struct af_vad {
+    af_vad_config cfg;
+    VadParams prm;
+    VadState host;                    // mirror of the device state after the last call
+    VadState *dev = nullptr;
+};
+
+static VadParams make_vad_params(const af_vad_config &c)
+{
+    VadParams p;
+    p.alpha = c.smoothing_factor;
+    p.e_min = vad_energy_threshold(c.threshold_db);
+    p.silence_timeout = c.silence_timeout_frames;
+    p.min_speech = c.min_speech_frames;
+    return p;
+}
+
+AF_API void af_vad_config_default(af_vad_config *cfg)
+{
+    if (!cfg) return;
+    cfg->threshold_db = -50.0f;
+    cfg->smoothing_factor = 0.3f;
+    cfg->silence_timeout_frames = 15;
+    cfg->min_speech_frames = 3;
+}
+
+AF_API int af_vad_create(const af_vad_config *cfg, af_vad **out)
+{
+    if (!out) return fail(AF_ERR_INVALID, "null out pointer");
+    int rc = require_ctx();
+    if (rc) return rc;
+    af_vad *v = new af_vad;
+    if (cfg) v->cfg = *cfg; else af_vad_config_default(&v->cfg);
+    v->prm = make_vad_params(v->cfg);
+    memset(&v->host, 0, sizeof(v->host));
+    cudaError_t e = cudaMalloc(&v->dev, sizeof(VadState));
+    if (e == cudaSuccess) e = cudaMemset(v->dev, 0, sizeof(VadState));
+    if (e != cudaSuccess) { delete v; AF_CUDA(e); }
+    *out = v;
+    return AF_OK;
+}
+
+AF_API void af_vad_destroy(af_vad *v)
+{
+    if (!v) return;
+    if (v->dev) cudaFree(v->dev);
+    delete v;
+}
+
+AF_API int af_vad_detect_frames(af_vad *v, const float *samples, size_t n, uint32_t frame_len, uint32_t hop,
+                                uint8_t *states, size_t states_cap, size_t *n_frames)
+{
+    if (!v || (!samples && n)) return fail(AF_ERR_INVALID, "null argument");
+    if (hop == 0) return fail(AF_ERR_INVALID, "hop must be positive");
+    size_t T = n >= frame_len ? 1 + (n - frame_len) / hop : 0;
+    if (frame_len == 0) T = 0;
+    if (n_frames) *n_frames = T;
+    if (T == 0) return AF_OK;
+    if (states && states_cap < T) return fail(AF_ERR_CAPACITY, "states capacity %zu < %zu frames", states_cap, T);
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    cudaStream_t st = g_ctx.stream;
+    AF_CUDA(g_ctx.scratch_in.reserve(n * sizeof(float)));
+    AF_CUDA(g_ctx.scratch_aux.reserve(T * sizeof(float)));
+    AF_CUDA(g_ctx.scratch_out.reserve(T));
+    AF_CUDA(cudaMemcpyAsync(g_ctx.scratch_in.p, samples, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    EnergyJob ej{};
+    ej.y = (const float *)g_ctx.scratch_in.p; ej.y_stride = 0; ej.n_frames = nullptr; ej.n_frames_all = (uint32_t)T;
+    ej.frame_len = frame_len; ej.hop = hop; ej.energy = (float *)g_ctx.scratch_aux.p; ej.energy_stride = 0; ej.n_streams = 1;
+    AF_CUDA(launch_frame_energy(ej, st));
+    ScanJob sj{};
+    sj.energy = (const float *)g_ctx.scratch_aux.p; sj.energy_stride = 0; sj.n_frames = nullptr; sj.n_frames_all = (uint32_t)T;
+    sj.states = (uint8_t *)g_ctx.scratch_out.p; sj.states_stride = 0; sj.state_io = v->dev; sj.final_out = nullptr;
+    sj.prm = v->prm; sj.n_streams = 1;
+    AF_CUDA(launch_vad_scan(sj, st));
+    count_launch(2);
+    if (states) AF_CUDA(cudaMemcpyAsync(states, g_ctx.scratch_out.p, T, cudaMemcpyDeviceToHost, st));
+    AF_CUDA(cudaMemcpyAsync(&v->host, v->dev, sizeof(VadState), cudaMemcpyDeviceToHost, st));
+    AF_CUDA(cudaStreamSynchronize(st));
+    return AF_OK;
+}
+
+AF_API int af_vad_detect(af_vad *v, const float *frame, size_t n, uint8_t *state)
+{
+    if (!v) return fail(AF_ERR_INVALID, "null detector");
+    if (n == 0) {
+        // calculate_energy returns 0.0 for an empty frame (vad.rs:158-160) and the state machine still steps:
+        // feed one zero sample, whose mean square is exactly 0.0 as well
+        const float zero = 0.0f;
+        uint8_t s = 0;
+        int rc = af_vad_detect_frames(v, &zero, 1, 1, 1, &s, 1, nullptr);
+        if (state) *state = s;
+        return rc;
+    }
+    if (n > 0xffffffffull) return fail(AF_ERR_INVALID, "frame too long");
+    uint8_t s = 0;
+    int rc = af_vad_detect_frames(v, frame, n, (uint32_t)n, (uint32_t)n, &s, 1, nullptr);
+    if (state) *state = s;
+    return rc;
+}
+
+AF_API int af_vad_reset(af_vad *v)
+{
+    if (!v) return fail(AF_ERR_INVALID, "null detector");
+    memset(&v->host, 0, sizeof(v->host));
+    AF_CUDA(cudaMemset(v->dev, 0, sizeof(VadState)));
+    return AF_OK;
+}
+AF_API int af_vad_state(const af_vad *v) { return v ? v->host.state : 0; }
+AF_API float af_vad_energy_db(const af_vad *v)
+{
+    // energy_to_dbfs(smoothed_energy) (vad.rs:171-176,192-194); host libm, same as the threshold derivation
+    if (!v || !(v->host.smoothed > 0.0f)) return -INFINITY;
+    return 20.0f * log10f(v->host.smoothed);
+}
+AF_API int af_vad_is_speaking(const af_vad *v) { return v && v->host.state == AF_VAD_SPEECH; }
+AF_API uint64_t af_vad_speech_frame_count(const af_vad *v) { return v ? v->host.speech_frames : 0; }
+AF_API float af_vad_smoothed_energy(const af_vad *v) { return v ? v->host.smoothed : 0.0f; }
+
+AF_API int af_vad_frame_energy(const float *frame, size_t n, float *energy)
+{
+    if (!energy || (!frame && n)) return fail(AF_ERR_INVALID, "null argument");
+    int rc = require_ctx();
+    if (rc) return rc;
+    if (n == 0) { *energy = 0.0f; return AF_OK; }
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    cudaStream_t st = g_ctx.stream;
+    AF_CUDA(g_ctx.scratch_in.reserve(n * sizeof(float)));
+    AF_CUDA(g_ctx.scratch_aux.reserve(sizeof(float)));
+    AF_CUDA(cudaMemcpyAsync(g_ctx.scratch_in.p, frame, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    EnergyJob ej{};
+    ej.y = (const float *)g_ctx.scratch_in.p; ej.n_frames_all = 1; ej.frame_len = (uint32_t)n; ej.hop = (uint32_t)n;
+    ej.energy = (float *)g_ctx.scratch_aux.p; ej.n_streams = 1;
+    AF_CUDA(launch_frame_energy(ej, st));
+    count_launch();
+    AF_CUDA(cudaMemcpyAsync(energy, g_ctx.scratch_aux.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+    AF_CUDA(cudaStreamSynchronize(st));
+    return AF_OK;
+}
+
+AF_API int af_pcm16_encode(const float *samples, size_t n, int16_t *out)
+{
+    if ((!samples || !out) && n) return fail(AF_ERR_INVALID, "null buffer");
+    int rc = require_ctx();
+    if (rc) return rc;
+    if (n == 0) return AF_OK;
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    cudaStream_t st = g_ctx.stream;
+    AF_CUDA(g_ctx.scratch_in.reserve(n * sizeof(float)));
+    AF_CUDA(g_ctx.scratch_out.reserve(n * sizeof(int16_t)));
+    AF_CUDA(cudaMemcpyAsync(g_ctx.scratch_in.p, samples, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    AF_CUDA(launch_pcm16((const float *)g_ctx.scratch_in.p, n, (int16_t *)g_ctx.scratch_out.p, st));
+    count_launch();
+    AF_CUDA(cudaMemcpyAsync(out, g_ctx.scratch_out.p, n * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    AF_CUDA(cudaStreamSynchronize(st));
+    return AF_OK;
+}
+
+AF_API int af_vad_segments(const uint8_t *states, uint64_t vad_stride, const uint32_t *n_frames, size_t n_streams,
+                           uint32_t *seg, uint32_t seg_cap, uint32_t *n_seg, void *cuda_stream)
+{
+    if (!states || !n_frames || !seg || !n_seg) return fail(AF_ERR_INVALID, "null argument");
+    int rc = require_ctx();
+    if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_ctx.stream;
+    AF_CUDA(launch_vad_segments(states, vad_stride, n_frames, (uint32_t)n_streams, seg, seg_cap, n_seg, st));
+    count_launch();
+    if (!cuda_stream) AF_CUDA(cudaStreamSynchronize(st));
+    return AF_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// batched pipeline
+// ------------------------------------------------------------------------------------------
+struct af_pipeline {
+    af_pipeline_config cfg;
+    VadParams vad_prm;
+    MelTables *d_mel = nullptr;
+};
+
+namespace {
+
+struct HostStream {                   // planned stream (host side)
+    af_stream_desc desc;
+    uint32_t n_in, n_out, n_frames, n_vad_frames, mode, p, q;
+    std::shared_ptr<FracTable> table;
+};
+
+struct SubBatch {                     // a group of streams resident on the device together
+    size_t first = 0, count = 0;      // range in af_batch::streams
+    std::vector<StreamDev> h_streams;
+    std::vector<TileDev> h_tiles;
+    StreamDev *d_streams = nullptr;
+    TileDev *d_tiles = nullptr;
+    uint32_t *d_nframes = nullptr, *d_nvad = nullptr;
+    std::vector<size_t> in_off;       // host mode: byte offset of each stream inside the slot input buffer
+    size_t in_bytes = 0;
+};
+
+}  // namespace
+
+struct af_batch {
+    af_pipeline *pipe = nullptr;
+    int mem = AF_MEM_DEVICE;
+    std::vector<HostStream> streams;
+    std::vector<SubBatch> subs;
+    uint64_t max_out = 0, max_frames = 0, max_vad = 0;
+    uint64_t pcm_stride = 0, logmel_stride = 0, vad_stride = 0;
+    // device scratch for outputs the caller did not ask for but the pipeline needs
+    float *d_energy = nullptr; uint64_t energy_stride = 0; size_t energy_rows = 0;
+    float *d_pcm_scratch = nullptr; size_t pcm_scratch_rows = 0;
+    // host mode slots
+    struct Slot {
+        void *d_in = nullptr; float *d_pcm = nullptr; float *d_logmel = nullptr; uint8_t *d_vad = nullptr;
+        float *d_energy = nullptr; VadState *d_final = nullptr;
+        cudaStream_t st = nullptr;
+    };
+    std::vector<Slot> slots;
+    size_t slot_rows = 0;
+};
+
+namespace {
+
+int build_sub(af_batch *b, SubBatch &sb, const void *slot_in_base)
+{
+    // (re)build the device tables of a sub-batch; slot_in_base != null (host mode) rebases the inputs
+    sb.h_streams.resize(sb.count);
+    sb.h_tiles.clear();
+    std::vector<uint32_t> nf(sb.count), nv(sb.count);
+    for (size_t i = 0; i < sb.count; ++i) {
+        const HostStream &hs = b->streams[sb.first + i];
+        StreamDev &d = sb.h_streams[i];
+        memset(&d, 0, sizeof(d));
+        d.data = slot_in_base ? (const void *)((const char *)slot_in_base + sb.in_off[i]) : hs.desc.data;
+        d.n_samples = hs.desc.n_samples;
+        d.n_in = hs.n_in; d.n_out = hs.n_out; d.n_frames = hs.n_frames; d.n_vad_frames = hs.n_vad_frames;
+        d.channels = hs.desc.channels; d.format = hs.desc.format;
+        d.p = hs.p; d.q = hs.q; d.mode = hs.mode;
+        d.frac = hs.table ? hs.table->d : nullptr;
+        d.tile_begin = (uint32_t)sb.h_tiles.size();
+        d.n_tiles = (hs.n_out + TILE_SAMPLES - 1) / TILE_SAMPLES;
+        for (uint32_t t = 0; t < d.n_tiles; ++t) sb.h_tiles.push_back(TileDev{(uint32_t)i, t});
+        nf[i] = hs.n_frames; nv[i] = hs.n_vad_frames;
+    }
+    if (!sb.d_streams) {
+        AF_CUDA(cudaMalloc(&sb.d_streams, sb.count * sizeof(StreamDev)));
+        AF_CUDA(cudaMalloc(&sb.d_tiles, (sb.h_tiles.size() + 1) * sizeof(TileDev)));
+        AF_CUDA(cudaMalloc(&sb.d_nframes, sb.count * sizeof(uint32_t)));
+        AF_CUDA(cudaMalloc(&sb.d_nvad, sb.count * sizeof(uint32_t)));
+    }
+    AF_CUDA(cudaMemcpy(sb.d_streams, sb.h_streams.data(), sb.count * sizeof(StreamDev), cudaMemcpyHostToDevice));
+    if (!sb.h_tiles.empty())
+        AF_CUDA(cudaMemcpy(sb.d_tiles, sb.h_tiles.data(), sb.h_tiles.size() * sizeof(TileDev), cudaMemcpyHostToDevice));
+    AF_CUDA(cudaMemcpy(sb.d_nframes, nf.data(), sb.count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    AF_CUDA(cudaMemcpy(sb.d_nvad, nv.data(), sb.count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return AF_OK;
+}
+
+// enqueue the kernels of one sub-batch on `st`; all pointers are device pointers of rows [0, sb.count)
+int run_sub(af_batch *b, SubBatch &sb, float *pcm, uint64_t pcm_stride, float *logmel, uint64_t logmel_stride,
+            uint8_t *vad, uint64_t vad_stride, float *energy, uint64_t energy_stride, VadState *vad_final,
+            cudaStream_t st)
+{
+    const af_pipeline_config &cfg = b->pipe->cfg;
+    const bool stft_vad = cfg.vad_enable && cfg.vad_frame_len == 0;
+    const bool custom_vad = cfg.vad_enable && cfg.vad_frame_len != 0;
+    if (!sb.h_tiles.empty()) {
+        FusedParams P{};
+        P.streams = sb.d_streams; P.tiles = sb.d_tiles; P.n_tiles = (uint32_t)sb.h_tiles.size();
+        P.fft = g_ctx.d_fft; P.mel = b->pipe->d_mel;
+        P.pcm = pcm; P.pcm_stride = pcm_stride;
+        P.logmel = cfg.n_mels ? logmel : nullptr; P.logmel_stride = logmel_stride;
+        P.energy = stft_vad ? energy : nullptr; P.energy_stride = energy_stride;
+        P.n_mels = (cfg.n_mels && logmel) ? cfg.n_mels : 0;
+        P.do_energy = stft_vad ? 1 : 0;
+        P.log_floor = cfg.log_floor;
+        P.log_scale = cfg.log10 ? 0.43429448190325176f : 1.0f;
+        const int n_ctas = (int)std::min<size_t>(sb.h_tiles.size(), (size_t)g_ctx.sm_count * 2);
+        AF_CUDA(launch_fused(P, n_ctas, st));
+        count_launch();
+    }
+    if (custom_vad) {
+        EnergyJob ej{};
+        ej.y = pcm; ej.y_stride = pcm_stride; ej.n_frames = sb.d_nvad; ej.n_frames_all = (uint32_t)b->max_vad;
+        ej.frame_len = cfg.vad_frame_len; ej.hop = cfg.vad_hop; ej.energy = energy; ej.energy_stride = energy_stride;
+        ej.n_streams = (uint32_t)sb.count;
+        AF_CUDA(launch_frame_energy(ej, st));
+        count_launch();
+    }
+    if (cfg.vad_enable) {
+        ScanJob sj{};
+        sj.energy = energy; sj.energy_stride = energy_stride; sj.n_frames = sb.d_nvad; sj.n_frames_all = 0;
+        sj.states = vad; sj.states_stride = vad_stride; sj.state_io = nullptr; sj.final_out = vad_final;
+        sj.prm = b->pipe->vad_prm; sj.n_streams = (uint32_t)sb.count;
+        AF_CUDA(launch_vad_scan(sj, st));
+        count_launch();
+    }
+    return AF_OK;
+}
+
+uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+extern "C" {
+
+AF_API void af_pipeline_config_default(af_pipeline_config *cfg)
+{
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->n_mels = 80;
+    cfg->f_min = 0.0f; cfg->f_max = 8000.0f;
+    cfg->log_floor = 1e-10f;
+    cfg->log10 = 0;
+    cfg->vad_enable = 1;
+    af_vad_config_default(&cfg->vad);
+    cfg->vad_frame_len = 0; cfg->vad_hop = 0;
+    cfg->write_pcm = 1;
+}
+
+AF_API int af_pipeline_create(const af_pipeline_config *cfg, af_pipeline **out)
+{
+    if (!out) return fail(AF_ERR_INVALID, "null out pointer");
+    int rc = require_ctx();
+    if (rc) return rc;
+    af_pipeline_config c;
+    if (cfg) c = *cfg; else af_pipeline_config_default(&c);
+    if (c.n_mels > MAX_MELS) return fail(AF_ERR_INVALID, "n_mels %u > %d", c.n_mels, MAX_MELS);
+    if (c.vad_enable && c.vad_frame_len != 0 && c.vad_hop == 0) return fail(AF_ERR_INVALID, "vad_hop must be positive");
+    if (c.n_mels && !(c.f_max > c.f_min && c.f_min >= 0.0f)) return fail(AF_ERR_INVALID, "bad mel band [%g, %g]", c.f_min, c.f_max);
+    af_pipeline *p = new af_pipeline;
+    p->cfg = c;
+    p->vad_prm = make_vad_params(c.vad);
+    if (c.n_mels) {
+        MelTables *h = new MelTables;
+        if (!build_mel_tables(c.n_mels, c.f_min, c.f_max, h)) { delete h; delete p; return fail(AF_ERR_INVALID, "mel table construction failed"); }
+        cudaError_t e = cudaMalloc(&p->d_mel, sizeof(MelTables));
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_mel, h, sizeof(MelTables), cudaMemcpyHostToDevice);
+        delete h;
+        if (e != cudaSuccess) { delete p; AF_CUDA(e); }
+    }
+    *out = p;
+    return AF_OK;
+}
+
+AF_API void af_pipeline_destroy(af_pipeline *p)
+{
+    if (!p) return;
+    if (p->d_mel) cudaFree(p->d_mel);
+    delete p;
+}
+
+AF_API void af_batch_destroy(af_batch *b)
+{
+    if (!b) return;
+    cudaDeviceSynchronize();
+    for (auto &sb : b->subs) {
+        if (sb.d_streams) cudaFree(sb.d_streams);
+        if (sb.d_tiles) cudaFree(sb.d_tiles);
+        if (sb.d_nframes) cudaFree(sb.d_nframes);
+        if (sb.d_nvad) cudaFree(sb.d_nvad);
+    }
+    if (b->d_energy) cudaFree(b->d_energy);
+    if (b->d_pcm_scratch) cudaFree(b->d_pcm_scratch);
+    for (auto &s : b->slots) {
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_pcm) cudaFree(s.d_pcm);
+        if (s.d_logmel) cudaFree(s.d_logmel);
+        if (s.d_vad) cudaFree(s.d_vad);
+        if (s.d_energy) cudaFree(s.d_energy);
+        if (s.d_final) cudaFree(s.d_final);
+        if (s.st) cudaStreamDestroy(s.st);
+    }
+    delete b;
+}
+
+AF_API int af_batch_create(af_pipeline *p, const af_stream_desc *streams, size_t n_streams, int mem, af_batch **out)
+{
+    if (!p || !out || (!streams && n_streams)) return fail(AF_ERR_INVALID, "null argument");
+    if (mem != AF_MEM_DEVICE && mem != AF_MEM_HOST) return fail(AF_ERR_INVALID, "bad memory kind %d", mem);
+    int rc = require_ctx();
+    if (rc) return rc;
+    std::unique_ptr<af_batch> b(new af_batch);
+    b->pipe = p; b->mem = mem;
+    b->streams.resize(n_streams);
+    const af_pipeline_config &cfg = p->cfg;
+    for (size_t i = 0; i < n_streams; ++i) {
+        HostStream &hs = b->streams[i];
+        hs.desc = streams[i];
+        const af_stream_desc &d = hs.desc;
+        if (d.channels == 0) return fail(AF_ERR_INVALID, "stream %zu: channels must be >= 1", i);
+        if (d.format != AF_FMT_F32 && d.format != AF_FMT_I16) return fail(AF_ERR_INVALID, "stream %zu: bad format %u", i, d.format);
+        if (!d.data && d.n_samples) return fail(AF_ERR_INVALID, "stream %zu: null data", i);
+        if (mem == AF_MEM_DEVICE && ((uintptr_t)d.data & 15)) return fail(AF_ERR_INVALID, "stream %zu: device data must be 16-byte aligned", i);
+        const uint64_t n_in = (d.n_samples + d.channels - 1) / d.channels;
+        if (n_in >= (1ull << 31)) return fail(AF_ERR_INVALID, "stream %zu: too long (%llu frames)", i, (unsigned long long)n_in);
+        uint64_t n_out = 0;
+        rc = plan_rate(d.sample_rate, OUT_RATE, n_in, &n_out, &hs.mode, &hs.p, &hs.q, &hs.table);
+        if (rc) return rc;
+        if (n_out >= (1ull << 31)) return fail(AF_ERR_INVALID, "stream %zu: output too long", i);
+        if (hs.mode != RS_PASSTHROUGH &&
+            (uint64_t)(TILE_SAMPLES + YLEN + FUSED_THREADS) * hs.p + hs.q >= (1ull << 32))
+            return fail(AF_ERR_RESAMPLING_FAILED, "stream %zu: unsupported rate ratio %u/%u", i, hs.p, hs.q);
+        hs.n_in = (uint32_t)n_in; hs.n_out = (uint32_t)n_out;
+        hs.n_frames = n_out >= WIN ? (uint32_t)(1 + (n_out - WIN) / HOP) : 0;
+        if (!cfg.vad_enable) hs.n_vad_frames = 0;
+        else if (cfg.vad_frame_len == 0) hs.n_vad_frames = hs.n_frames;
+        else hs.n_vad_frames = n_out >= cfg.vad_frame_len ? (uint32_t)(1 + (n_out - cfg.vad_frame_len) / cfg.vad_hop) : 0;
+        b->max_out = std::max<uint64_t>(b->max_out, hs.n_out);
+        b->max_frames = std::max<uint64_t>(b->max_frames, hs.n_frames);
+        b->max_vad = std::max<uint64_t>(b->max_vad, hs.n_vad_frames);
+    }
+    b->pcm_stride = round_up(std::max<uint64_t>(b->max_out, 4), 4);
+    b->logmel_stride = round_up(std::max<uint64_t>(b->max_frames * cfg.n_mels, 4), 4);
+    b->vad_stride = round_up(std::max<uint64_t>(b->max_vad, 16), 16);
+    b->energy_stride = round_up(std::max<uint64_t>(b->max_vad, 4), 4);
+
+    if (mem == AF_MEM_DEVICE) {
+        b->subs.resize(1);
+        b->subs[0].first = 0; b->subs[0].count = n_streams;
+        if (n_streams) { rc = build_sub(b.get(), b->subs[0], nullptr); if (rc) return rc; }
+    } else {
+        // host mode: groups of streams of ~96 MB input, cycled through 3 slots so that the H2D copy of
+        // group g+1, the kernels of group g and the D2H copy of group g-1 overlap
+        const size_t target = 96ull << 20;
+        size_t i = 0;
+        while (i < n_streams) {
+            SubBatch sb;
+            sb.first = i;
+            size_t bytes = 0;
+            while (i < n_streams && (sb.count == 0 || bytes < target)) {
+                const af_stream_desc &d = b->streams[i].desc;
+                const size_t sz = d.n_samples * (d.format == AF_FMT_I16 ? 2 : 4);
+                sb.in_off.push_back(bytes);
+                bytes += round_up(sz, 256);
+                sb.count++; i++;
+            }
+            sb.in_bytes = bytes;
+            b->subs.push_back(std::move(sb));
+        }
+        size_t max_rows = 0, max_in = 0;
+        for (auto &sb : b->subs) { max_rows = std::max(max_rows, sb.count); max_in = std::max(max_in, sb.in_bytes); }
+        b->slot_rows = max_rows;
+        const size_t n_slots = std::min<size_t>(3, std::max<size_t>(1, b->subs.size()));
+        b->slots.resize(n_slots);
+        for (auto &s : b->slots) {
+            AF_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+            AF_CUDA(cudaMalloc(&s.d_in, std::max<size_t>(max_in, 256)));
+            AF_CUDA(cudaMalloc(&s.d_pcm, std::max<size_t>(max_rows * b->pcm_stride * sizeof(float), 256)));
+            if (cfg.n_mels) AF_CUDA(cudaMalloc(&s.d_logmel, std::max<size_t>(max_rows * b->logmel_stride * sizeof(float), 256)));
+            if (cfg.vad_enable) {
+                AF_CUDA(cudaMalloc(&s.d_vad, std::max<size_t>(max_rows * b->vad_stride, 256)));
+                AF_CUDA(cudaMalloc(&s.d_energy, std::max<size_t>(max_rows * b->energy_stride * sizeof(float), 256)));
+                AF_CUDA(cudaMalloc(&s.d_final, std::max<size_t>(max_rows * sizeof(VadState), 256)));
+            }
+        }
+        for (size_t g = 0; g < b->subs.size(); ++g) {
+            rc = build_sub(b.get(), b->subs[g], b->slots[g % n_slots].d_in);
+            if (rc) return rc;
+        }
+    }
+    *out = b.release();
+    return AF_OK;
+}
+
+AF_API size_t af_batch_n_streams(const af_batch *b) { return b ? b->streams.size() : 0; }
+
+AF_API int af_batch_counts(const af_batch *b, uint32_t *n_out, uint32_t *n_feat_frames, uint32_t *n_vad_frames)
+{
+    if (!b) return fail(AF_ERR_INVALID, "null batch");
+    for (size_t i = 0; i < b->streams.size(); ++i) {
+        if (n_out) n_out[i] = b->streams[i].n_out;
+        if (n_feat_frames) n_feat_frames[i] = b->pipe->cfg.n_mels ? b->streams[i].n_frames : 0;
+        if (n_vad_frames) n_vad_frames[i] = b->streams[i].n_vad_frames;
+    }
+    return AF_OK;
+}
+
+AF_API int af_batch_strides(const af_batch *b, uint64_t *pcm_stride, uint64_t *logmel_stride, uint64_t *vad_stride)
+{
+    if (!b) return fail(AF_ERR_INVALID, "null batch");
+    if (pcm_stride) *pcm_stride = b->pcm_stride;
+    if (logmel_stride) *logmel_stride = b->logmel_stride;
+    if (vad_stride) *vad_stride = b->vad_stride;
+    return AF_OK;
+}
+
+static int check_outputs(const af_batch *b, const af_outputs *o)
+{
+    const af_pipeline_config &cfg = b->pipe->cfg;
+    if (!o) return fail(AF_ERR_INVALID, "null outputs");
+    if (o->pcm && (o->pcm_stride < b->max_out || (o->pcm_stride & 3))) return fail(AF_ERR_CAPACITY, "pcm_stride %llu too small or not a multiple of 4 (need >= %llu)", (unsigned long long)o->pcm_stride, (unsigned long long)b->max_out);
+    if (o->logmel && cfg.n_mels && (o->logmel_stride < b->max_frames * cfg.n_mels || (o->logmel_stride & 3))) return fail(AF_ERR_CAPACITY, "logmel_stride too small or not a multiple of 4");
+    if (o->vad && o->vad_stride < b->max_vad) return fail(AF_ERR_CAPACITY, "vad_stride too small");
+    if (o->energy && o->energy_stride < b->max_vad) return fail(AF_ERR_CAPACITY, "energy_stride too small");
+    return AF_OK;
+}
+
+AF_API int af_batch_run(af_batch *b, const af_outputs *o, void *cuda_stream)
+{
+    if (!b) return fail(AF_ERR_INVALID, "null batch");
+    if (b->mem != AF_MEM_DEVICE) return fail(AF_ERR_INVALID, "batch was planned for host buffers; use af_batch_run_host");
+    int rc = check_outputs(b, o);
+    if (rc) return rc;
+    if (b->streams.empty()) return AF_OK;
+    const af_pipeline_config &cfg = b->pipe->cfg;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_ctx.stream;
+    const size_t S = b->streams.size();
+    float *energy = o->energy; uint64_t energy_stride = o->energy_stride;
+    if (cfg.vad_enable && !energy) {
+        if (!b->d_energy) AF_CUDA(cudaMalloc(&b->d_energy, std::max<size_t>(S * b->energy_stride * sizeof(float), 256)));
+        energy = b->d_energy; energy_stride = b->energy_stride;
+    }
+    float *pcm = cfg.write_pcm ? o->pcm : nullptr; uint64_t pcm_stride = o->pcm_stride;
+    if (cfg.vad_enable && cfg.vad_frame_len != 0 && !pcm) {      // custom VAD frames read the PCM back
+        if (!b->d_pcm_scratch) AF_CUDA(cudaMalloc(&b->d_pcm_scratch, std::max<size_t>(S * b->pcm_stride * sizeof(float), 256)));
+        pcm = b->d_pcm_scratch; pcm_stride = b->pcm_stride;
+    }
+    rc = run_sub(b, b->subs[0], pcm, pcm_stride, o->logmel, o->logmel_stride, o->vad, o->vad_stride, energy,
+                 energy_stride, reinterpret_cast<VadState *>(o->vad_final), st);
+    if (rc) return rc;
+    if (!cuda_stream) AF_CUDA(cudaStreamSynchronize(st));
+    return AF_OK;
+}
+
+AF_API int af_batch_run_host(af_batch *b, const af_outputs *o)
+{
+    if (!b) return fail(AF_ERR_INVALID, "null batch");
+    if (b->mem != AF_MEM_HOST) return fail(AF_ERR_INVALID, "batch was planned for device buffers; use af_batch_run");
+    int rc = check_outputs(b, o);
+    if (rc) return rc;
+    const af_pipeline_config &cfg = b->pipe->cfg;
+    const size_t n_slots = b->slots.size();
+    for (size_t g = 0; g < b->subs.size(); ++g) {
+        SubBatch &sb = b->subs[g];
+        af_batch::Slot &sl = b->slots[g % n_slots];
+        cudaStream_t st = sl.st;
+        for (size_t i = 0; i < sb.count; ++i) {
+            const af_stream_desc &d = b->streams[sb.first + i].desc;
+            const size_t sz = d.n_samples * (d.format == AF_FMT_I16 ? 2 : 4);
+            if (sz) AF_CUDA(cudaMemcpyAsync((char *)sl.d_in + sb.in_off[i], d.data, sz, cudaMemcpyHostToDevice, st));
+        }
+        const bool need_pcm = (cfg.write_pcm && o->pcm) || (cfg.vad_enable && cfg.vad_frame_len != 0);
+        rc = run_sub(b, sb, need_pcm ? sl.d_pcm : nullptr, b->pcm_stride, sl.d_logmel, b->logmel_stride, sl.d_vad,
+                     b->vad_stride, sl.d_energy, b->energy_stride, sl.d_final, st);
+        if (rc) return rc;
+        const size_t r0 = sb.first;
+        if (cfg.write_pcm && o->pcm)
+            AF_CUDA(cudaMemcpy2DAsync(o->pcm + r0 * o->pcm_stride, o->pcm_stride * sizeof(float), sl.d_pcm,
+                                      b->pcm_stride * sizeof(float), b->max_out * sizeof(float), sb.count,
+                                      cudaMemcpyDeviceToHost, st));
+        if (cfg.n_mels && o->logmel && b->max_frames)
+            AF_CUDA(cudaMemcpy2DAsync(o->logmel + r0 * o->logmel_stride, o->logmel_stride * sizeof(float), sl.d_logmel,
+                                      b->logmel_stride * sizeof(float), b->max_frames * cfg.n_mels * sizeof(float),
+                                      sb.count, cudaMemcpyDeviceToHost, st));
+        if (cfg.vad_enable && b->max_vad) {
+            if (o->vad)
+                AF_CUDA(cudaMemcpy2DAsync(o->vad + r0 * o->vad_stride, o->vad_stride, sl.d_vad, b->vad_stride, b->max_vad,
+                                          sb.count, cudaMemcpyDeviceToHost, st));
+            if (o->energy)
+                AF_CUDA(cudaMemcpy2DAsync(o->energy + r0 * o->energy_stride, o->energy_stride * sizeof(float), sl.d_energy,
+                                          b->energy_stride * sizeof(float), b->max_vad * sizeof(float), sb.count,
+                                          cudaMemcpyDeviceToHost, st));
+        }
+        if (cfg.vad_enable && o->vad_final)
+            AF_CUDA(cudaMemcpyAsync(o->vad_final + r0, sl.d_final, sb.count * sizeof(VadState), cudaMemcpyDeviceToHost, st));
+    }
+    for (auto &sl : b->slots) AF_CUDA(cudaStreamSynchronize(sl.st));
+    return AF_OK;
+}
+
+AF_API int af_pipeline_run(af_pipeline *p, const af_stream_desc *streams, size_t n_streams, const af_outputs *out)
+{
+    af_batch *b = nullptr;
+    int rc = af_batch_create(p, streams, n_streams, AF_MEM_HOST, &b);
+    if (rc) return rc;
+    rc = af_batch_run_host(b, out);
+    af_batch_destroy(b);
+    return rc;
+}
+
+AF_API float af_debug_vad_energy_threshold(float threshold_db) { return vad_energy_threshold(threshold_db); }
+
+AF_API size_t af_debug_resample_plan(uint32_t input_rate, uint32_t output_rate, size_t n_chunks, float *frac, size_t cap,
+                                     int *mode)
+{
+    RsRecurrence r;
+    r.init(input_rate, output_rate);
+    if (mode) *mode = (int)r.mode();
+    if (r.passthrough || r.end_idx <= 0) return 0;
+    std::vector<float> f;
+    for (size_t c = 0; c < n_chunks; ++c) r.step(&f);
+    for (size_t i = 0; i < f.size() && i < cap; ++i) frac[i] = f[i];
+    return f.size();
+}
+
+// ---- streaming sessions: implemented in af_session.cu ----
+
+}  // extern "C"
+
+extern "C" int af_session_fail(void) { return fail(AF_ERR_INVALID, "streaming sessions are not implemented in this build"); }

@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 audio hot path (BASELINE.json metric:
+audio-seconds processed per second; HBM GB/s vs measured peak; CPU path timed beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the fused pipeline (downmix -> resample -> STFT -> log-mel, PCM and
+log-mel written) over one batch of BASELINE config 2 per GPU: 256 x 30 s 48 kHz mono f32 streams.
+N > 1 shards independent streams across ranks (256 per rank, weak scaling, no data-path
+collective); per-stream result summaries are gathered to every rank with NCCL after each step.
+PyTorch is used only for device memory, streams/events and torch.distributed.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.join(ROOT, "audio-flow-rs_b200"), os.path.join(ROOT, "oracle")]
+
+STREAMS_PER_GPU = 256
+SECONDS = 30.0
+RATE = 48000
+N_MELS = 80
+# algorithmic bytes per audio-second = R_in*C*b_in + 16000*4 (PCM) + 100*M*4 (log-mel)
+BYTES_PER_AUDIO_S = RATE * 1 * 4 + 16000 * 4 + 100 * N_MELS * 4          # 288000 (VAD off)
+BYTES_PER_AUDIO_S_VAD = BYTES_PER_AUDIO_S + 100                          # + u8 VAD state per frame
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+
+    def sample(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                     0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            self.sample()
+            self._stop_evt.wait(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs (the oracle port of the reference path, all host threads)
+# ---------------------------------------------------------------------------------------------
+WORKLOAD = "cfg2: 256 x 30 s 48 kHz mono f32 streams per GPU -> 16 kHz PCM + 25/10 ms STFT + 80-bin log-mel"
+PORT_NOTE = ("oracle/oracle.c port of the reference CPU path: to_mono (capture.rs:30-42) + BatchResampler over rubato "
+             "FastFixedIn cubic (resampler.rs:132-166) + spec-defined f32 STFT/log-mel (not reference code; the reference has none)")
+
+
+def cpu_pipeline_rate(n_streams: int, seconds: float, with_features: bool = True, repeats: int = 1, with_vad: bool = False):
+    """Times the CPU restatement of the reference path (oracle/, kind "port") on n_streams synthetic
+    streams of the bench shape, spread over all host threads.  Returns (audio_s_per_s, cores, secs)."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    from audioflow import synth
+    L = oracle.lib()
+    cores = os.cpu_count() or 1
+    n = int(SECONDS * RATE) if seconds == SECONDS else int(seconds * RATE)
+    rng = np.random.default_rng(0)
+    base = synth.stream(0, min(seconds, 4.0), RATE, 1)
+    reps = int(np.ceil(n / len(base)))
+    xs = [np.ascontiguousarray(np.tile(np.roll(base, int(rng.integers(0, len(base)))), reps)[:n]) for _ in range(min(n_streams, 8))]
+    feat = oracle.default_feat_config(N_MELS)
+    plan = oracle.FeatPlan(feat) if with_features else None
+    vc = oracle.default_vad_config()
+    cap = L.orc_resample_max_output(RATE, 16000, n)
+    fp = C.POINTER(C.c_float)
+
+    def work(i):
+        x = xs[i % len(xs)]
+        mono = np.empty(n, np.float32)
+        pcm = np.empty(cap, np.float32)
+        T = cap // 160 + 1
+        lm = np.empty(T * N_MELS, np.float32)
+        vad = np.empty(T, np.uint8)
+        nf = C.c_size_t(0)
+        L.orc_pipeline_stream(x.ctypes.data_as(fp), n, 1, RATE, plan._h if plan else None, C.byref(vc) if with_vad else None, 400, 160,
+                              mono.ctypes.data_as(fp), pcm.ctypes.data_as(fp), cap,
+                              lm.ctypes.data_as(fp) if plan else None, vad.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(nf))
+        return nf.value
+
+    best = None
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            list(ex.map(work, range(n_streams)))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return n_streams * seconds / best, cores, best
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is Rust and
+    cannot be built in this image (no toolchain, rubato sources absent), so this is the oracle PORT of it,
+    timed with all host threads on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+    oracle.lib()
+    sample_streams = 64
+    for _ in range(args.warmup):
+        cpu_pipeline_rate(4, 5.0)
+    t_total, units = 0.0, 0.0
+    cores = os.cpu_count() or 1
+    for _ in range(args.steps):
+        rate, cores, dt = cpu_pipeline_rate(sample_streams, SECONDS)
+        t_total += dt
+        units += sample_streams * SECONDS
+    value = units / t_total
+    line = {
+        "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "streams_per_gpu": STREAMS_PER_GPU, "seconds": SECONDS, "sample_rate": RATE,
+                   "n_mels": N_MELS, "vad": False,
+                   "sample": f"{sample_streams} of the {STREAMS_PER_GPU} streams x {SECONDS:.0f} s per step on {cores} host threads"},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_streams} x {SECONDS:.0f} s streams per step, {args.steps} steps; " + PORT_NOTE},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="auto")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import audioflow as af
+    from audioflow import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (libaudioflow_gpu has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    af.init(local_rank)
+    af.set_kernel_variant(args.variant)
+
+    S, n = STREAMS_PER_GPU, int(SECONDS * RATE)
+    x = synth.torch_batch(S, SECONDS, RATE, 1, dev, seed=rank)             # resident in HBM before timing
+    descs = [(x[i].data_ptr(), n, RATE, 1, af.AF_FMT_F32) for i in range(S)]
+
+    def make(vad_enable):
+        pipe = af.Pipeline(af.pipeline_config(n_mels=N_MELS, vad_enable=vad_enable))
+        b = pipe.batch(descs, af.AF_MEM_DEVICE)
+        pcm = torch.empty((S, b.pcm_stride), device=dev)
+        lm = torch.empty((S, b.logmel_stride), device=dev)
+        vad = torch.zeros((S, b.vad_stride), device=dev, dtype=torch.uint8) if vad_enable else None
+        o = b.outputs_struct(pcm.data_ptr(), b.pcm_stride, lm.data_ptr(), b.logmel_stride,
+                             vad.data_ptr() if vad_enable else 0, b.vad_stride, 0, 0, 0)
+        return pipe, b, o, (pcm, lm, vad)
+
+    pipe, batch, outs, bufs = make(False)
+    audio_s_per_step_rank = S * SECONDS
+    summary = torch.tensor(np.stack([batch.n_out[:S], batch.n_feat[:S]], 1).astype(np.int32), device=dev)
+    gathered = torch.empty((world,) + tuple(summary.shape), device=dev, dtype=torch.int32) if world > 1 else None
+    stream = torch.cuda.current_stream()
+
+    def step(b, o):
+        b.run_device(o, stream.cuda_stream)
+        if world > 1:                      # gather per-stream result summaries (the only exchange step)
+            dist.all_gather_into_tensor(gathered, summary)
+
+    def timed(b, o, steps):
+        for _ in range(args.warmup):
+            step(b, o)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        l0 = af.kernel_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step(b, o)
+        e1.record(stream)
+        sampler.sample()
+        sampler.start()
+        torch.cuda.synchronize()
+        sampler.stop()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = af.kernel_launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, sampler.summary()
+
+    ms, launches, clocks = timed(batch, outs, args.steps)
+    ms_per_step = ms / args.steps
+    value = world * audio_s_per_step_rank / (ms_per_step * 1e-3)
+
+    # the same step with the VAD on (energies fused into the kernel + sequential scan kernel)
+    pipe_v, batch_v, outs_v, bufs_v = make(True)
+    ms_v, launches_v, _ = timed(batch_v, outs_v, max(args.steps // 2, 3))
+    ms_v_per_step = ms_v / max(args.steps // 2, 3)
+
+    # ---- roofline of the dominant kernel: with the VAD off a step IS one launch of af_fused_kernel ----
+    peak, peak_src = measured_peak_gbs()
+    alg_bytes = BYTES_PER_AUDIO_S * audio_s_per_step_rank
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("af_fused_kernel_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- e2e: the reference-facing call with HOST (pinned) buffers, H2D + D2H inside the timed region ----
+    e2e = None
+    if args.e2e_steps > 0:
+        L = af.load_library()
+        in_bytes = S * n * 4
+        hp = C.c_void_p()
+        af._check(L.af_host_alloc(C.byref(hp), in_bytes))
+        hin = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_float)), shape=(S, n))
+        hin[:] = x.cpu().numpy()
+        hdescs = [(hin[i].ctypes.data, n, RATE, 1, af.AF_FMT_F32) for i in range(S)]
+        hb = pipe.batch(hdescs, af.AF_MEM_HOST)
+        po, pl = C.c_void_p(), C.c_void_p()
+        pcm_bytes, lm_bytes = S * hb.pcm_stride * 4, S * hb.logmel_stride * 4
+        af._check(L.af_host_alloc(C.byref(po), pcm_bytes))
+        af._check(L.af_host_alloc(C.byref(pl), lm_bytes))
+        ho = hb.outputs_struct(po.value, hb.pcm_stride, pl.value, hb.logmel_stride, 0, 0, 0, 0, 0)
+        af._check(L.af_batch_run_host(hb._h, C.byref(ho)))            # warm-up
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            af._check(L.af_batch_run_host(hb._h, C.byref(ho)))        # blocking: returns when results are on the host
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        d2h = int(S * (int(hb.n_out.max()) * 4 + int(hb.n_feat.max()) * N_MELS * 4))
+        e2e = {"value": world * args.e2e_steps * audio_s_per_step_rank / dt, "unit": "audio-s/s",
+               "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": d2h,
+               "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "note": "af_batch_run_host: pinned host PCM in, PCM + log-mel back on the host; 3-slot H2D/compute/D2H overlap"}
+        # spot-check of the e2e result against the device-resident run
+        lm_host = np.ctypeslib.as_array(C.cast(pl, C.POINTER(C.c_float)), shape=(S, hb.logmel_stride))
+        T = int(hb.n_feat[0])
+        if not np.array_equal(lm_host[3, :T * N_MELS], bufs[1][3, :T * N_MELS].cpu().numpy()):
+            raise SystemExit("e2e result differs from the device-resident result")
+        del hb
+        L.af_host_free(hp); L.af_host_free(po); L.af_host_free(pl)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, dt = cpu_pipeline_rate(64, SECONDS)
+        cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+               "sample": f"64 of the {S} streams x {SECONDS:.0f} s (all {cores} host threads, {dt:.1f} s wall); " + PORT_NOTE}
+
+    if rank == 0:
+        line = {
+            "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD,
+                       "streams_per_gpu": S, "seconds": SECONDS, "sample_rate": RATE, "n_mels": N_MELS, "vad": False,
+                       "parallelism": f"stream-sharded x{world}", "bytes_per_audio_s": BYTES_PER_AUDIO_S,
+                       "l2": "inputs (1.47 GB per GPU) larger than L2; no explicit flush",
+                       "kernel_variant": args.variant},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "af_fused_kernel", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "with_vad": {"value": world * audio_s_per_step_rank / (ms_v_per_step * 1e-3), "ms_per_step": ms_v_per_step,
+                         "gpu_launches_per_step": launches_v / max(args.steps // 2, 3),
+                         "hbm_gbs": BYTES_PER_AUDIO_S_VAD * audio_s_per_step_rank / (ms_v_per_step * 1e-3) / 1e9},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,247 @@
+/*
+ * audioflow_gpu.h -- C ABI of libaudioflow_gpu.so, the B200 (sm_100a) implementation of the
+ * audio hot path of forfd8960/audio-flow-rs:
+ *
+ *     interleaved f32/i16 PCM -> downmix -> resample to 16 kHz -> 25 ms/10 ms frames
+ *     -> Hann -> 512-pt STFT -> log-mel,  and energy VAD frame decisions.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference repo root).  The reference has no FFI of its own (plain Rust structs re-exported
+ * at src-tauri/src/modules/audio/mod.rs:9-11), so these are exactly the functions a Rust
+ * `extern "C"` block for that module would bind; INTEGRATION.md shows that binding.
+ *
+ * Conventions
+ *   - plain C types only; every function returns an af_status (0 = ok) unless noted.
+ *   - on failure a thread-local message is available from af_last_error(); the Rust shim
+ *     turns it into AudioError::ResamplingFailed(msg) (src-tauri/src/error.rs:109-110).
+ *   - handles are NOT thread-safe individually (they mirror `&mut self`); distinct handles
+ *     may be used from distinct threads.
+ *   - there is no CPU fallback: without a CUDA device every call fails with AF_ERR_NO_DEVICE.
+ */
+#ifndef AUDIOFLOW_GPU_H
+#define AUDIOFLOW_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AF_API __attribute__((visibility("default")))
+#else
+#define AF_API
+#endif
+
+typedef enum af_status {
+    AF_OK = 0,
+    AF_ERR_INVALID = 1,           /* bad argument */
+    AF_ERR_RESAMPLING_FAILED = 2, /* AudioError::ResamplingFailed (error.rs:109-110) */
+    AF_ERR_CUDA = 3,              /* CUDA runtime failure (also surfaced as ResamplingFailed by the shim) */
+    AF_ERR_NO_DEVICE = 4,         /* no CUDA device / not initialised */
+    AF_ERR_CAPACITY = 5           /* caller-provided output buffer too small */
+} af_status;
+
+/* ---- library ------------------------------------------------------------------------- */
+AF_API int af_init(int device);                 /* binds the calling process to one GPU */
+AF_API int af_shutdown(void);
+AF_API size_t af_last_error(char *buf, size_t cap);   /* returns strlen of the full message */
+AF_API int af_device_count(int *count);
+AF_API const char *af_version(void);
+/* Number of kernels this library has launched since af_init (bench.py's gpu_launches). */
+AF_API uint64_t af_kernel_launch_count(void);
+
+/* pinned host memory for the host-buffer entry points (optional but much faster) */
+AF_API int af_host_alloc(void **ptr, size_t bytes);
+AF_API int af_host_free(void *ptr);
+
+/* ---- AudioFrame::to_mono  (src-tauri/src/modules/audio/capture.rs:30-42) ---------------- */
+/* host buffers; out needs ceil(n_samples / channels) floats.  channels == 1 -> copy. */
+AF_API int af_to_mono(const float *samples, size_t n_samples, uint16_t channels, float *out, size_t out_cap,
+                      size_t *n_out);
+
+/* ---- AudioResampler  (src-tauri/src/modules/audio/resampler.rs:12-112, 169-178) -------- */
+typedef struct af_resampler af_resampler;
+/* AudioResampler::new (resampler.rs:32-57); create_48k_to_16k (:60-62) == create(48000,16000) */
+AF_API int af_resampler_create(uint32_t input_rate, uint32_t output_rate, af_resampler **out);
+AF_API void af_resampler_destroy(af_resampler *r);
+/* AudioResampler::process (resampler.rs:71-93): equal rates -> copy; otherwise ONE rubato
+ * FastFixedIn step: consumes exactly 128 frames (extra ignored), fewer than 128 ->
+ * AF_ERR_RESAMPLING_FAILED.  Host buffers. */
+AF_API int af_resampler_process(af_resampler *r, const float *input, size_t n, float *out, size_t out_cap,
+                                size_t *n_out);
+AF_API uint32_t af_resampler_input_rate(const af_resampler *r);   /* resampler.rs:96-98  */
+AF_API uint32_t af_resampler_output_rate(const af_resampler *r);  /* resampler.rs:101-103 */
+AF_API int af_resampler_needs_resampling(const af_resampler *r);  /* resampler.rs:106-108 */
+AF_API size_t af_resampler_chunk_size(const af_resampler *r);     /* 128, or 0 for passthrough */
+/* upper bound of the number of output frames produced for n_in input frames */
+AF_API size_t af_resample_max_output(uint32_t input_rate, uint32_t output_rate, size_t n_in);
+/* exact number of output frames of BatchResampler::process(all n_in) + flush() */
+AF_API int af_resample_output_len(uint32_t input_rate, uint32_t output_rate, size_t n_in, size_t *n_out);
+
+/* ---- BatchResampler  (src-tauri/src/modules/audio/resampler.rs:115-166) ---------------- */
+typedef struct af_batch_resampler af_batch_resampler;
+AF_API int af_batch_resampler_create(uint32_t input_rate, uint32_t output_rate, af_batch_resampler **out);
+AF_API void af_batch_resampler_destroy(af_batch_resampler *b);
+/* BatchResampler::process (:132-147): buffers input, emits the output of every complete
+ * 128-frame chunk.  Equal rates: passthrough (the reference would loop forever there). */
+AF_API int af_batch_resampler_process(af_batch_resampler *b, const float *input, size_t n, float *out,
+                                      size_t out_cap, size_t *n_out);
+/* BatchResampler::flush (:150-166): zero-pads the residual to one chunk and processes it. */
+AF_API int af_batch_resampler_flush(af_batch_resampler *b, float *out, size_t out_cap, size_t *n_out);
+
+/* ---- VoiceActivityDetector  (src-tauri/src/modules/audio/vad.rs) ---------------------- */
+typedef struct af_vad_config {      /* VadConfig, vad.rs:21-32 */
+    float threshold_db;
+    float smoothing_factor;
+    uint64_t silence_timeout_frames;
+    uint64_t min_speech_frames;
+} af_vad_config;
+
+enum { AF_VAD_SILENCE = 0, AF_VAD_SPEECH = 1, AF_VAD_ENDING = 2 };   /* VadState, vad.rs:47-54 */
+
+typedef struct af_vad af_vad;
+AF_API void af_vad_config_default(af_vad_config *cfg);                 /* vad.rs:34-43 */
+AF_API int af_vad_create(const af_vad_config *cfg, af_vad **out);      /* vad.rs:80-88 */
+AF_API void af_vad_destroy(af_vad *v);
+/* detect (vad.rs:97-154): one frame of any length -> post-transition state */
+AF_API int af_vad_detect(af_vad *v, const float *frame, size_t n, uint8_t *state);
+/* the same detector driven over many frames [f*hop, f*hop+frame_len) of one host signal in a
+ * single launch; writes one state per frame */
+AF_API int af_vad_detect_frames(af_vad *v, const float *samples, size_t n, uint32_t frame_len, uint32_t hop,
+                                uint8_t *states, size_t states_cap, size_t *n_frames);
+AF_API int af_vad_reset(af_vad *v);                                    /* vad.rs:179-184 */
+AF_API int af_vad_state(const af_vad *v);                              /* vad.rs:187-189 */
+AF_API float af_vad_energy_db(const af_vad *v);                        /* vad.rs:192-194 */
+AF_API int af_vad_is_speaking(const af_vad *v);                        /* vad.rs:197-199 */
+AF_API uint64_t af_vad_speech_frame_count(const af_vad *v);            /* vad.rs:202-204 */
+AF_API float af_vad_smoothed_energy(const af_vad *v);                  /* the field behind energy_db */
+/* mean-square frame energy exactly as calculate_energy (vad.rs:157-168), on the GPU */
+AF_API int af_vad_frame_energy(const float *frame, size_t n, float *energy);
+
+/* ---- PCM16 wire encode  (src-tauri/src/modules/network/websocket.rs:246-251) ---------- */
+AF_API int af_pcm16_encode(const float *samples, size_t n, int16_t *out);
+
+/* ======================================================================================= */
+/* Batched fast path: many independent streams through                                     */
+/*   to_mono -> BatchResampler(all)+flush -> STFT/log-mel -> framed VAD                     */
+/* in one launch sequence.  Results are identical to driving the per-object API above      */
+/* stream by stream.                                                                       */
+/* ======================================================================================= */
+enum { AF_FMT_F32 = 0, AF_FMT_I16 = 1 };            /* sample format; i16 decodes as s / 32768 */
+enum { AF_MEM_DEVICE = 0, AF_MEM_HOST = 1 };        /* where stream data and outputs live */
+
+typedef struct af_pipeline_config {
+    uint32_t n_mels;          /* 0 = no STFT/log-mel; else 1..128 (80 and 128 are the BASELINE configs) */
+    float f_min, f_max;       /* mel band edges in Hz (0, 8000) */
+    float log_floor;          /* log(max(mel, floor)), 1e-10 */
+    uint32_t log10;           /* 0 natural log, 1 log10 */
+    uint32_t vad_enable;      /* run the VAD */
+    af_vad_config vad;
+    uint32_t vad_frame_len;   /* 0 -> the STFT frames (400 / 160); else e.g. 320 / 320 (20 ms) */
+    uint32_t vad_hop;
+    uint32_t write_pcm;       /* write the resampled 16 kHz PCM */
+} af_pipeline_config;
+
+AF_API void af_pipeline_config_default(af_pipeline_config *cfg);
+
+typedef struct af_stream_desc {
+    const void *data;         /* interleaved samples [frame][channel] */
+    uint64_t n_samples;       /* TOTAL interleaved sample count (AudioFrame::samples.len()) */
+    uint32_t sample_rate;     /* AudioFrame::sample_rate; output is always 16 kHz */
+    uint16_t channels;        /* AudioFrame::channels */
+    uint16_t format;          /* AF_FMT_* */
+} af_stream_desc;
+
+typedef struct af_vad_final {   /* detector state after the last frame of a stream */
+    float smoothed_energy;
+    int32_t state;
+    uint64_t silence_frames;
+    uint64_t speech_frames;
+} af_vad_final;
+
+typedef struct af_outputs {
+    float *pcm;               /* [n_streams][pcm_stride]    resampled mono 16 kHz (or NULL) */
+    uint64_t pcm_stride;      /* floats per row, multiple of 4 */
+    float *logmel;            /* [n_streams][logmel_stride] rows of [frame][mel] (or NULL) */
+    uint64_t logmel_stride;   /* floats per row, multiple of 4 */
+    uint8_t *vad;             /* [n_streams][vad_stride]    VadState per frame (or NULL) */
+    uint64_t vad_stride;
+    float *energy;            /* [n_streams][energy_stride] mean-square energy per VAD frame (or NULL) */
+    uint64_t energy_stride;
+    af_vad_final *vad_final;  /* [n_streams] (or NULL) */
+} af_outputs;
+
+typedef struct af_pipeline af_pipeline;
+typedef struct af_batch af_batch;
+
+AF_API int af_pipeline_create(const af_pipeline_config *cfg, af_pipeline **out);
+AF_API void af_pipeline_destroy(af_pipeline *p);
+
+/* Plans a batch: validates the descriptors, computes per-stream output lengths with the exact
+ * chunk recurrence of the reference resampler, builds the device-side stream/tile tables.
+ * mem = AF_MEM_DEVICE: desc.data are device pointers (16-byte aligned), the batch can be run
+ * many times.  mem = AF_MEM_HOST: desc.data are host pointers, used by af_batch_run_host. */
+AF_API int af_batch_create(af_pipeline *p, const af_stream_desc *streams, size_t n_streams, int mem,
+                           af_batch **out);
+AF_API void af_batch_destroy(af_batch *b);
+AF_API size_t af_batch_n_streams(const af_batch *b);
+/* per-stream counts (host arrays of n_streams): resampled length, STFT frames, VAD frames */
+AF_API int af_batch_counts(const af_batch *b, uint32_t *n_out, uint32_t *n_feat_frames, uint32_t *n_vad_frames);
+/* minimal strides (already rounded to the required multiples) */
+AF_API int af_batch_strides(const af_batch *b, uint64_t *pcm_stride, uint64_t *logmel_stride,
+                            uint64_t *vad_stride);
+
+/* Device-resident run: outputs are device pointers.  Enqueues on `cuda_stream`
+ * (a cudaStream_t passed as void*, NULL = the library's own stream) and returns without
+ * synchronising when cuda_stream != NULL. */
+AF_API int af_batch_run(af_batch *b, const af_outputs *out, void *cuda_stream);
+/* Host-buffer run (the reference-facing call): copies the streams H2D (chunked, overlapped
+ * with compute), runs the pipeline and copies the requested outputs back; blocking. */
+AF_API int af_batch_run_host(af_batch *b, const af_outputs *out);
+/* One-shot convenience: create + run_host + destroy. */
+AF_API int af_pipeline_run(af_pipeline *p, const af_stream_desc *streams, size_t n_streams,
+                           const af_outputs *out);
+
+/* which variant of the fused kernel to launch (default "auto"); for tests and ncu comparisons.
+ * names: "auto", "sync" (plain loads), "tma" (bulk-copy staged input).  Returns AF_ERR_INVALID
+ * for unknown names. */
+AF_API int af_set_kernel_variant(const char *name);
+
+/* ---- VAD segmentation (consumer of VadState) --------------------------- */
+/* device buffers: states [n_streams][vad_stride] -> seg [n_streams][seg_cap][2] = [start,end)
+ * frames, n_seg [n_streams].  A segment runs from the first Speech frame to the frame that
+ * reports Ending (inclusive) or that falls back to Silence (exclusive). */
+AF_API int af_vad_segments(const uint8_t *states, uint64_t vad_stride, const uint32_t *n_frames,
+                           size_t n_streams, uint32_t *seg, uint32_t seg_cap, uint32_t *n_seg,
+                           void *cuda_stream);
+
+/* ---- host-side planning diagnostics (no GPU needed; used by the CPU test-suite) ---------- */
+/* smallest f32 energy e with 20*log10f(e) > threshold_db under the host libm (NaN if none):
+ * the device compares energies against this instead of taking a log (VAD). */
+AF_API float af_debug_vad_energy_threshold(float threshold_db);
+/* the f32 fractional offsets the host plan derives for the first n_chunks 128-frame chunks of
+ * an (input_rate -> output_rate) stream; returns the number of outputs (may exceed cap). */
+AF_API size_t af_debug_resample_plan(uint32_t input_rate, uint32_t output_rate, size_t n_chunks, float *frac,
+                                     size_t cap, int *mode);
+
+/* ---- streaming sessions (persistent per-stream state; BASELINE config 5) ---------------- */
+typedef struct af_session af_session;
+/* n_streams concurrent streams of one (rate, channels, format); state (resampler position,
+ * residual input, STFT overlap, VAD) stays on the device between ticks. */
+AF_API int af_session_create(af_pipeline *p, size_t n_streams, uint32_t sample_rate, uint16_t channels,
+                             uint16_t format, uint32_t max_tick_samples, af_session **out);
+AF_API void af_session_destroy(af_session *s);
+/* One tick: every stream pushes `n_samples` interleaved samples (device or host per `mem`,
+ * rows `in_stride` samples apart).  Outputs produced by this tick are appended at the row
+ * starts of `out`; counts (host arrays of n_streams, may be NULL) receive how many
+ * PCM samples / feature frames / VAD frames each stream emitted. */
+AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, uint32_t n_samples, int mem,
+                           const af_outputs *out, uint32_t *n_pcm, uint32_t *n_feat, uint32_t *n_vad);
+AF_API int af_session_reset(af_session *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIOFLOW_GPU_H */

@@ -1,0 +1,198 @@
+"""CPU tests of the oracle (oracle/oracle.c): the reference's own known-answer tests, structural
+properties of the restated resampler, the spec-defined feature path against numpy, and the
+committed golden vectors.  No GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KAT = json.load(open(os.path.join(HERE, "golden", "reference_kat.json")))
+STATE = {"Silence": 0, "Speech": 1, "Ending": 2}
+
+
+def _frame(spec):
+    return np.full(spec["len"], spec["value"], np.float32)
+
+
+def _vad_cfg(orc, d):
+    c = orc.default_vad_config()
+    for k, v in d.items():
+        setattr(c, k, v)
+    return c
+
+
+# ---- reference known-answer tests ----
+@pytest.mark.parametrize("case", KAT["to_mono"], ids=lambda c: c["src"])
+def test_kat_to_mono(orc, case):
+    out = orc.to_mono(case["samples"], case["channels"])
+    exp = np.array(case["expect"], np.float32)
+    assert len(out) == len(exp)
+    if case.get("exact"):
+        assert np.array_equal(out, exp)
+    else:
+        assert np.all(np.abs(out - exp) < case["tol"])
+
+
+def test_kat_resampler(orc):
+    for case in KAT["resampler"]:
+        r = orc.AudioResampler(case["in_rate"], case["out_rate"])
+        if "input" in case:
+            x = np.array(case["input"], np.float32)
+            assert np.array_equal(r.process(x), x)
+        if "needs_resampling" in case:
+            assert r.needs_resampling() == case["needs_resampling"]
+            assert r.input_rate() == case["in_rate"] and r.output_rate() == case["out_rate"]
+
+
+@pytest.mark.parametrize("case", KAT["vad"], ids=lambda c: c["src"])
+def test_kat_vad(orc, case):
+    v = orc.VoiceActivityDetector(_vad_cfg(orc, case["config"]))
+    assert v.state() == 0
+    got = [v.detect(_frame(f)) for f in case["frames"]]
+    assert got == [STATE[s] for s in case["expect"]]
+
+
+def test_kat_vad_reset(orc):
+    v = orc.VoiceActivityDetector()
+    v.detect(_frame(KAT["vad_reset"]["frame"]))
+    assert v.is_speaking()
+    v.reset()
+    assert v.state() == 0 and not v.is_speaking()
+
+
+def test_kat_energy(orc):
+    v = orc.VoiceActivityDetector()
+    for case in KAT["energy"]:
+        e = v.calculate_energy(_frame(case["frame"]))
+        if case.get("exact"):
+            assert e == case["expect"]
+        else:
+            assert abs(e - case["expect"]) < case["tol"]
+
+
+# ---- resampler restatement: structure (SURVEY.md 8(c) simulated consequences) ----
+def test_resampler_48k_counts_and_decimation(orc):
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(480000).astype(np.float32)
+    rs = orc.AudioResampler(48000, 16000)
+    counts = [len(rs.process(x[i * 128:(i + 1) * 128])) for i in range(7)]
+    assert counts == [40, 43, 43, 42, 43, 43, 42]
+    y = orc.resample_stream(x, 48000)
+    assert len(y) == 159998                       # ideal - 2 (resampler.rs flush does not drain the interpolator)
+    assert y[0] == 0.0                            # x[-1]
+    assert np.array_equal(y[1:], x[2:3 * len(y) - 1:3])   # y[n] = x[3n - 1]: pure decimation, bit exact
+    assert len(orc.resample_stream(np.zeros(1440000, np.float32), 48000)) == 479998
+
+
+def test_resampler_441_structure(orc):
+    x = np.random.default_rng(2).standard_normal(1323000).astype(np.float32)
+    y, frac = orc.resample_stream(x, 44100, return_frac=True)
+    assert len(y) == 480001
+    assert np.allclose(frac[:4], [0.75625, 0.5125, 0.26875, 0.025], atol=1e-6)   # positions -1.24375, 1.5125, ...
+    # a sine well below Nyquist is reproduced by the cubic interpolator
+    t = np.arange(44100) / 44100.0
+    s = np.sin(2 * np.pi * 440.0 * t).astype(np.float32)
+    ys = orc.resample_stream(s, 44100)
+    n = np.arange(len(ys))
+    pos = (-4 + (n + 1) * 441 / 160) / 44100.0
+    ref = np.sin(2 * np.pi * 440.0 * pos)
+    ok = (pos > 0.001) & (pos < 0.99)
+    assert np.max(np.abs(ys[ok] - ref[ok])) < 2e-4
+
+
+def test_resampler_short_input_errors(orc):
+    rs = orc.AudioResampler(48000, 16000)
+    with pytest.raises(orc.ResamplingFailed):
+        rs.process(np.zeros(100, np.float32))
+    # extra input beyond one chunk is ignored (rubato fixed-in semantics)
+    a = orc.AudioResampler(48000, 16000).process(np.arange(300, dtype=np.float32))
+    b = orc.AudioResampler(48000, 16000).process(np.arange(128, dtype=np.float32))
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("rate", [48000, 44100, 32000, 22050, 8000])
+def test_batch_resampler_chunking_invariance(orc, rate):
+    """BatchResampler output does not depend on how the input is split across process() calls."""
+    rng = np.random.default_rng(rate)
+    x = rng.standard_normal(20000).astype(np.float32)
+    whole = orc.resample_stream(x, rate)
+    b = orc.BatchResampler(rate, 16000)
+    parts, pos = [], 0
+    while pos < len(x):
+        n = int(rng.integers(1, 2000))
+        parts.append(b.process(x[pos:pos + n]))
+        pos += n
+    parts.append(b.flush())
+    assert np.array_equal(np.concatenate(parts), whole)
+
+
+def test_vad_ema_and_db(orc):
+    v = orc.VoiceActivityDetector()
+    v.detect(np.full(480, 0.5, np.float32))
+    assert abs(v.smoothed_energy() - 0.3 * 0.25) < 1e-7        # alpha * E + (1 - alpha) * 0
+    assert abs(v.energy_db() - 20 * np.log10(0.075)) < 1e-4     # 20*log10 applied to POWER (vad.rs:175)
+    assert orc.energy_to_dbfs(0.0) == -np.inf
+    # Ending swallows a speech frame (vad.rs:146-150)
+    c = _vad_cfg(orc, dict(silence_timeout_frames=1, min_speech_frames=1, smoothing_factor=0.0))
+    v = orc.VoiceActivityDetector(c)
+    sp, si = np.full(320, 0.5, np.float32), np.zeros(320, np.float32)
+    assert [v.detect(sp), v.detect(si), v.detect(sp), v.detect(sp)] == [1, 2, 0, 1]
+    # too-short speech is dropped
+    c = _vad_cfg(orc, dict(silence_timeout_frames=1, min_speech_frames=3, smoothing_factor=0.0))
+    v = orc.VoiceActivityDetector(c)
+    assert [v.detect(sp), v.detect(si)] == [1, 0]
+    assert v.detect(np.zeros(0, np.float32)) == 0               # empty frame -> energy 0.0
+
+
+# ---- spec-defined features against an independent numpy evaluation ----
+def test_logmel_matches_numpy(orc):
+    rng = np.random.default_rng(3)
+    y = (0.1 * rng.standard_normal(16000)).astype(np.float32)
+    cfg = orc.default_feat_config(80)
+    lm, pw = orc.logmel(y, cfg, return_power=True)
+    T = 1 + (16000 - 400) // 160
+    assert lm.shape == (T, 80)
+    w = orc.hann_window(400)
+    assert abs(w[0]) == 0 and abs(w[200] - 1.0) < 1e-7 and abs(w[100] - 0.5) < 1e-6
+    fb = orc.mel_filterbank(cfg)
+    frames = np.stack([y[f * 160:f * 160 + 400] * w for f in range(T)]).astype(np.float32)
+    P = np.abs(np.fft.rfft(frames.astype(np.float64), 512, axis=1)) ** 2
+    assert np.allclose(pw, P, rtol=1e-6, atol=1e-12)
+    ref = np.log(np.maximum(P @ fb.astype(np.float64), 1e-10))
+    assert np.max(np.abs(lm - ref)) < 1e-5
+    # filterbank sanity: triangles, peak <= 1, every bin in at most 2 filters
+    assert fb.min() >= 0 and fb.max() <= 1.0
+    assert (np.count_nonzero(fb, axis=1) <= 2).all()
+    # f32 CPU baseline path agrees with the f64 oracle within the stated tolerance
+    lm32 = orc.FeatPlan(cfg).logmel(y)
+    assert np.max(np.abs(lm32 - lm)) < 1e-4
+
+
+def test_pcm16(orc):
+    x = np.array([0.0, 1.0, -1.0, 2.0, -2.0, 0.5, -0.5, 1e-5, np.nan, 0.99999], np.float32)
+    assert orc.pcm16_encode(x).tolist() == [0, 32767, -32767, 32767, -32767, 16383, -16383, 0, 0, 32766]
+
+
+def test_segments(orc):
+    st = np.array([0, 1, 1, 1, 2, 0, 0, 1, 1, 0, 1], np.uint8)
+    assert orc.vad_segments(st).tolist() == [[1, 5], [7, 9], [10, 11]]
+
+
+# ---- committed golden vectors pin the oracle ----
+def test_oracle_matches_committed_golden(orc):
+    from audioflow import synth
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(os.path.join(HERE, "golden", "oracle_vectors.npz"))
+    for (sid, sec, rate, ch, fmt, mels) in mg.CASES:
+        x = synth.stream(sid, sec, rate, ch, fmt)
+        r = orc.pipeline_stream(x, ch, rate, orc.default_feat_config(mels), orc.default_vad_config(), 400, 160, fmt)
+        k = f"s{sid}"
+        assert np.array_equal(r["pcm"], g[k + "_pcm"])
+        assert np.array_equal(r["vad"], g[k + "_vad"])
+        assert np.array_equal(r["energy"], g[k + "_energy"])
+        assert np.max(np.abs(r["logmel"] - g[k + "_logmel"])) < 1e-6
