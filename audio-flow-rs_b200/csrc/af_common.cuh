@@ -18,10 +18,10 @@ constexpr int RS_CHUNK = 128;     // chunk_size
 constexpr int RS_POLY = 8;        // rubato POLYNOMIAL_LEN
 
 // ---- fused kernel tiling ----
-constexpr int SF = 32;                       // frames per step (one VAD warp lane per frame)
-constexpr int STEP_SAMPLES = SF * HOP;       // 5120 new 16 kHz samples per step
+constexpr int SF = 16;                       // frames per step: one per half-warp of the 8 FFT warps
+constexpr int STEP_SAMPLES = SF * HOP;       // 2560 new 16 kHz samples per step
 constexpr int CARRY = WIN - HOP;             // 240 samples shared with the next step
-constexpr int YLEN = STEP_SAMPLES + CARRY;   // 5360 samples live per step
+constexpr int YLEN = STEP_SAMPLES + CARRY;   // 2800 samples live per step
 constexpr int TILE_FRAMES = 128;             // frames per tile (work unit of one CTA)
 constexpr int TILE_SAMPLES = TILE_FRAMES * HOP;   // 20480
 constexpr int FFT_WARPS = 8;
@@ -35,7 +35,8 @@ constexpr int YBUF_FLOATS = ((ypad(YLEN + 32) + 31) / 32) * 32;
 
 constexpr int SCR_ROW = 18;                  // complex per transposed row (16 + 2 pad -> LDS.128 conflict free)
 constexpr int SCR_FLOATS_PER_FRAME = 16 * SCR_ROW * 2;   // 576 floats = 2304 B
-constexpr int PB_ROW = 36;                   // floats per power row: 32 frames + 4 pad
+constexpr int PB_ROW = SF + 4;               // floats per power row: 16 frames + 4 pad (16-byte aligned rows)
+constexpr int STAGE_BYTES = 34816;           // TMA-staged raw input of one step (34 KB)
 constexpr int PBUF_FLOATS = NBIN * PB_ROW;
 
 // formats / flags (mirror include/audioflow_gpu.h)
@@ -56,6 +57,8 @@ struct StreamDev {
     const float *frac;       // RS_TABLE: f32 fractional offsets by output index
     uint32_t tile_begin;     // first global tile of this stream
     uint32_t n_tiles;
+    uint32_t staged;         // 1: the step input fits the shared-memory stage (bulk-copy path)
+    uint32_t pad_;
 };
 enum : uint32_t { RS_PASSTHROUGH = 0, RS_EXACT = 1, RS_TABLE = 2 };
 
@@ -107,7 +110,8 @@ struct FusedParams {
     uint32_t n_mels;         // 0: skip STFT/mel
     uint32_t do_energy;      // VAD energies on the STFT frames
     float log_floor;
-    float log_scale;         // 1 (ln) or log10(e)
+    float log_scale;         // ln(2) (natural log) or log10(2): multiplies log2(mel)
+    uint32_t use_stage;      // 0: plain global loads everywhere ("sync" variant)
 };
 
 }  // namespace af

@@ -1,5 +1,7 @@
 // af_fused.cu -- the fused hot-path kernel for sm_100a:
-//   K1 downmix + cubic (rubato FastFixedIn) resample  -> 16 kHz tile in shared memory
+//   K1 downmix + cubic (rubato FastFixedIn) resample  -> 16 kHz step buffer in shared memory; the raw
+//      input of the NEXT step is staged into shared memory by a TMA bulk copy (cp.async.bulk +
+//      mbarrier) while the current step is in its FFT phase
 //   K2 Hann window + 512-point real FFT (packed 256-point complex, 16x16 in registers,
 //      one half-warp per frame, transposed through shared memory, Hermitian split by shuffles)
 //   K3 sparse banded mel projection + log
@@ -12,45 +14,194 @@
 
 namespace af {
 
-struct FusedSmem {
+struct __align__(128) FusedSmem {
+    unsigned char stage[STAGE_BYTES];                // raw interleaved input of one step (bulk-copy target)
     float ybuf[YBUF_FLOATS];                         // padded 16 kHz samples of the current step
-    float scr[16 * SCR_FLOATS_PER_FRAME];            // per half-warp transpose scratch / output stage
+    float scr[16 * SCR_FLOATS_PER_FRAME];            // per half-warp transpose scratch / log-mel stage
     float pbuf[PBUF_FLOATS];                         // 4*|X[k]|^2, [bin][frame]
     FftTables fft;
     MelTables mel;
     StreamDev stream;                                // descriptor of the tile's stream
+    unsigned long long mbar;                         // completion barrier of the in-flight stage fill
+    unsigned long long st_lo, st_hi;                 // interleaved element range [lo, hi) held by the stage
     int tile_k;                                      // floor(position) of the tile's first output
     uint32_t tile_rem;                               // and its remainder (numerator units)
     uint32_t inc_k, inc_rem;                         // position increment for FUSED_THREADS outputs
 };
 
+// ---- mbarrier / bulk-copy wrappers (PTX; SASS: SYNCS.*, UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- stage fill: issued by ONE thread for the step (tile, g); always completes one mbarrier phase ----
+__device__ __forceinline__ void issue_fill(FusedSmem &sm, const FusedParams &P, uint32_t tile, uint32_t g)
+{
+    const TileDev td = P.tiles[tile];
+    const StreamDev *sp = P.streams + td.stream;
+    const uint32_t n_out = sp->n_out, n_in = sp->n_in, mode = sp->mode, p = sp->p, q = sp->q;
+    const uint32_t ch = sp->channels, bps = sp->format == FMT_I16 ? 2u : 4u;
+    const unsigned long long n_samples = sp->n_samples;
+    unsigned long long lo = 0, hi = 0;
+    uint32_t bytes = 0;
+    const char *src = reinterpret_cast<const char *>(sp->data);
+    if (P.use_stage && sp->staged) {
+        const unsigned long long n_first = (unsigned long long)td.tile * TILE_SAMPLES + (unsigned long long)g * STEP_SAMPLES +
+                                           (g == 0 ? 0 : CARRY);
+        unsigned long long n_last = (unsigned long long)td.tile * TILE_SAMPLES + (unsigned long long)g * STEP_SAMPLES + YLEN;
+        if (n_last > n_out) n_last = n_out;
+        if (n_first < n_last) {
+            long long k0, k1;
+            if (mode == RS_PASSTHROUGH) { k0 = (long long)n_first; k1 = (long long)n_last - 1; }
+            else {
+                uint32_t r;
+                resample_pos(n_first, p, q, &k0, &r);
+                resample_pos(n_last - 1, p, q, &k1, &r);
+            }
+            long long i_lo = k0 - 2, i_hi = k1 + 3;              // taps k-1..k+2, and k-1 when the recurrence sits below an integer
+            if (i_lo < 0) i_lo = 0;
+            if (i_hi > (long long)n_in) i_hi = (long long)n_in;
+            if (i_lo < i_hi) {
+                unsigned long long b_lo = ((unsigned long long)i_lo * ch * bps) & ~15ull;
+                unsigned long long e_hi = (unsigned long long)i_hi * ch;
+                if (e_hi > n_samples) e_hi = n_samples;
+                unsigned long long b_hi = (e_hi * bps + 15ull) & ~15ull;
+                const unsigned long long b_end = (n_samples * bps) & ~15ull;   // never read past the stream's last full 16 bytes
+                if (b_hi > b_end) b_hi = b_end;
+                if (b_hi > b_lo && b_hi - b_lo <= (unsigned long long)STAGE_BYTES) {
+                    bytes = (uint32_t)(b_hi - b_lo);
+                    lo = b_lo / bps; hi = b_hi / bps;
+                    src += b_lo;
+                }
+            }
+        }
+    }
+    sm.st_lo = lo; sm.st_hi = hi;
+    if (bytes) {
+        mbar_arrive_expect_tx(&sm.mbar, bytes);
+        bulk_g2s(sm.stage, src, bytes, &sm.mbar);
+    } else {
+        mbar_arrive(&sm.mbar);
+    }
+}
+
+// ---- one mono input frame (downmixed) for the resampler, from the stage when it holds it ----
+enum { K_F32_1 = 0, K_I16_1 = 1, K_F32_2 = 2, K_I16_2 = 3, K_GENERIC = 4 };
+
+template <int KIND>
+__device__ __forceinline__ float tap(const FusedSmem &sm, const StreamDev &s, uint32_t st_lo, uint32_t st_hi, int idx)
+{
+    if ((uint32_t)idx >= s.n_in) return 0.0f;                        // also covers idx < 0
+    if (KIND == K_F32_1) {
+        const uint32_t e = (uint32_t)idx;
+        if (e >= st_lo && e < st_hi) return reinterpret_cast<const float *>(sm.stage)[e - st_lo];
+        return __ldg(reinterpret_cast<const float *>(s.data) + e);
+    } else if (KIND == K_I16_1) {
+        const uint32_t e = (uint32_t)idx;
+        short v;
+        if (e >= st_lo && e < st_hi) v = reinterpret_cast<const short *>(sm.stage)[e - st_lo];
+        else v = __ldg(reinterpret_cast<const short *>(s.data) + e);
+        return (float)v * (1.0f / 32768.0f);
+    } else if (KIND == K_F32_2) {
+        const uint32_t e = 2u * (uint32_t)idx;
+        if (e >= st_lo && e + 2 <= st_hi) {
+            const float2 v = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(sm.stage) + (e - st_lo));
+            return __fmul_rn(__fadd_rn(__fadd_rn(0.0f, v.x), v.y), 0.5f);
+        }
+        return load_mono(s.data, s.n_samples, s.n_in, 2, FMT_F32, idx);
+    } else if (KIND == K_I16_2) {
+        const uint32_t e = 2u * (uint32_t)idx;
+        if (e >= st_lo && e + 2 <= st_hi) {
+            const short2 v = *reinterpret_cast<const short2 *>(reinterpret_cast<const short *>(sm.stage) + (e - st_lo));
+            const float l = (float)v.x * (1.0f / 32768.0f), r = (float)v.y * (1.0f / 32768.0f);
+            return __fmul_rn(__fadd_rn(__fadd_rn(0.0f, l), r), 0.5f);
+        }
+        return load_mono(s.data, s.n_samples, s.n_in, 2, FMT_I16, idx);
+    } else {
+        return load_mono(s.data, s.n_samples, s.n_in, s.channels, s.format, idx);
+    }
+}
+
 // ---- phase 1: resample the 16 kHz samples [base + i_begin, base + YLEN) of the stream into ybuf ----
+template <int KIND>
 __device__ __forceinline__ void resample_step(FusedSmem &sm, const StreamDev &s, uint32_t tile_off, uint32_t base,
-                                              int i_begin, float inv_q)
+                                              int i_begin)
 {
     const int tid = threadIdx.x;
+    const uint32_t st_lo = (uint32_t)sm.st_lo, st_hi = (uint32_t)sm.st_hi;
+    const uint32_t n_out = s.n_out, mode = s.mode;
     int i = i_begin + tid;
-    if (s.mode == RS_PASSTHROUGH) {
+    if (mode == RS_PASSTHROUGH) {
         for (; i < YLEN; i += FUSED_THREADS) {
             const uint32_t n = base + i;
-            float v = 0.0f;
-            if (n < s.n_out) v = load_mono(s.data, s.n_samples, s.n_in, s.channels, s.format, (int)n);
-            sm.ybuf[ypad(i)] = v;
+            sm.ybuf[ypad(i)] = n < n_out ? tap<KIND>(sm, s, st_lo, st_hi, (int)n) : 0.0f;
         }
         return;
     }
     // exact integer position of this thread's first output, relative to the tile start
-    uint32_t a = sm.tile_rem + (tile_off + (uint32_t)i) * s.p;
+    const uint32_t q = s.q;
+    const uint32_t a = sm.tile_rem + (tile_off + (uint32_t)i) * s.p;
     uint32_t dk, rem;
-    if (s.q == 1) { dk = a; rem = 0; }
-    else { dk = a / s.q; rem = a - dk * s.q; }
+    if (q == 1) { dk = a; rem = 0; }
+    else { dk = a / q; rem = a - dk * q; }
     int k = sm.tile_k + (int)dk;
-    const uint32_t inc_k = sm.inc_k, inc_rem = sm.inc_rem, q = s.q;
+    const uint32_t inc_k = sm.inc_k, inc_rem = sm.inc_rem;
+    const float inv_q = 1.0f / (float)q;
+    const float *__restrict__ frac_tab = s.frac;
     for (; i < YLEN; i += FUSED_THREADS) {
         const uint32_t n = base + i;
         float v = 0.0f;
-        if (n < s.n_out)
-            v = resample_one(s.data, s.n_samples, s.n_in, s.channels, s.format, s.mode, inv_q, s.frac, n, k, rem);
+        if (n < n_out) {
+            int kk = k;
+            float frac;
+            if (mode == RS_TABLE) {
+                frac = __ldg(frac_tab + n);
+                kk += __float2int_rn((float)rem * inv_q - frac);      // -1 when the f64 recurrence sits just below an integer
+            } else {
+                frac = (float)rem * inv_q;                            // q is a power of two: exact
+            }
+            const float y0 = tap<KIND>(sm, s, st_lo, st_hi, kk - 1);
+            const float y1 = tap<KIND>(sm, s, st_lo, st_hi, kk);
+            const float y2 = tap<KIND>(sm, s, st_lo, st_hi, kk + 1);
+            const float y3 = tap<KIND>(sm, s, st_lo, st_hi, kk + 2);
+            // frac == 0 (48 kHz -> 16 kHz): a0 + a1*0 + a2*0 + a3*0 == y1 bit for bit whenever y1 != 0 and the
+            // coefficients are finite; only then skip the polynomial
+            const float big = (fabsf(y0) + fabsf(y1)) + (fabsf(y2) + fabsf(y3));   // NaN / Inf propagate
+            if (frac == 0.0f && y1 != 0.0f && big < 1e30f) v = y1;
+            else v = interp_cubic(frac, y0, y1, y2, y3);
+        }
         sm.ybuf[ypad(i)] = v;
         k += (int)inc_k;
         rem += inc_rem;
@@ -159,11 +310,12 @@ __device__ __forceinline__ float frame_energy_smem(const float *__restrict__ ybu
 
 __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedParams P)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l = lane & 15, half = lane >> 4;
     const uint32_t M = P.n_mels;
+    const bool is_filler = (tid == FUSED_THREADS - 1);              // last lane of the VAD warp (it has no frame)
 
     // constant tables -> shared memory (once per CTA)
     {
@@ -176,9 +328,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
             for (int i = tid; i < (int)(sizeof(MelTables) / 4); i += FUSED_THREADS) md[i] = ms[i];
         }
     }
+    if (is_filler) {
+        mbar_init(&sm.mbar, 1);
+        if (blockIdx.x < P.n_tiles) issue_fill(sm, P, blockIdx.x, 0);
+    }
     __syncthreads();
     const uint32_t pitch = M | 1u;                      // odd row pitch of the log-mel stage
-    float *stage = sm.scr;
+    float *stage_lm = sm.scr;
+    const float log_mul = P.log_scale;
+    uint32_t fill_parity = 0;
 
     for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         const TileDev td = P.tiles[tile];
@@ -190,7 +348,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
         const uint32_t tile_end = min(n_tile0 + (uint32_t)TILE_SAMPLES, s.n_out);
         const uint32_t f_tile0 = td.tile * TILE_FRAMES;
         const uint32_t n_steps = (tile_end - n_tile0 + STEP_SAMPLES - 1) / STEP_SAMPLES;
-        const float inv_q = 1.0f / (float)s.q;
         if (tid == 0 && s.mode != RS_PASSTHROUGH) {
             long long k; uint32_t rem;
             resample_pos(n_tile0, s.p, s.q, &k, &rem);
@@ -199,6 +356,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
             sm.inc_k = inc / s.q; sm.inc_rem = inc % s.q;
         }
         __syncthreads();
+        int kind = K_GENERIC;
+        if (s.channels == 1) kind = s.format == FMT_F32 ? K_F32_1 : K_I16_1;
+        else if (s.channels == 2) kind = s.format == FMT_F32 ? K_F32_2 : K_I16_2;
         float *pcm_row = P.pcm ? P.pcm + (uint64_t)td.stream * P.pcm_stride : nullptr;
         float *lm_row = P.logmel ? P.logmel + (uint64_t)td.stream * P.logmel_stride : nullptr;
         float *en_row = P.energy ? P.energy + (uint64_t)td.stream * P.energy_stride : nullptr;
@@ -208,11 +368,24 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
             const uint32_t f0 = f_tile0 + g * SF;                   // first frame of the step
             const int n_valid = f0 < s.n_frames ? (int)min((uint32_t)SF, s.n_frames - f0) : 0;
 
-            // ---- phase 1: resample (first step of a tile also recomputes the 240-sample halo) ----
-            resample_step(sm, s, g * STEP_SAMPLES, base, g == 0 ? 0 : CARRY, inv_q);
+            // ---- phase 1: wait for the staged input, resample (first step of a tile also recomputes the halo) ----
+            mbar_wait(&sm.mbar, fill_parity);
+            fill_parity ^= 1u;
+            const int i_begin = g == 0 ? 0 : CARRY;
+            switch (kind) {
+            case K_F32_1: resample_step<K_F32_1>(sm, s, g * STEP_SAMPLES, base, i_begin); break;
+            case K_I16_1: resample_step<K_I16_1>(sm, s, g * STEP_SAMPLES, base, i_begin); break;
+            case K_F32_2: resample_step<K_F32_2>(sm, s, g * STEP_SAMPLES, base, i_begin); break;
+            case K_I16_2: resample_step<K_I16_2>(sm, s, g * STEP_SAMPLES, base, i_begin); break;
+            default: resample_step<K_GENERIC>(sm, s, g * STEP_SAMPLES, base, i_begin); break;
+            }
             __syncthreads();
 
-            // ---- phase 2: PCM write-out, FFT (warps 0..7), energies (warp 8) ----
+            // ---- phase 2: next stage fill (async), PCM write-out, FFT (warps 0..7), energies (warp 8) ----
+            if (is_filler) {
+                if (g + 1 < n_steps) issue_fill(sm, P, tile, g + 1);
+                else if (tile + gridDim.x < P.n_tiles) issue_fill(sm, P, tile + gridDim.x, 0);
+            }
             if (pcm_row) {
                 const uint32_t own_end = min(base + (uint32_t)STEP_SAMPLES, tile_end);
                 for (uint32_t i4 = tid * 4; base + i4 < own_end; i4 += FUSED_THREADS * 4) {
@@ -228,14 +401,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
             }
             if (n_valid > 0) {
                 if (warp < FFT_WARPS) {
-                    if (M) {
-#pragma unroll 1
-                        for (int round = 0; round < 2; ++round) {
-                            const int hw = warp * 2 + half;
-                            const int q = round * 16 + hw;
-                            if (round * 16 + warp * 2 < n_valid)     // warp-uniform: skip fully invalid pairs
-                                fft_frame(sm, sm.scr + hw * SCR_FLOATS_PER_FRAME, q, l, lane);
-                        }
+                    if (M && warp * 2 < n_valid) {                    // warp-uniform: skip fully invalid pairs
+                        const int hw = warp * 2 + half;
+                        fft_frame(sm, sm.scr + hw * SCR_FLOATS_PER_FRAME, hw, l, lane);
                     }
                 } else if (P.do_energy && en_row) {
                     if (lane < n_valid) en_row[f0 + lane] = frame_energy_smem(sm.ybuf, lane);
@@ -246,9 +414,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
             // ---- phase 3: carry the 240-sample overlap forward; mel + log into the stage ----
             if (g + 1 < n_steps && tid < CARRY) sm.ybuf[ypad(tid)] = sm.ybuf[ypad(tid) + ypad(STEP_SAMPLES)];
             if (M && n_valid > 0) {
-                const int n_items = (int)M * 8;
+                const int n_items = (int)M * (SF / 4);
                 for (int item = tid; item < n_items; item += FUSED_THREADS) {
-                    const int m = item >> 3, fq = item & 7;
+                    const int m = item >> 2, fq = item & 3;
                     if (fq * 4 >= n_valid) continue;
                     const int lo = sm.mel.lo[m], cnt = sm.mel.cnt[m];
                     const float *w = sm.mel.w + sm.mel.off[m];
@@ -260,11 +428,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
                         a0 = fmaf(wj, p4.x, a0); a1 = fmaf(wj, p4.y, a1);
                         a2 = fmaf(wj, p4.z, a2); a3 = fmaf(wj, p4.w, a3);
                     }
-                    float *st = stage + (4 * fq) * pitch + m;
-                    st[0] = logf(fmaxf(a0, P.log_floor)) * P.log_scale;
-                    st[pitch] = logf(fmaxf(a1, P.log_floor)) * P.log_scale;
-                    st[2 * pitch] = logf(fmaxf(a2, P.log_floor)) * P.log_scale;
-                    st[3 * pitch] = logf(fmaxf(a3, P.log_floor)) * P.log_scale;
+                    float *st = stage_lm + (4 * fq) * pitch + m;
+                    st[0] = __log2f(fmaxf(a0, P.log_floor)) * log_mul;
+                    st[pitch] = __log2f(fmaxf(a1, P.log_floor)) * log_mul;
+                    st[2 * pitch] = __log2f(fmaxf(a2, P.log_floor)) * log_mul;
+                    st[3 * pitch] = __log2f(fmaxf(a3, P.log_floor)) * log_mul;
                 }
             }
             __syncthreads();
@@ -272,11 +440,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
             // ---- phase 4: coalesced copy-out of the step's [n_valid][M] log-mel block ----
             if (M && n_valid > 0 && lm_row) {
                 float *dst = lm_row + (uint64_t)f0 * M;
-                const int total = n_valid * (int)M;
-                for (int e = tid; e < total; e += FUSED_THREADS) {
-                    const int f = e / (int)M, m = e - f * (int)M;
-                    dst[e] = stage[f * pitch + m];
-                }
+                for (int f = warp; f < n_valid; f += FUSED_WARPS)
+                    for (int m = lane; m < (int)M; m += 32) dst[f * (int)M + m] = stage_lm[f * pitch + m];
             }
             // the barrier after the next phase 1 (or the tile prologue) orders stage/pbuf reuse
         }

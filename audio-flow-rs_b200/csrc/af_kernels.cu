@@ -99,6 +99,9 @@ cudaError_t launch_frame_energy(const EnergyJob &job, cudaStream_t st)
 }
 
 // ---- detect() EMA + threshold + state machine (vad.rs:101-153): strictly sequential per stream ----
+// One thread per stream.  The dependent chain is ~3 FP32 ops + a few integer ops per frame; the kernel is
+// latency bound, so energies are fetched 16 frames ahead as 4 x float4 (software pipelined) and the states
+// leave as one 16-byte store per 16 frames.
 __global__ void af_vad_scan_kernel(const ScanJob J)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,19 +112,42 @@ __global__ void af_vad_scan_kernel(const ScanJob J)
     VadState v;
     if (J.state_io) v = J.state_io[s];
     else { v.smoothed = 0.0f; v.state = 0; v.silence_frames = 0; v.speech_frames = 0; }
+    const VadParams prm = J.prm;
     uint32_t f = 0;
-    for (; f + 8 <= T; f += 8) {                 // batch the loads so the chain is not memory-latency bound
-        float eb[8];
+    const bool vec_in = ((reinterpret_cast<uintptr_t>(e) & 15) == 0);
+    const bool vec_out = out && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (vec_in && T >= 16) {
+        const float4 *e4 = reinterpret_cast<const float4 *>(e);
+        float4 nb[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) eb[j] = e[f + j];
+        for (int j = 0; j < 4; ++j) nb[j] = e4[j];
+        for (; f + 16 <= T; f += 16) {
+            float4 cb[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int st = vad_step(v, J.prm, eb[j]);
-            if (out) out[f + j] = (uint8_t)st;
+            for (int j = 0; j < 4; ++j) cb[j] = nb[j];
+            if (f + 32 <= T) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) nb[j] = e4[(f + 16) / 4 + j];       // prefetch the next 16 frames
+            }
+            uint32_t packed[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t s0 = (uint32_t)vad_step(v, prm, cb[j].x);
+                const uint32_t s1 = (uint32_t)vad_step(v, prm, cb[j].y);
+                const uint32_t s2 = (uint32_t)vad_step(v, prm, cb[j].z);
+                const uint32_t s3 = (uint32_t)vad_step(v, prm, cb[j].w);
+                packed[j] = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+            }
+            if (vec_out) {
+                *reinterpret_cast<uint4 *>(out + f) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            } else if (out) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) out[f + j] = (uint8_t)(packed[j >> 2] >> (8 * (j & 3)));
+            }
         }
     }
     for (; f < T; ++f) {
-        const int st = vad_step(v, J.prm, e[f]);
+        const int st = vad_step(v, prm, e[f]);
         if (out) out[f] = (uint8_t)st;
     }
     if (J.state_io) J.state_io[s] = v;

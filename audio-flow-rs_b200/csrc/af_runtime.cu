@@ -680,6 +680,11 @@ int build_sub(af_batch *b, SubBatch &sb, const void *slot_in_base)
         d.channels = hs.desc.channels; d.format = hs.desc.format;
         d.p = hs.p; d.q = hs.q; d.mode = hs.mode;
         d.frac = hs.table ? hs.table->d : nullptr;
+        {   // does the raw input of one step fit the shared-memory stage of the fused kernel?
+            const uint64_t bps = hs.desc.format == AF_FMT_I16 ? 2 : 4;
+            const uint64_t frames = hs.mode == RS_PASSTHROUGH ? (uint64_t)YLEN : ((uint64_t)YLEN * hs.p + hs.q - 1) / hs.q;
+            d.staged = hs.desc.channels <= 2 && (frames + 8) * hs.desc.channels * bps + 32 <= (uint64_t)STAGE_BYTES;
+        }
         d.tile_begin = (uint32_t)sb.h_tiles.size();
         d.n_tiles = (hs.n_out + TILE_SAMPLES - 1) / TILE_SAMPLES;
         for (uint32_t t = 0; t < d.n_tiles; ++t) sb.h_tiles.push_back(TileDev{(uint32_t)i, t});
@@ -717,7 +722,8 @@ int run_sub(af_batch *b, SubBatch &sb, float *pcm, uint64_t pcm_stride, float *l
         P.n_mels = (cfg.n_mels && logmel) ? cfg.n_mels : 0;
         P.do_energy = stft_vad ? 1 : 0;
         P.log_floor = cfg.log_floor;
-        P.log_scale = cfg.log10 ? 0.43429448190325176f : 1.0f;
+        P.log_scale = cfg.log10 ? 0.30102999566398120f : 0.69314718055994531f;   // log10(2) : ln(2)
+        P.use_stage = g_ctx.variant == "sync" ? 0u : 1u;
         const int n_ctas = (int)std::min<size_t>(sb.h_tiles.size(), (size_t)g_ctx.sm_count * 2);
         AF_CUDA(launch_fused(P, n_ctas, st));
         count_launch();

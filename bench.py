@@ -232,7 +232,7 @@ def main():
     pipe, batch, outs, bufs = make(False)
     audio_s_per_step_rank = S * SECONDS
     summary = torch.tensor(np.stack([batch.n_out[:S], batch.n_feat[:S]], 1).astype(np.int32), device=dev)
-    gathered = torch.empty((world,) + tuple(summary.shape), device=dev, dtype=torch.int32) if world > 1 else None
+    gathered = torch.empty((world * summary.shape[0], summary.shape[1]), device=dev, dtype=torch.int32) if world > 1 else None
     stream = torch.cuda.current_stream()
 
     def step(b, o):
