@@ -24,6 +24,7 @@ struct __align__(128) FusedSmem {
     StreamDev stream;                                // descriptor of the tile's stream
     unsigned long long mbar;                         // completion barrier of the in-flight stage fill
     unsigned long long st_lo, st_hi;                 // interleaved element range [lo, hi) held by the stage
+    uint32_t st_interior;                            // 1: every tap of the step is inside the stage and the stream
     int tile_k;                                      // floor(position) of the tile's first output
     uint32_t tile_rem;                               // and its remainder (numerator units)
     uint32_t inc_k, inc_rem;                         // position increment for FUSED_THREADS outputs
@@ -66,6 +67,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  : "memory");
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 // ---- stage fill: issued by ONE thread for the step (tile, g); always completes one mbarrier phase ----
 __device__ __forceinline__ void issue_fill(FusedSmem &sm, const FusedParams &P, uint32_t tile, uint32_t g)
 {
@@ -75,7 +85,7 @@ __device__ __forceinline__ void issue_fill(FusedSmem &sm, const FusedParams &P, 
     const uint32_t ch = sp->channels, bps = sp->format == FMT_I16 ? 2u : 4u;
     const unsigned long long n_samples = sp->n_samples;
     unsigned long long lo = 0, hi = 0;
-    uint32_t bytes = 0;
+    uint32_t bytes = 0, interior = 0;
     const char *src = reinterpret_cast<const char *>(sp->data);
     if (P.use_stage && sp->staged) {
         const unsigned long long n_first = (unsigned long long)td.tile * TILE_SAMPLES + (unsigned long long)g * STEP_SAMPLES +
@@ -104,11 +114,15 @@ __device__ __forceinline__ void issue_fill(FusedSmem &sm, const FusedParams &P, 
                     bytes = (uint32_t)(b_hi - b_lo);
                     lo = b_lo / bps; hi = b_hi / bps;
                     src += b_lo;
+                    // interior step: no tap leaves the stream or the stage, no output beyond n_out
+                    interior = (k0 - 2 >= 0) && (k1 + 3 <= (long long)n_in) &&
+                               ((unsigned long long)(k1 + 3) * ch <= hi) && ((unsigned long long)(k1 + 3) * ch <= n_samples) &&
+                               (n_last == (unsigned long long)td.tile * TILE_SAMPLES + (unsigned long long)g * STEP_SAMPLES + YLEN);
                 }
             }
         }
     }
-    sm.st_lo = lo; sm.st_hi = hi;
+    sm.st_lo = lo; sm.st_hi = hi; sm.st_interior = interior;
     if (bytes) {
         mbar_arrive_expect_tx(&sm.mbar, bytes);
         bulk_g2s(sm.stage, src, bytes, &sm.mbar);
@@ -151,6 +165,75 @@ __device__ __forceinline__ float tap(const FusedSmem &sm, const StreamDev &s, ui
         return load_mono(s.data, s.n_samples, s.n_in, 2, FMT_I16, idx);
     } else {
         return load_mono(s.data, s.n_samples, s.n_in, s.channels, s.format, idx);
+    }
+}
+
+// unchecked tap for interior steps: `off` = mono frame index relative to the first staged frame
+template <int KIND>
+__device__ __forceinline__ float tap_fast(const unsigned char *stage, int off)
+{
+    if (KIND == K_F32_1) return reinterpret_cast<const float *>(stage)[off];
+    if (KIND == K_I16_1) return (float)reinterpret_cast<const short *>(stage)[off] * (1.0f / 32768.0f);
+    if (KIND == K_F32_2) {
+        const float2 v = reinterpret_cast<const float2 *>(stage)[off];
+        return __fmul_rn(__fadd_rn(__fadd_rn(0.0f, v.x), v.y), 0.5f);
+    }
+    const short2 v = reinterpret_cast<const short2 *>(stage)[off];
+    const float l = (float)v.x * (1.0f / 32768.0f), r = (float)v.y * (1.0f / 32768.0f);
+    return __fmul_rn(__fadd_rn(__fadd_rn(0.0f, l), r), 0.5f);
+}
+
+// ---- phase 1, interior steps: every tap comes unchecked from the stage ----
+template <int KIND>
+__device__ __forceinline__ void resample_step_fast(FusedSmem &sm, const StreamDev &s, uint32_t tile_off, uint32_t base,
+                                                   int i_begin)
+{
+    const int tid = threadIdx.x;
+    const uint32_t mode = s.mode;
+    const int ch = (KIND == K_F32_2 || KIND == K_I16_2) ? 2 : 1;
+    const int f_lo = (int)((uint32_t)sm.st_lo / ch);                 // first staged mono frame
+    int i = i_begin + tid;
+    if (mode == RS_PASSTHROUGH) {
+        for (; i < YLEN; i += FUSED_THREADS) sm.ybuf[ypad(i)] = tap_fast<KIND>(sm.stage, (int)(base + i) - f_lo);
+        return;
+    }
+    const uint32_t q = s.q;
+    const uint32_t a = sm.tile_rem + (tile_off + (uint32_t)i) * s.p;
+    if (q == 1) {
+        // integer step (48 kHz -> 16 kHz): frac == 0 exactly; the cubic returns y1 bit for bit whenever y1 != 0 and
+        // the coefficients are finite -- checked per sample, everything else takes the polynomial
+        int o = sm.tile_k + (int)a - 1 - f_lo;
+        const int inc = (int)sm.inc_k;
+        for (; i < YLEN; i += FUSED_THREADS, o += inc) {
+            const float y0 = tap_fast<KIND>(sm.stage, o), y1 = tap_fast<KIND>(sm.stage, o + 1);
+            const float y2 = tap_fast<KIND>(sm.stage, o + 2), y3 = tap_fast<KIND>(sm.stage, o + 3);
+            const float big = (fabsf(y0) + fabsf(y1)) + (fabsf(y2) + fabsf(y3));   // NaN / Inf propagate
+            float v = y1;
+            if (!(y1 != 0.0f && big < 1e30f)) v = interp_cubic(0.0f, y0, y1, y2, y3);
+            sm.ybuf[ypad(i)] = v;
+        }
+        return;
+    }
+    uint32_t dk = a / q, rem = a - dk * q;
+    int k = sm.tile_k + (int)dk - 1 - f_lo;
+    const uint32_t inc_k = sm.inc_k, inc_rem = sm.inc_rem;
+    const float inv_q = 1.0f / (float)q;
+    const float *__restrict__ frac_tab = s.frac + base;
+    for (; i < YLEN; i += FUSED_THREADS) {
+        int o = k;
+        float frac;
+        if (mode == RS_TABLE) {
+            frac = __ldg(frac_tab + i);
+            o += __float2int_rn((float)rem * inv_q - frac);           // -1 when the f64 recurrence sits just below an integer
+        } else {
+            frac = (float)rem * inv_q;                                // q is a power of two: exact
+        }
+        const float y0 = tap_fast<KIND>(sm.stage, o), y1 = tap_fast<KIND>(sm.stage, o + 1);
+        const float y2 = tap_fast<KIND>(sm.stage, o + 2), y3 = tap_fast<KIND>(sm.stage, o + 3);
+        sm.ybuf[ypad(i)] = interp_cubic(frac, y0, y1, y2, y3);
+        k += (int)inc_k;
+        rem += inc_rem;
+        if (rem >= q) { rem -= q; k += 1; }
     }
 }
 
@@ -333,7 +416,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
         if (blockIdx.x < P.n_tiles) issue_fill(sm, P, blockIdx.x, 0);
     }
     __syncthreads();
-    const uint32_t pitch = M | 1u;                      // odd row pitch of the log-mel stage
+    const uint32_t pitch = M + 4u;                      // row pitch of the log-mel stage (16-byte aligned rows)
     float *stage_lm = sm.scr;
     const float log_mul = P.log_scale;
     uint32_t fill_parity = 0;
@@ -372,78 +455,110 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
             mbar_wait(&sm.mbar, fill_parity);
             fill_parity ^= 1u;
             const int i_begin = g == 0 ? 0 : CARRY;
-            switch (kind) {
-            case K_F32_1: resample_step<K_F32_1>(sm, s, g * STEP_SAMPLES, base, i_begin); break;
-            case K_I16_1: resample_step<K_I16_1>(sm, s, g * STEP_SAMPLES, base, i_begin); break;
-            case K_F32_2: resample_step<K_F32_2>(sm, s, g * STEP_SAMPLES, base, i_begin); break;
-            case K_I16_2: resample_step<K_I16_2>(sm, s, g * STEP_SAMPLES, base, i_begin); break;
-            default: resample_step<K_GENERIC>(sm, s, g * STEP_SAMPLES, base, i_begin); break;
+            const uint32_t toff = g * STEP_SAMPLES;
+            if (sm.st_interior) {
+                switch (kind) {
+                case K_F32_1: resample_step_fast<K_F32_1>(sm, s, toff, base, i_begin); break;
+                case K_I16_1: resample_step_fast<K_I16_1>(sm, s, toff, base, i_begin); break;
+                case K_F32_2: resample_step_fast<K_F32_2>(sm, s, toff, base, i_begin); break;
+                default: resample_step_fast<K_I16_2>(sm, s, toff, base, i_begin); break;
+                }
+            } else {
+                switch (kind) {
+                case K_F32_1: resample_step<K_F32_1>(sm, s, toff, base, i_begin); break;
+                case K_I16_1: resample_step<K_I16_1>(sm, s, toff, base, i_begin); break;
+                case K_F32_2: resample_step<K_F32_2>(sm, s, toff, base, i_begin); break;
+                case K_I16_2: resample_step<K_I16_2>(sm, s, toff, base, i_begin); break;
+                default: resample_step<K_GENERIC>(sm, s, toff, base, i_begin); break;
+                }
             }
             __syncthreads();
 
-            // ---- phase 2: next stage fill (async), PCM write-out, FFT (warps 0..7), energies (warp 8) ----
-            if (is_filler) {
-                if (g + 1 < n_steps) issue_fill(sm, P, tile, g + 1);
-                else if (tile + gridDim.x < P.n_tiles) issue_fill(sm, P, tile + gridDim.x, 0);
-            }
-            if (pcm_row) {
-                const uint32_t own_end = min(base + (uint32_t)STEP_SAMPLES, tile_end);
-                for (uint32_t i4 = tid * 4; base + i4 < own_end; i4 += FUSED_THREADS * 4) {
-                    const float4 v = *reinterpret_cast<const float4 *>(sm.ybuf + ypad((int)i4));
-                    const uint32_t n = base + i4;
-                    if (n + 4 <= own_end) {
-                        *reinterpret_cast<float4 *>(pcm_row + n) = v;
+            if (warp == FFT_WARPS) {
+                // ================= VAD warp: runs beside phases 2-4 of the FFT warps =================
+                if (is_filler) {                                      // next stage fill (async bulk copy)
+                    if (g + 1 < n_steps) issue_fill(sm, P, tile, g + 1);
+                    else if (tile + gridDim.x < P.n_tiles) issue_fill(sm, P, tile + gridDim.x, 0);
+                }
+                if (P.do_energy && en_row && lane < n_valid) en_row[f0 + lane] = frame_energy_smem(sm.ybuf, lane);
+                __syncwarp();
+                named_bar_sync(2, FUSED_THREADS);                     // every FFT warp is done reading ybuf
+                if (g + 1 < n_steps) {                                // carry the 240-sample overlap forward
+                    for (int i = lane; i < CARRY; i += 32) sm.ybuf[ypad(i)] = sm.ybuf[ypad(i) + ypad(STEP_SAMPLES)];
+                }
+            } else {
+                // ================= FFT warps (256 threads) =================
+                // ---- phase 2: PCM write-out, one frame per half-warp ----
+                if (pcm_row) {
+                    const uint32_t own_end = min(base + (uint32_t)STEP_SAMPLES, tile_end);
+                    for (uint32_t i4 = tid * 4; base + i4 < own_end; i4 += FFT_WARPS * 32 * 4) {
+                        const float4 v = *reinterpret_cast<const float4 *>(sm.ybuf + ypad((int)i4));
+                        const uint32_t n = base + i4;
+                        if (n + 4 <= own_end) {
+                            *reinterpret_cast<float4 *>(pcm_row + n) = v;
+                        } else {
+                            if (n < own_end) pcm_row[n] = v.x;
+                            if (n + 1 < own_end) pcm_row[n + 1] = v.y;
+                            if (n + 2 < own_end) pcm_row[n + 2] = v.z;
+                        }
+                    }
+                }
+                if (M && warp * 2 < n_valid) {                        // warp-uniform: skip fully invalid pairs
+                    const int hw = warp * 2 + half;
+                    fft_frame(sm, sm.scr + hw * SCR_FLOATS_PER_FRAME, hw, l, lane);
+                }
+                __syncwarp();
+                named_bar_arrive(2, FUSED_THREADS);                   // ybuf no longer needed by this warp
+                named_bar_sync(1, FFT_WARPS * 32);                    // pbuf complete
+
+                // ---- phase 3: mel + log into the stage (thread = filter x 4 frames) ----
+                if (M && n_valid > 0) {
+                    const int n_items = (int)M * (SF / 4);
+                    for (int item = tid; item < n_items; item += FFT_WARPS * 32) {
+                        const int m = item >> 2, fq = item & 3;
+                        if (fq * 4 >= n_valid) continue;
+                        const int lo = sm.mel.lo[m], cnt = sm.mel.cnt[m];
+                        const float *w = sm.mel.w + sm.mel.off[m];
+                        const float *pp = sm.pbuf + lo * PB_ROW + 4 * fq;
+                        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                        int j = 0;
+                        for (; j + 2 <= cnt; j += 2) {
+                            const float w0 = w[j], w1 = w[j + 1];
+                            const float4 p0 = *reinterpret_cast<const float4 *>(pp + j * PB_ROW);
+                            const float4 p1 = *reinterpret_cast<const float4 *>(pp + (j + 1) * PB_ROW);
+                            a0 = fmaf(w0, p0.x, a0); a1 = fmaf(w0, p0.y, a1); a2 = fmaf(w0, p0.z, a2); a3 = fmaf(w0, p0.w, a3);
+                            a0 = fmaf(w1, p1.x, a0); a1 = fmaf(w1, p1.y, a1); a2 = fmaf(w1, p1.z, a2); a3 = fmaf(w1, p1.w, a3);
+                        }
+                        if (j < cnt) {
+                            const float w0 = w[j];
+                            const float4 p0 = *reinterpret_cast<const float4 *>(pp + j * PB_ROW);
+                            a0 = fmaf(w0, p0.x, a0); a1 = fmaf(w0, p0.y, a1); a2 = fmaf(w0, p0.z, a2); a3 = fmaf(w0, p0.w, a3);
+                        }
+                        float *st = stage_lm + (4 * fq) * pitch + m;
+                        st[0] = __log2f(fmaxf(a0, P.log_floor)) * log_mul;
+                        st[pitch] = __log2f(fmaxf(a1, P.log_floor)) * log_mul;
+                        st[2 * pitch] = __log2f(fmaxf(a2, P.log_floor)) * log_mul;
+                        st[3 * pitch] = __log2f(fmaxf(a3, P.log_floor)) * log_mul;
+                    }
+                }
+                named_bar_sync(1, FFT_WARPS * 32);
+
+                // ---- phase 4: coalesced copy-out of the step's [n_valid][M] log-mel block ----
+                if (M && n_valid > 0 && lm_row) {
+                    float *dst = lm_row + (uint64_t)f0 * M;
+                    if ((M & 3) == 0) {
+                        const int m4 = (int)M >> 2;
+                        for (int f = warp; f < n_valid; f += FFT_WARPS)
+                            if (lane < m4)
+                                reinterpret_cast<float4 *>(dst + f * (int)M)[lane] =
+                                    *reinterpret_cast<const float4 *>(stage_lm + f * pitch + 4 * lane);
                     } else {
-                        const float e[4] = {v.x, v.y, v.z, v.w};
-                        for (uint32_t c = 0; n + c < own_end; ++c) pcm_row[n + c] = e[c];
+                        for (int f = warp; f < n_valid; f += FFT_WARPS)
+                            for (int m = lane; m < (int)M; m += 32) dst[f * (int)M + m] = stage_lm[f * pitch + m];
                     }
                 }
             }
-            if (n_valid > 0) {
-                if (warp < FFT_WARPS) {
-                    if (M && warp * 2 < n_valid) {                    // warp-uniform: skip fully invalid pairs
-                        const int hw = warp * 2 + half;
-                        fft_frame(sm, sm.scr + hw * SCR_FLOATS_PER_FRAME, hw, l, lane);
-                    }
-                } else if (P.do_energy && en_row) {
-                    if (lane < n_valid) en_row[f0 + lane] = frame_energy_smem(sm.ybuf, lane);
-                }
-            }
-            __syncthreads();
-
-            // ---- phase 3: carry the 240-sample overlap forward; mel + log into the stage ----
-            if (g + 1 < n_steps && tid < CARRY) sm.ybuf[ypad(tid)] = sm.ybuf[ypad(tid) + ypad(STEP_SAMPLES)];
-            if (M && n_valid > 0) {
-                const int n_items = (int)M * (SF / 4);
-                for (int item = tid; item < n_items; item += FUSED_THREADS) {
-                    const int m = item >> 2, fq = item & 3;
-                    if (fq * 4 >= n_valid) continue;
-                    const int lo = sm.mel.lo[m], cnt = sm.mel.cnt[m];
-                    const float *w = sm.mel.w + sm.mel.off[m];
-                    const float *pp = sm.pbuf + lo * PB_ROW + 4 * fq;
-                    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-                    for (int j = 0; j < cnt; ++j) {
-                        const float wj = w[j];
-                        const float4 p4 = *reinterpret_cast<const float4 *>(pp + j * PB_ROW);
-                        a0 = fmaf(wj, p4.x, a0); a1 = fmaf(wj, p4.y, a1);
-                        a2 = fmaf(wj, p4.z, a2); a3 = fmaf(wj, p4.w, a3);
-                    }
-                    float *st = stage_lm + (4 * fq) * pitch + m;
-                    st[0] = __log2f(fmaxf(a0, P.log_floor)) * log_mul;
-                    st[pitch] = __log2f(fmaxf(a1, P.log_floor)) * log_mul;
-                    st[2 * pitch] = __log2f(fmaxf(a2, P.log_floor)) * log_mul;
-                    st[3 * pitch] = __log2f(fmaxf(a3, P.log_floor)) * log_mul;
-                }
-            }
-            __syncthreads();
-
-            // ---- phase 4: coalesced copy-out of the step's [n_valid][M] log-mel block ----
-            if (M && n_valid > 0 && lm_row) {
-                float *dst = lm_row + (uint64_t)f0 * M;
-                for (int f = warp; f < n_valid; f += FUSED_WARPS)
-                    for (int m = lane; m < (int)M; m += 32) dst[f * (int)M + m] = stage_lm[f * pitch + m];
-            }
-            // the barrier after the next phase 1 (or the tile prologue) orders stage/pbuf reuse
+            __syncthreads();        // ybuf carried, log-mel stage consumed: the next phase 1 may overwrite both
         }
         __syncthreads();
     }
