@@ -481,3 +481,52 @@ class Batch:
                                       speech_frames=int(f.speech_frames), silence_frames=int(f.silence_frames))
             res.append(r)
         return res
+
+
+# ---------------------------------------------------------------------------------------------
+# streaming sessions (BASELINE config 5)
+# ---------------------------------------------------------------------------------------------
+class Session:
+    """n_streams lockstep streams with persistent device state (resampler position + residual input,
+    STFT overlap, VAD).  push() takes host arrays [n_streams, n_samples] and returns per-tick outputs."""
+
+    def __init__(self, pipe: Pipeline, n_streams: int, sample_rate: int, channels: int = 1, fmt: int = AF_FMT_F32,
+                 max_tick_samples: int = 4096):
+        self.pipe, self.S, self.rate, self.channels, self.fmt = pipe, n_streams, sample_rate, channels, fmt
+        h = C.c_void_p()
+        _check(load_library().af_session_create(pipe._h, n_streams, sample_rate, channels, fmt, max_tick_samples, C.byref(h)))
+        self._h = h
+        max_frames = max_tick_samples // channels
+        self.max_pcm = load_library().af_resample_max_output(sample_rate, 16000, max_frames + 128) + 8
+        self.max_T = self.max_pcm // 160 + 4
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.af_session_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        _check(load_library().af_session_reset(self._h))
+
+    def push(self, x: np.ndarray) -> dict:
+        cfg = self.pipe.cfg
+        x = np.ascontiguousarray(x, dtype=np.int16 if self.fmt == AF_FMT_I16 else np.float32)
+        assert x.ndim == 2 and x.shape[0] == self.S
+        n = x.shape[1]
+        M = max(cfg.n_mels, 1)
+        pcm = np.zeros((self.S, (self.max_pcm + 3) // 4 * 4), np.float32)
+        lm = np.zeros((self.S, (self.max_T * M + 3) // 4 * 4), np.float32)
+        vad = np.zeros((self.S, (self.max_T + 15) // 16 * 16), np.uint8)
+        fin = (VadFinalC * self.S)()
+        o = OutputsC(pcm.ctypes.data if cfg.write_pcm else None, pcm.shape[1], lm.ctypes.data if cfg.n_mels else None,
+                     lm.shape[1], vad.ctypes.data if cfg.vad_enable else None, vad.shape[1], None, 0,
+                     C.addressof(fin) if cfg.vad_enable else None)
+        u32p = C.POINTER(C.c_uint32)
+        npcm, nf, nv = (np.zeros(self.S, np.uint32) for _ in range(3))
+        _check(load_library().af_session_push(self._h, x.ctypes.data, n, n, AF_MEM_HOST, C.byref(o),
+                                              npcm.ctypes.data_as(u32p), nf.ctypes.data_as(u32p), nv.ctypes.data_as(u32p)))
+        T = int(max(nf[0], nv[0]))
+        return {"pcm": pcm[:, :npcm[0]].copy(), "logmel": lm[:, :int(nf[0]) * M].reshape(self.S, int(nf[0]), M).copy(),
+                "vad": vad[:, :int(nv[0])].copy(), "n_frames": T,
+                "vad_final": [dict(state=int(f.state), smoothed=float(f.smoothed_energy), speech_frames=int(f.speech_frames))
+                              for f in fin]}

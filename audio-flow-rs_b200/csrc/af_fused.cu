@@ -17,8 +17,7 @@ namespace af {
 struct __align__(128) FusedSmem {
     unsigned char stage[STAGE_BYTES];                // raw interleaved input of one step (bulk-copy target)
     float ybuf[YBUF_FLOATS];                         // padded 16 kHz samples of the current step
-    float scr[16 * SCR_FLOATS_PER_FRAME];            // per half-warp transpose scratch / log-mel stage
-    float pbuf[PBUF_FLOATS];                         // 4*|X[k]|^2, [bin][frame]
+    float scr[16 * SCR_FLOATS_PER_FRAME];            // per half-warp transpose scratch; then per-warp power + log-mel
     FftTables fft;
     MelTables mel;
     StreamDev stream;                                // descriptor of the tile's stream
@@ -198,6 +197,34 @@ __device__ __forceinline__ void resample_step_fast(FusedSmem &sm, const StreamDe
         return;
     }
     const uint32_t q = s.q;
+    if (KIND == K_F32_1 && q == 1 && s.p == 3) {
+        // 48 kHz -> 16 kHz mono f32, four outputs per thread: output n reads x[3n-2 .. 3n+1]; for n = 0 mod 4 that
+        // is an 8-byte aligned float2 followed by three 16-byte aligned float4 of the stage (14 floats, 13 used)
+        const float *stg = reinterpret_cast<const float *>(sm.stage);
+        const int kbase = sm.tile_k + 3 * (int)tile_off - 1 - f_lo;
+        for (int i4 = i_begin + 4 * tid; i4 < YLEN; i4 += 4 * FUSED_THREADS) {
+            const float *px = stg + (kbase + 3 * i4);
+            float v[14];
+            const float2 h = *reinterpret_cast<const float2 *>(px);
+            const float4 a4 = *reinterpret_cast<const float4 *>(px + 2);
+            const float4 b4 = *reinterpret_cast<const float4 *>(px + 6);
+            const float4 c4 = *reinterpret_cast<const float4 *>(px + 10);
+            v[0] = h.x; v[1] = h.y; v[2] = a4.x; v[3] = a4.y; v[4] = a4.z; v[5] = a4.w; v[6] = b4.x; v[7] = b4.y;
+            v[8] = b4.z; v[9] = b4.w; v[10] = c4.x; v[11] = c4.y; v[12] = c4.z; v[13] = c4.w;
+            float big = 0.0f;
+#pragma unroll
+            for (int t = 0; t < 13; ++t) big += fabsf(v[t]);                      // NaN / Inf propagate
+            float4 y = make_float4(v[1], v[4], v[7], v[10]);
+            if (!(big < 1e30f && y.x != 0.0f && y.y != 0.0f && y.z != 0.0f && y.w != 0.0f)) {
+                y.x = interp_cubic(0.0f, v[0], v[1], v[2], v[3]);
+                y.y = interp_cubic(0.0f, v[3], v[4], v[5], v[6]);
+                y.z = interp_cubic(0.0f, v[6], v[7], v[8], v[9]);
+                y.w = interp_cubic(0.0f, v[9], v[10], v[11], v[12]);
+            }
+            *reinterpret_cast<float4 *>(sm.ybuf + ypad(i4)) = y;
+        }
+        return;
+    }
     const uint32_t a = sm.tile_rem + (tile_off + (uint32_t)i) * s.p;
     if (q == 1) {
         // integer step (48 kHz -> 16 kHz): frac == 0 exactly; the cubic returns y1 bit for bit whenever y1 != 0 and
@@ -292,8 +319,9 @@ __device__ __forceinline__ void resample_step(FusedSmem &sm, const StreamDev &s,
     }
 }
 
-// ---- phase 2a: one frame per half-warp: window, packed real FFT, power -> pbuf[bin][q] ----
-__device__ __forceinline__ void fft_frame(FusedSmem &sm, float *__restrict__ scr, int q, int l, int lane)
+// ---- phase 2a: one frame per half-warp: window, packed real FFT, power -> pw[bin][half] (warp private) ----
+__device__ __forceinline__ void fft_frame(FusedSmem &sm, float *__restrict__ scr, float *__restrict__ pw, int q, int l,
+                                          int lane)
 {
     float xr[16], xi[16];
     const float *yb = sm.ybuf + 180 * q + 2 * l;      // ypad(160 q + 32 n1 + 2 l) = 180 q + 36 n1 + 2 l
@@ -340,7 +368,7 @@ __device__ __forceinline__ void fft_frame(FusedSmem &sm, float *__restrict__ scr
     // Z[l + 16 k2] is in slot(k2).  Hermitian split: pair k = l + 16 r with 256 - k, which lives in
     // lane (16 - l) & 15 at k2 = 15 - r (lane 0 pairs with itself at k2 = (16 - r) & 15).
     const int src = ((16 - l) & 15) | (lane & 16);
-    float *pb = sm.pbuf + q;
+    float *pb = pw + (lane >> 4);                       // interleaved: power of frame `half` at pw[2 k + half]
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const float zr = xr[fft16_slot(r)], zi = xi[fft16_slot(r)];
@@ -355,12 +383,12 @@ __device__ __forceinline__ void fft_frame(FusedSmem &sm, float *__restrict__ scr
         const float ti = w.x * o2i + w.y * o2r;
         const float ar = e2r + tr, ai = e2i + ti;      // 2 X[k]
         const float br = e2r - tr, bi = e2i - ti;      // 2 conj(X[256-k])
-        pb[k * PB_ROW] = ar * ar + ai * ai;
-        pb[(256 - k) * PB_ROW] = br * br + bi * bi;
+        pb[2 * k] = ar * ar + ai * ai;
+        pb[2 * (256 - k)] = br * br + bi * bi;
     }
     if (l == 0) {                                       // k = 128 pairs with itself
         const float zr = xr[fft16_slot(8)], zi = xi[fft16_slot(8)];
-        pb[128 * PB_ROW] = 4.0f * (zr * zr + zi * zi);
+        pb[2 * 128] = 4.0f * (zr * zr + zi * zi);
     }
 }
 
@@ -416,8 +444,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
         if (blockIdx.x < P.n_tiles) issue_fill(sm, P, blockIdx.x, 0);
     }
     __syncthreads();
-    const uint32_t pitch = M + 4u;                      // row pitch of the log-mel stage (16-byte aligned rows)
-    float *stage_lm = sm.scr;
     const float log_mul = P.log_scale;
     uint32_t fill_parity = 0;
 
@@ -503,59 +529,53 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
                         }
                     }
                 }
-                if (M && warp * 2 < n_valid) {                        // warp-uniform: skip fully invalid pairs
-                    const int hw = warp * 2 + half;
-                    fft_frame(sm, sm.scr + hw * SCR_FLOATS_PER_FRAME, hw, l, lane);
-                }
+                float *wscr = sm.scr + warp * 2 * SCR_FLOATS_PER_FRAME;        // this warp's 4.5 KB
+                const bool do_fft = M && warp * 2 < n_valid;                  // warp-uniform: skip fully invalid pairs
+                if (do_fft) fft_frame(sm, wscr + half * SCR_FLOATS_PER_FRAME, wscr + WP_POWER, warp * 2 + half, l, lane);
                 __syncwarp();
                 named_bar_arrive(2, FUSED_THREADS);                   // ybuf no longer needed by this warp
-                named_bar_sync(1, FFT_WARPS * 32);                    // pbuf complete
 
-                // ---- phase 3: mel + log into the stage (thread = filter x 4 frames) ----
-                if (M && n_valid > 0) {
-                    const int n_items = (int)M * (SF / 4);
-                    for (int item = tid; item < n_items; item += FFT_WARPS * 32) {
-                        const int m = item >> 2, fq = item & 3;
-                        if (fq * 4 >= n_valid) continue;
-                        const int lo = sm.mel.lo[m], cnt = sm.mel.cnt[m];
+                // ---- phase 3 (warp local): mel + log of the warp's two frames; lane = balanced set of filters ----
+                if (do_fft) {
+                    const float2 *pw = reinterpret_cast<const float2 *>(wscr + WP_POWER);
+                    float *lmw = wscr + WP_LOGMEL;
+#pragma unroll 1
+                    for (int t = 0; t < 4; ++t) {
+                        const int m = sm.mel.sched[lane][t];
+                        if (m == 0xFF) break;
+                        const int cnt = sm.mel.cnt[m];
                         const float *w = sm.mel.w + sm.mel.off[m];
-                        const float *pp = sm.pbuf + lo * PB_ROW + 4 * fq;
-                        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                        const float2 *pp = pw + sm.mel.lo[m];
+                        float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
                         int j = 0;
                         for (; j + 2 <= cnt; j += 2) {
                             const float w0 = w[j], w1 = w[j + 1];
-                            const float4 p0 = *reinterpret_cast<const float4 *>(pp + j * PB_ROW);
-                            const float4 p1 = *reinterpret_cast<const float4 *>(pp + (j + 1) * PB_ROW);
-                            a0 = fmaf(w0, p0.x, a0); a1 = fmaf(w0, p0.y, a1); a2 = fmaf(w0, p0.z, a2); a3 = fmaf(w0, p0.w, a3);
-                            a0 = fmaf(w1, p1.x, a0); a1 = fmaf(w1, p1.y, a1); a2 = fmaf(w1, p1.z, a2); a3 = fmaf(w1, p1.w, a3);
+                            const float2 p0 = pp[j], p1 = pp[j + 1];
+                            a0 = fmaf(w0, p0.x, a0); a1 = fmaf(w0, p0.y, a1);
+                            b0 = fmaf(w1, p1.x, b0); b1 = fmaf(w1, p1.y, b1);
                         }
                         if (j < cnt) {
                             const float w0 = w[j];
-                            const float4 p0 = *reinterpret_cast<const float4 *>(pp + j * PB_ROW);
-                            a0 = fmaf(w0, p0.x, a0); a1 = fmaf(w0, p0.y, a1); a2 = fmaf(w0, p0.z, a2); a3 = fmaf(w0, p0.w, a3);
+                            const float2 p0 = pp[j];
+                            a0 = fmaf(w0, p0.x, a0); a1 = fmaf(w0, p0.y, a1);
                         }
-                        float *st = stage_lm + (4 * fq) * pitch + m;
-                        st[0] = __log2f(fmaxf(a0, P.log_floor)) * log_mul;
-                        st[pitch] = __log2f(fmaxf(a1, P.log_floor)) * log_mul;
-                        st[2 * pitch] = __log2f(fmaxf(a2, P.log_floor)) * log_mul;
-                        st[3 * pitch] = __log2f(fmaxf(a3, P.log_floor)) * log_mul;
+                        lmw[m] = __log2f(fmaxf(a0 + b0, P.log_floor)) * log_mul;
+                        lmw[M + m] = __log2f(fmaxf(a1 + b1, P.log_floor)) * log_mul;
                     }
-                }
-                named_bar_sync(1, FFT_WARPS * 32);
-
-                // ---- phase 4: coalesced copy-out of the step's [n_valid][M] log-mel block ----
-                if (M && n_valid > 0 && lm_row) {
-                    float *dst = lm_row + (uint64_t)f0 * M;
-                    if ((M & 3) == 0) {
-                        const int m4 = (int)M >> 2;
-                        for (int f = warp; f < n_valid; f += FFT_WARPS)
-                            if (lane < m4)
-                                reinterpret_cast<float4 *>(dst + f * (int)M)[lane] =
-                                    *reinterpret_cast<const float4 *>(stage_lm + f * pitch + 4 * lane);
-                    } else {
-                        for (int f = warp; f < n_valid; f += FFT_WARPS)
-                            for (int m = lane; m < (int)M; m += 32) dst[f * (int)M + m] = stage_lm[f * pitch + m];
+                    __syncwarp();
+                    // ---- phase 4 (warp local): the warp's rows are contiguous in the [frame][mel] output ----
+                    if (lm_row) {
+                        const int rows = min(2, n_valid - warp * 2);
+                        float *dst = lm_row + (uint64_t)(f0 + warp * 2) * M;
+                        const int total = rows * (int)M;
+                        if ((M & 3) == 0) {
+                            for (int i = lane; i < (total >> 2); i += 32)
+                                reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(lmw)[i];
+                        } else {
+                            for (int i = lane; i < total; i += 32) dst[i] = lmw[i];
+                        }
                     }
+                    __syncwarp();
                 }
             }
             __syncthreads();        // ybuf carried, log-mel stage consumed: the next phase 1 may overwrite both

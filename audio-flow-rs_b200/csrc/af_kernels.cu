@@ -99,9 +99,31 @@ cudaError_t launch_frame_energy(const EnergyJob &job, cudaStream_t st)
 }
 
 // ---- detect() EMA + threshold + state machine (vad.rs:101-153): strictly sequential per stream ----
-// One thread per stream.  The dependent chain is ~3 FP32 ops + a few integer ops per frame; the kernel is
-// latency bound, so energies are fetched 16 frames ahead as 4 x float4 (software pipelined) and the states
+// One thread per stream; the kernel is bound by the latency of two dependent chains, so they are kept
+// minimal and run side by side: the EMA chain (fmul, fadd per frame) of block b+1 is interleaved with the
+// branch-free integer state machine of block b.  Energies arrive 16 frames ahead as 4 x float4, states
 // leave as one 16-byte store per 16 frames.
+struct VadMachine {
+    int st;
+    unsigned long long sil, spk;
+};
+
+__device__ __forceinline__ uint32_t vad_machine_step(VadMachine &m, bool sp, unsigned long long timeout,
+                                                     unsigned long long min_speech)
+{
+    // vad.rs:121-153, branch free
+    const bool is0 = m.st == 0, is1 = m.st == 1;
+    const unsigned long long sil1 = sp ? 0ull : m.sil + 1ull;
+    const unsigned long long spk1 = sp ? m.spk + 1ull : m.spk;
+    const bool to = is1 && !sp && sil1 >= timeout;
+    const int st1 = to ? (spk1 >= min_speech ? 2 : 0) : 1;
+    const int st_new = is0 ? (sp ? 1 : 0) : (is1 ? st1 : 0);
+    const unsigned long long spk_new = is0 ? (sp ? 1ull : m.spk) : (is1 ? (to ? 0ull : spk1) : m.spk);
+    const unsigned long long sil_new = is0 ? (sp ? 0ull : m.sil) : (is1 ? sil1 : 0ull);
+    m.st = st_new; m.spk = spk_new; m.sil = sil_new;
+    return (uint32_t)st_new;
+}
+
 __global__ void af_vad_scan_kernel(const ScanJob J)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,43 +135,69 @@ __global__ void af_vad_scan_kernel(const ScanJob J)
     if (J.state_io) v = J.state_io[s];
     else { v.smoothed = 0.0f; v.state = 0; v.silence_frames = 0; v.speech_frames = 0; }
     const VadParams prm = J.prm;
+    const float alpha = prm.alpha, beta = __fsub_rn(1.0f, prm.alpha), e_min = prm.e_min;
+    const bool use_smoothed = alpha > 0.0f;
+    float sm = v.smoothed;
+    VadMachine m{v.state, v.silence_frames, v.speech_frames};
     uint32_t f = 0;
     const bool vec_in = ((reinterpret_cast<uintptr_t>(e) & 15) == 0);
     const bool vec_out = out && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     if (vec_in && T >= 16) {
         const float4 *e4 = reinterpret_cast<const float4 *>(e);
-        float4 nb[4];
+        const uint32_t n_blocks = T / 16;
+        float eb[16];
+        {
+            const float4 a = e4[0], b = e4[1], c = e4[2], d = e4[3];
+            eb[0] = a.x; eb[1] = a.y; eb[2] = a.z; eb[3] = a.w; eb[4] = b.x; eb[5] = b.y; eb[6] = b.z; eb[7] = b.w;
+            eb[8] = c.x; eb[9] = c.y; eb[10] = c.z; eb[11] = c.w; eb[12] = d.x; eb[13] = d.y; eb[14] = d.z; eb[15] = d.w;
+        }
+        uint32_t bits_cur = 0;                       // is_speech bits of the block whose machine steps are pending
+        for (uint32_t b = 0; b <= n_blocks; ++b) {
+            float4 nx[4];
+            const bool have_next = b + 1 < n_blocks;
+            if (have_next) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) nb[j] = e4[j];
-        for (; f + 16 <= T; f += 16) {
-            float4 cb[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) cb[j] = nb[j];
-            if (f + 32 <= T) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) nb[j] = e4[(f + 16) / 4 + j];       // prefetch the next 16 frames
+                for (int j = 0; j < 4; ++j) nx[j] = e4[(b + 1) * 4 + j];       // prefetch
             }
-            uint32_t packed[4];
+            uint32_t bits_new = 0, packed[4] = {0, 0, 0, 0};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t s0 = (uint32_t)vad_step(v, prm, cb[j].x);
-                const uint32_t s1 = (uint32_t)vad_step(v, prm, cb[j].y);
-                const uint32_t s2 = (uint32_t)vad_step(v, prm, cb[j].z);
-                const uint32_t s3 = (uint32_t)vad_step(v, prm, cb[j].w);
-                packed[j] = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+            for (int j = 0; j < 16; ++j) {
+                if (b < n_blocks) {                  // EMA chain of block b (vad.rs:101-118)
+                    sm = __fadd_rn(__fmul_rn(alpha, eb[j]), __fmul_rn(beta, sm));
+                    const float det = use_smoothed ? sm : eb[j];
+                    bits_new |= (det >= e_min ? 1u : 0u) << j;
+                }
+                if (b > 0) {                         // state machine of block b - 1
+                    const uint32_t stv = vad_machine_step(m, (bits_cur >> j) & 1u, prm.silence_timeout, prm.min_speech);
+                    packed[j >> 2] |= stv << (8 * (j & 3));
+                }
             }
-            if (vec_out) {
-                *reinterpret_cast<uint4 *>(out + f) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            } else if (out) {
+            if (b > 0) {
+                const uint32_t f0 = (b - 1) * 16;
+                if (vec_out) {
+                    *reinterpret_cast<uint4 *>(out + f0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                } else if (out) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) out[f + j] = (uint8_t)(packed[j >> 2] >> (8 * (j & 3)));
+                    for (int j = 0; j < 16; ++j) out[f0 + j] = (uint8_t)(packed[j >> 2] >> (8 * (j & 3)));
+                }
+            }
+            bits_cur = bits_new;
+            if (have_next) {
+                eb[0] = nx[0].x; eb[1] = nx[0].y; eb[2] = nx[0].z; eb[3] = nx[0].w; eb[4] = nx[1].x; eb[5] = nx[1].y;
+                eb[6] = nx[1].z; eb[7] = nx[1].w; eb[8] = nx[2].x; eb[9] = nx[2].y; eb[10] = nx[2].z; eb[11] = nx[2].w;
+                eb[12] = nx[3].x; eb[13] = nx[3].y; eb[14] = nx[3].z; eb[15] = nx[3].w;
             }
         }
+        f = n_blocks * 16;
     }
     for (; f < T; ++f) {
-        const int st = vad_step(v, prm, e[f]);
-        if (out) out[f] = (uint8_t)st;
+        const float ev = e[f];
+        sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
+        const float det = use_smoothed ? sm : ev;
+        const uint32_t stv = vad_machine_step(m, det >= e_min, prm.silence_timeout, prm.min_speech);
+        if (out) out[f] = (uint8_t)stv;
     }
+    v.smoothed = sm; v.state = m.st; v.silence_frames = m.sil; v.speech_frames = m.spk;
     if (J.state_io) J.state_io[s] = v;
     if (J.final_out) J.final_out[s] = v;
 }
@@ -157,8 +205,100 @@ __global__ void af_vad_scan_kernel(const ScanJob J)
 cudaError_t launch_vad_scan(const ScanJob &job, cudaStream_t st)
 {
     if (job.n_streams == 0) return cudaSuccess;
-    const int threads = 32;                       // few streams per CTA: spread the chains over the SMs
+    const int threads = 32;                       // one warp per CTA: spread the chains over the SMs
     af_vad_scan_kernel<<<(job.n_streams + threads - 1) / threads, threads, 0, st>>>(job);
+    return cudaGetLastError();
+}
+
+// ---- streaming sessions (all streams advance in lockstep) ----
+// ingest: carry the retained input frames to the front of the new buffer and append the downmixed new frames
+__global__ void af_session_ingest_kernel(const SessionIngest J)
+{
+    const uint32_t s = blockIdx.y;
+    const float *old = J.old_buf + (uint64_t)s * J.buf_stride;
+    float *neu = J.new_buf + (uint64_t)s * J.buf_stride;
+    const char *in = reinterpret_cast<const char *>(J.input) + (uint64_t)s * J.in_stride_bytes;
+    const uint32_t total = J.keep + J.n_new_frames;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float v;
+        if (i < J.keep) v = old[J.drop + i];
+        else v = load_mono(in, J.n_samples, J.n_new_frames, J.channels, J.format, (int)(i - J.keep));
+        neu[i] = v;
+    }
+}
+
+cudaError_t launch_session_ingest(const SessionIngest &J, uint32_t n_streams, cudaStream_t st)
+{
+    const uint32_t total = J.keep + J.n_new_frames;
+    if (n_streams == 0 || total == 0) return cudaSuccess;
+    dim3 grid((total + 255) / 256, n_streams);
+    af_session_ingest_kernel<<<grid, 256, 0, st>>>(J);
+    return cudaGetLastError();
+}
+
+// resample the complete chunks of this tick for every stream; carries the unconsumed 16 kHz tail forward
+__global__ void af_session_resample_kernel(const SessionResample J)
+{
+    const uint32_t s = blockIdx.y;
+    const float *in = J.in_buf + (uint64_t)s * J.in_stride;
+    const float *yold = J.y_old + (uint64_t)s * J.y_stride;
+    float *ynew = J.y_new + (uint64_t)s * J.y_stride;
+    const uint32_t n_new = (uint32_t)(J.n_end - J.n_begin);
+    const uint32_t total = J.y_keep + n_new;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float v;
+        if (i < J.y_keep) {
+            v = yold[J.y_drop + i];
+        } else {
+            const unsigned long long n = J.n_begin + (i - J.y_keep);
+            if (J.mode == RS_PASSTHROUGH) {
+                const long long idx = (long long)n;
+                v = (idx < J.data_base || idx >= J.n_valid_end) ? 0.0f : in[idx - J.data_base];
+            } else {
+                long long k; uint32_t rem;
+                resample_pos(n, J.p, J.q, &k, &rem);
+                float frac;
+                if (J.mode == RS_TABLE) {
+                    frac = J.frac[i - J.y_keep];
+                    k += __float2int_rn((float)rem * (1.0f / (float)J.q) - frac);
+                } else {
+                    frac = (float)rem * (1.0f / (float)J.q);
+                }
+                float y[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const long long idx = k - 1 + t;
+                    y[t] = (idx < J.data_base || idx >= J.n_valid_end) ? 0.0f : in[idx - J.data_base];
+                }
+                v = interp_cubic(frac, y[0], y[1], y[2], y[3]);
+            }
+        }
+        ynew[i] = v;
+    }
+}
+
+cudaError_t launch_session_resample(const SessionResample &J, uint32_t n_streams, cudaStream_t st)
+{
+    const uint32_t total = J.y_keep + (uint32_t)(J.n_end - J.n_begin);
+    if (n_streams == 0 || total == 0) return cudaSuccess;
+    dim3 grid((total + 255) / 256, n_streams);
+    af_session_resample_kernel<<<grid, 256, 0, st>>>(J);
+    return cudaGetLastError();
+}
+
+// every stream of a session has the same lengths: refresh the fused kernel's stream table in place
+__global__ void af_session_setup_kernel(StreamDev *tab, uint32_t n_streams, uint32_t n, uint32_t n_frames, uint32_t n_vad)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    tab[s].n_samples = n; tab[s].n_in = n; tab[s].n_out = n; tab[s].n_frames = n_frames; tab[s].n_vad_frames = n_vad;
+}
+
+cudaError_t launch_session_setup(StreamDev *tab, uint32_t n_streams, uint32_t n, uint32_t n_frames, uint32_t n_vad,
+                                 cudaStream_t st)
+{
+    if (n_streams == 0) return cudaSuccess;
+    af_session_setup_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(tab, n_streams, n, n_frames, n_vad);
     return cudaGetLastError();
 }
 

@@ -35,7 +35,28 @@ struct ScanJob {             // EMA + threshold + state machine, one stream per 
     uint32_t n_streams;
 };
 
+struct SessionIngest {
+    const float *old_buf; float *new_buf; uint64_t buf_stride;   // mono f32 input history, ping-pong
+    uint32_t drop, keep;                                         // retained frames: old[drop .. drop + keep)
+    const void *input; uint64_t in_stride_bytes;                 // this tick's interleaved samples, one row per stream
+    uint64_t n_samples; uint32_t n_new_frames; uint32_t channels, format;
+};
+
+struct SessionResample {
+    const float *in_buf; uint64_t in_stride;
+    long long data_base, n_valid_end;                            // global frame index of in_buf[0]; frames beyond read 0
+    unsigned long long n_begin, n_end;                           // global output range of this tick
+    uint32_t p, q, mode;
+    const float *frac;                                           // RS_TABLE: frac[n - n_begin]
+    const float *y_old; float *y_new; uint64_t y_stride;         // 16 kHz carry + new samples, ping-pong
+    uint32_t y_drop, y_keep;
+};
+
 size_t fused_smem_bytes();
+cudaError_t launch_session_ingest(const SessionIngest &J, uint32_t n_streams, cudaStream_t st);
+cudaError_t launch_session_resample(const SessionResample &J, uint32_t n_streams, cudaStream_t st);
+cudaError_t launch_session_setup(StreamDev *tab, uint32_t n_streams, uint32_t n, uint32_t n_frames, uint32_t n_vad,
+                                 cudaStream_t st);
 cudaError_t launch_fused(const FusedParams &P, int n_ctas, cudaStream_t st);
 
 cudaError_t launch_to_mono(const float *in, uint64_t n_samples, uint32_t channels, float *out, uint64_t n_frames,

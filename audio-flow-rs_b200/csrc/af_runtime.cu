@@ -1043,8 +1043,311 @@ AF_API size_t af_debug_resample_plan(uint32_t input_rate, uint32_t output_rate, 
     return f.size();
 }
 
-// ---- streaming sessions: implemented in af_session.cu ----
-
 }  // extern "C"
 
-extern "C" int af_session_fail(void) { return fail(AF_ERR_INVALID, "streaming sessions are not implemented in this build"); }
+// ------------------------------------------------------------------------------------------
+// streaming sessions (BASELINE config 5): n_streams lockstep streams, state resident on the device
+// ------------------------------------------------------------------------------------------
+struct af_session {
+    af_pipeline *pipe = nullptr;
+    size_t S = 0;
+    uint32_t rate = 0, channels = 1, format = 0, max_tick_frames = 0;
+    RsRecurrence rec;                 // shared by every stream (same number of frames pushed to all)
+    // input history: last 16 frames + residual (< 128), ping-pong
+    float *in_buf[2] = {nullptr, nullptr}; uint64_t in_stride = 0; int in_cur = 0;
+    uint32_t in_len = 0;              // frames currently held in in_buf[in_cur]
+    long long in_base = 0;            // global frame index of in_buf[in_cur][0]
+    // 16 kHz carry (samples not yet covered by an emitted frame), ping-pong
+    float *y_buf[2] = {nullptr, nullptr}; uint64_t y_stride = 0; int y_cur = 0;
+    uint32_t y_len = 0;
+    uint32_t frame_len = WIN, hop = HOP;   // framing of the features / VAD
+    bool framing = false;
+    StreamDev *d_tab[2] = {nullptr, nullptr};
+    TileDev *d_tiles = nullptr;
+    VadState *d_vad = nullptr;
+    float *d_energy = nullptr; uint64_t energy_stride = 0;
+    float *d_frac = nullptr; size_t frac_cap = 0;
+    void *d_in_stage = nullptr; size_t in_stage_bytes = 0;    // host-mode staging of the tick input
+    float *d_lm = nullptr; uint8_t *d_states = nullptr;       // host-mode staging of outputs
+    uint64_t lm_stride = 0, st_stride = 0;
+    std::vector<float> frac_host;
+    uint64_t frames_emitted = 0;
+};
+
+extern "C" {
+
+AF_API void af_session_destroy(af_session *s)
+{
+    if (!s) return;
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) {
+        if (s->in_buf[i]) cudaFree(s->in_buf[i]);
+        if (s->y_buf[i]) cudaFree(s->y_buf[i]);
+        if (s->d_tab[i]) cudaFree(s->d_tab[i]);
+    }
+    if (s->d_tiles) cudaFree(s->d_tiles);
+    if (s->d_vad) cudaFree(s->d_vad);
+    if (s->d_energy) cudaFree(s->d_energy);
+    if (s->d_frac) cudaFree(s->d_frac);
+    if (s->d_in_stage) cudaFree(s->d_in_stage);
+    if (s->d_lm) cudaFree(s->d_lm);
+    if (s->d_states) cudaFree(s->d_states);
+    delete s;
+}
+
+AF_API int af_session_reset(af_session *s)
+{
+    if (!s) return fail(AF_ERR_INVALID, "null session");
+    s->rec.init(s->rate, OUT_RATE);
+    s->in_cur = 0; s->y_cur = 0; s->y_len = 0; s->frames_emitted = 0;
+    s->in_len = 2 * RS_POLY;                       // rubato starts with 16 zero frames of history
+    s->in_base = -2 * RS_POLY;
+    AF_CUDA(cudaMemset(s->in_buf[0], 0, s->S * s->in_stride * sizeof(float)));
+    AF_CUDA(cudaMemset(s->d_vad, 0, s->S * sizeof(VadState)));
+    return AF_OK;
+}
+
+AF_API int af_session_create(af_pipeline *p, size_t n_streams, uint32_t sample_rate, uint16_t channels, uint16_t format,
+                             uint32_t max_tick_samples, af_session **out)
+{
+    if (!p || !out || n_streams == 0) return fail(AF_ERR_INVALID, "bad argument");
+    if (channels == 0 || (format != AF_FMT_F32 && format != AF_FMT_I16) || sample_rate == 0 || max_tick_samples == 0)
+        return fail(AF_ERR_INVALID, "bad stream format");
+    int rc = require_ctx();
+    if (rc) return rc;
+    const af_pipeline_config &cfg = p->cfg;
+    if (cfg.n_mels && cfg.vad_enable && cfg.vad_frame_len != 0 && (cfg.vad_frame_len != WIN || cfg.vad_hop != HOP))
+        return fail(AF_ERR_INVALID, "sessions need the VAD on the STFT frames when features are enabled");
+    std::unique_ptr<af_session, void (*)(af_session *)> s(new af_session, af_session_destroy);
+    s->pipe = p; s->S = n_streams; s->rate = sample_rate; s->channels = channels; s->format = format;
+    s->max_tick_frames = (max_tick_samples + channels - 1) / channels;
+    s->rec.init(sample_rate, OUT_RATE);
+    if (!s->rec.passthrough && s->rec.end_idx <= 0) return fail(AF_ERR_RESAMPLING_FAILED, "unsupported resampling ratio");
+    s->framing = cfg.n_mels != 0 || cfg.vad_enable;
+    if (cfg.vad_enable && cfg.vad_frame_len != 0) { s->frame_len = cfg.vad_frame_len; s->hop = cfg.vad_hop; }
+    s->in_stride = round_up(2 * RS_POLY + RS_CHUNK + s->max_tick_frames + 8, 4);
+    const uint64_t max_new_y = af_resample_max_output(sample_rate, OUT_RATE, s->max_tick_frames + RS_CHUNK) + 8;
+    s->y_stride = round_up(s->frame_len + s->hop + max_new_y + 8, 4);
+    const uint64_t max_frames = (s->y_stride) / s->hop + 2;
+    s->energy_stride = round_up(max_frames, 4);
+    s->lm_stride = round_up(max_frames * std::max<uint32_t>(cfg.n_mels, 1), 4);
+    s->st_stride = round_up(max_frames, 16);
+    for (int i = 0; i < 2; ++i) {
+        AF_CUDA(cudaMalloc(&s->in_buf[i], n_streams * s->in_stride * sizeof(float)));
+        AF_CUDA(cudaMalloc(&s->y_buf[i], n_streams * s->y_stride * sizeof(float)));
+        AF_CUDA(cudaMemset(s->y_buf[i], 0, n_streams * s->y_stride * sizeof(float)));
+        AF_CUDA(cudaMalloc(&s->d_tab[i], n_streams * sizeof(StreamDev)));
+        std::vector<StreamDev> tab(n_streams);
+        for (size_t k = 0; k < n_streams; ++k) {
+            StreamDev &d = tab[k];
+            memset(&d, 0, sizeof(d));
+            d.data = s->y_buf[i] + k * s->y_stride;
+            d.channels = 1; d.format = FMT_F32; d.p = 1; d.q = 1; d.mode = RS_PASSTHROUGH;
+            d.tile_begin = (uint32_t)k; d.n_tiles = 1; d.staged = 1;
+        }
+        AF_CUDA(cudaMemcpy(s->d_tab[i], tab.data(), n_streams * sizeof(StreamDev), cudaMemcpyHostToDevice));
+    }
+    if (s->y_stride > (uint64_t)TILE_SAMPLES) return fail(AF_ERR_INVALID, "max_tick_samples too large for a session (%u)", max_tick_samples);
+    std::vector<TileDev> tiles(n_streams);
+    for (size_t k = 0; k < n_streams; ++k) tiles[k] = TileDev{(uint32_t)k, 0};
+    AF_CUDA(cudaMalloc(&s->d_tiles, n_streams * sizeof(TileDev)));
+    AF_CUDA(cudaMemcpy(s->d_tiles, tiles.data(), n_streams * sizeof(TileDev), cudaMemcpyHostToDevice));
+    AF_CUDA(cudaMalloc(&s->d_vad, n_streams * sizeof(VadState)));
+    AF_CUDA(cudaMalloc(&s->d_energy, n_streams * s->energy_stride * sizeof(float)));
+    s->frac_cap = max_new_y + 64;
+    AF_CUDA(cudaMalloc(&s->d_frac, s->frac_cap * sizeof(float)));
+    rc = af_session_reset(s.get());
+    if (rc) return rc;
+    *out = s.release();
+    return AF_OK;
+}
+
+AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, uint32_t n_samples, int mem,
+                           const af_outputs *o, uint32_t *n_pcm, uint32_t *n_feat, uint32_t *n_vad)
+{
+    if (!s || (!data && n_samples)) return fail(AF_ERR_INVALID, "null argument");
+    if (n_samples % s->channels) return fail(AF_ERR_INVALID, "a tick must hold whole frames (n_samples %% channels == 0)");
+    const uint32_t n_new = n_samples / s->channels;
+    if (n_new > s->max_tick_frames) return fail(AF_ERR_CAPACITY, "tick of %u frames exceeds max_tick_samples", n_new);
+    if (in_stride < n_samples) return fail(AF_ERR_INVALID, "in_stride smaller than n_samples");
+    const af_pipeline_config &cfg = s->pipe->cfg;
+    cudaStream_t st = g_ctx.stream;
+    const size_t S = s->S;
+    const uint32_t bps = s->format == AF_FMT_I16 ? 2 : 4;
+    af_outputs none{};
+    if (!o) o = &none;
+
+    // ---- 1. input: host ticks are staged; then carry history + residual and append the downmixed frames ----
+    const void *d_in = data;
+    uint64_t d_in_stride_bytes = in_stride * bps;
+    if (mem == AF_MEM_HOST && n_samples) {
+        const size_t row = round_up((uint64_t)n_samples * bps, 16);
+        if (s->in_stage_bytes < row * S) {
+            if (s->d_in_stage) cudaFree(s->d_in_stage);
+            s->d_in_stage = nullptr; s->in_stage_bytes = 0;
+            AF_CUDA(cudaMalloc(&s->d_in_stage, row * S));
+            s->in_stage_bytes = row * S;
+        }
+        AF_CUDA(cudaMemcpy2DAsync(s->d_in_stage, row, data, in_stride * bps, (size_t)n_samples * bps, S, cudaMemcpyHostToDevice, st));
+        d_in = s->d_in_stage; d_in_stride_bytes = row;
+    }
+    // frames held: [history 16 | residual r | new n_new]; chunks formed from residual + new
+    const uint32_t residual = s->in_len - 2 * RS_POLY;
+    const uint32_t avail = residual + n_new;
+    const uint32_t chunks = s->rec.passthrough ? 0 : avail / RS_CHUNK;
+    SessionIngest ing{};
+    ing.old_buf = s->in_buf[s->in_cur]; ing.new_buf = s->in_buf[s->in_cur ^ 1]; ing.buf_stride = s->in_stride;
+    ing.drop = 0; ing.keep = s->in_len;
+    ing.input = d_in; ing.in_stride_bytes = d_in_stride_bytes; ing.n_samples = n_samples; ing.n_new_frames = n_new;
+    ing.channels = s->channels; ing.format = s->format;
+    AF_CUDA(launch_session_ingest(ing, (uint32_t)S, st));
+    count_launch();
+    s->in_cur ^= 1;
+    s->in_len += n_new;
+
+    // ---- 2. resample the complete chunks (shared f64 recurrence on the host, fractions uploaded) ----
+    const uint64_t n_begin = s->rec.passthrough ? (uint64_t)(s->in_base + 2 * RS_POLY + residual) : s->rec.n_out;
+    uint64_t n_end = n_begin;
+    s->frac_host.clear();
+    if (s->rec.passthrough) n_end = n_begin + n_new;
+    else {
+        for (uint32_t c = 0; c < chunks; ++c) s->rec.step(s->rec.exact ? nullptr : &s->frac_host);
+        n_end = s->rec.n_out;
+    }
+    const uint32_t n_y_new = (uint32_t)(n_end - n_begin);
+    if (s->y_len + n_y_new > s->y_stride) return fail(AF_ERR_CAPACITY, "internal: 16 kHz carry overflow");
+    if (!s->frac_host.empty()) {
+        if (s->frac_host.size() > s->frac_cap) return fail(AF_ERR_CAPACITY, "internal: fraction buffer overflow");
+        AF_CUDA(cudaMemcpyAsync(s->d_frac, s->frac_host.data(), s->frac_host.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    SessionResample rs{};
+    rs.in_buf = s->in_buf[s->in_cur]; rs.in_stride = s->in_stride;
+    rs.data_base = s->in_base;
+    rs.n_valid_end = s->rec.passthrough ? s->in_base + (long long)s->in_len
+                                        : s->in_base + 2 * RS_POLY + (long long)((residual + n_new) / RS_CHUNK * RS_CHUNK);
+    rs.n_begin = n_begin; rs.n_end = n_end; rs.p = s->rec.p; rs.q = s->rec.q; rs.mode = s->rec.mode();
+    rs.frac = s->d_frac;
+    rs.y_old = s->y_buf[s->y_cur]; rs.y_new = s->y_buf[s->y_cur ^ 1]; rs.y_stride = s->y_stride;
+    rs.y_drop = 0; rs.y_keep = s->y_len;
+    AF_CUDA(launch_session_resample(rs, (uint32_t)S, st));
+    count_launch();
+    s->y_cur ^= 1;
+    const uint32_t y_total = s->y_len + n_y_new;
+    float *ycur = s->y_buf[s->y_cur];
+
+    // ---- 3. PCM of this tick ----
+    if (cfg.write_pcm && o->pcm && n_y_new)
+        AF_CUDA(cudaMemcpy2DAsync(o->pcm, o->pcm_stride * sizeof(float), ycur + s->y_len, s->y_stride * sizeof(float),
+                                  (size_t)n_y_new * sizeof(float), S,
+                                  mem == AF_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+
+    // ---- 4. frames that became complete: features + VAD ----
+    uint32_t T = 0;
+    if (s->framing && y_total >= s->frame_len) T = 1 + (y_total - s->frame_len) / s->hop;
+    const bool stft_frames = (s->frame_len == WIN && s->hop == HOP);
+    if (T) {
+        float *lm = nullptr; uint64_t lm_stride = 0;
+        uint8_t *states = nullptr; uint64_t st_stride = 0;
+        if (cfg.n_mels && o->logmel) {
+            if (mem == AF_MEM_HOST) {
+                if (!s->d_lm) AF_CUDA(cudaMalloc(&s->d_lm, S * s->lm_stride * sizeof(float)));
+                lm = s->d_lm; lm_stride = s->lm_stride;
+            } else { lm = o->logmel; lm_stride = o->logmel_stride; }
+            if (lm_stride < (uint64_t)T * cfg.n_mels) return fail(AF_ERR_CAPACITY, "logmel_stride too small for %u frames", T);
+        }
+        if (cfg.vad_enable && o->vad) {
+            if (mem == AF_MEM_HOST) {
+                if (!s->d_states) AF_CUDA(cudaMalloc(&s->d_states, S * s->st_stride));
+                states = s->d_states; st_stride = s->st_stride;
+            } else { states = o->vad; st_stride = o->vad_stride; }
+            if (st_stride < T) return fail(AF_ERR_CAPACITY, "vad_stride too small for %u frames", T);
+        }
+        if (stft_frames) {
+            AF_CUDA(launch_session_setup(s->d_tab[s->y_cur], (uint32_t)S, y_total, T, cfg.vad_enable ? T : 0, st));
+            FusedParams P{};
+            P.streams = s->d_tab[s->y_cur]; P.tiles = s->d_tiles; P.n_tiles = (uint32_t)S;
+            P.fft = g_ctx.d_fft; P.mel = s->pipe->d_mel;
+            P.pcm = nullptr; P.pcm_stride = 0;
+            P.logmel = lm; P.logmel_stride = lm_stride;
+            P.energy = cfg.vad_enable ? s->d_energy : nullptr; P.energy_stride = s->energy_stride;
+            P.n_mels = lm ? cfg.n_mels : 0;
+            P.do_energy = cfg.vad_enable ? 1 : 0;
+            P.log_floor = cfg.log_floor;
+            P.log_scale = cfg.log10 ? 0.30102999566398120f : 0.69314718055994531f;
+            P.use_stage = g_ctx.variant == "sync" ? 0u : 1u;
+            if (P.n_mels || P.do_energy) {
+                AF_CUDA(launch_fused(P, (int)std::min<size_t>(S, (size_t)g_ctx.sm_count * 2), st));
+                count_launch(2);
+            }
+        } else {
+            EnergyJob ej{};
+            ej.y = ycur; ej.y_stride = s->y_stride; ej.n_frames = nullptr; ej.n_frames_all = T;
+            ej.frame_len = s->frame_len; ej.hop = s->hop; ej.energy = s->d_energy; ej.energy_stride = s->energy_stride;
+            ej.n_streams = (uint32_t)S;
+            AF_CUDA(launch_frame_energy(ej, st));
+            count_launch();
+        }
+        if (cfg.vad_enable) {
+            ScanJob sj{};
+            sj.energy = s->d_energy; sj.energy_stride = s->energy_stride; sj.n_frames = nullptr; sj.n_frames_all = T;
+            sj.states = states; sj.states_stride = st_stride; sj.state_io = s->d_vad;
+            sj.final_out = mem == AF_MEM_DEVICE ? reinterpret_cast<VadState *>(o->vad_final) : nullptr;
+            sj.prm = s->pipe->vad_prm; sj.n_streams = (uint32_t)S;
+            AF_CUDA(launch_vad_scan(sj, st));
+            count_launch();
+        }
+        if (mem == AF_MEM_HOST) {
+            if (lm) AF_CUDA(cudaMemcpy2DAsync(o->logmel, o->logmel_stride * sizeof(float), lm, lm_stride * sizeof(float),
+                                              (size_t)T * cfg.n_mels * sizeof(float), S, cudaMemcpyDeviceToHost, st));
+            if (states) AF_CUDA(cudaMemcpy2DAsync(o->vad, o->vad_stride, states, st_stride, T, S, cudaMemcpyDeviceToHost, st));
+            if (cfg.vad_enable && o->vad_final)
+                AF_CUDA(cudaMemcpyAsync(o->vad_final, s->d_vad, S * sizeof(VadState), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    AF_CUDA(cudaStreamSynchronize(st));
+
+    // ---- 5. bookkeeping: drop the consumed chunks and the samples every future frame starts after ----
+    if (!s->rec.passthrough) {
+        const uint32_t consumed = chunks * RS_CHUNK;
+        if (consumed) {
+            // keep [history 16 | new residual]: compact on the next ingest by dropping `consumed` frames
+            SessionIngest cp{};
+            cp.old_buf = s->in_buf[s->in_cur]; cp.new_buf = s->in_buf[s->in_cur ^ 1]; cp.buf_stride = s->in_stride;
+            cp.drop = consumed; cp.keep = s->in_len - consumed; cp.n_new_frames = 0; cp.channels = 1; cp.format = 0;
+            AF_CUDA(launch_session_ingest(cp, (uint32_t)S, st));
+            count_launch();
+            s->in_cur ^= 1; s->in_len -= consumed; s->in_base += consumed;
+        }
+    } else {
+        // passthrough keeps nothing but the 16-frame history slot
+        SessionIngest cp{};
+        cp.old_buf = s->in_buf[s->in_cur]; cp.new_buf = s->in_buf[s->in_cur ^ 1]; cp.buf_stride = s->in_stride;
+        cp.drop = s->in_len - 2 * RS_POLY; cp.keep = 2 * RS_POLY; cp.n_new_frames = 0; cp.channels = 1; cp.format = 0;
+        AF_CUDA(launch_session_ingest(cp, (uint32_t)S, st));
+        count_launch();
+        s->in_cur ^= 1; s->in_base += (long long)(s->in_len - 2 * RS_POLY); s->in_len = 2 * RS_POLY;
+    }
+    uint32_t y_drop = s->framing ? T * s->hop : y_total;
+    if (y_drop > y_total) y_drop = y_total;
+    if (y_drop) {
+        SessionResample cp{};
+        cp.in_buf = s->in_buf[s->in_cur]; cp.in_stride = s->in_stride; cp.n_begin = cp.n_end = 0; cp.mode = RS_PASSTHROUGH;
+        cp.p = cp.q = 1;
+        cp.y_old = s->y_buf[s->y_cur]; cp.y_new = s->y_buf[s->y_cur ^ 1]; cp.y_stride = s->y_stride;
+        cp.y_drop = y_drop; cp.y_keep = y_total - y_drop;
+        AF_CUDA(launch_session_resample(cp, (uint32_t)S, st));
+        count_launch();
+        s->y_cur ^= 1;
+    }
+    s->y_len = y_total - y_drop;
+    s->frames_emitted += T;
+    AF_CUDA(cudaStreamSynchronize(st));
+    for (size_t k = 0; k < S; ++k) {
+        if (n_pcm) n_pcm[k] = n_y_new;
+        if (n_feat) n_feat[k] = cfg.n_mels ? T : 0;
+        if (n_vad) n_vad[k] = cfg.vad_enable ? T : 0;
+    }
+    return AF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+"""GPU tests of the streaming sessions (BASELINE config 5): persistent per-stream state across ticks must
+reproduce exactly what the reference objects produce when fed the same chunks:
+BatchResampler::process per tick (resampler.rs:132-147), detect per completed frame (vad.rs:97-154)."""
+import numpy as np
+import pytest
+
+from test_parity_gpu import assert_bit_equal, assert_logmel_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rate,tick,fmt,ch", [(48000, 960, "f32", 1), (44100, 882, "f32", 1), (48000, 1000, "i16", 2),
+                                               (16000, 320, "f32", 1), (32000, 77, "f32", 1)])
+def test_session_matches_reference_objects(af, orc, rate, tick, fmt, ch):
+    from audioflow import synth
+    S, n_ticks = 5, 40
+    total = tick * n_ticks
+    xs = [synth.stream(60 + i, total / rate + 0.01, rate, ch, fmt)[: total * ch] for i in range(S)]
+    pipe = af.Pipeline(af.pipeline_config(n_mels=80))
+    ses = af.Session(pipe, S, rate, ch, af.AF_FMT_I16 if fmt == "i16" else af.AF_FMT_F32, max_tick_samples=tick * ch)
+    pcm = [[] for _ in range(S)]
+    lm = [[] for _ in range(S)]
+    vad = [[] for _ in range(S)]
+    per_tick_counts = []
+    for t in range(n_ticks):
+        x = np.stack([xs[i][t * tick * ch:(t + 1) * tick * ch] for i in range(S)])
+        r = ses.push(x)
+        per_tick_counts.append(r["pcm"].shape[1])
+        for i in range(S):
+            pcm[i].append(r["pcm"][i]); lm[i].append(r["logmel"][i]); vad[i].append(r["vad"][i])
+    for i in range(S):
+        xi = orc.i16_to_f32(xs[i]) if fmt == "i16" else xs[i]
+        mono = orc.to_mono(xi, ch)
+        b = orc.BatchResampler(rate, 16000)
+        ref_chunks = [b.process(mono[t * tick:(t + 1) * tick]) for t in range(n_ticks)]
+        if i == 0:
+            assert per_tick_counts == [len(c) for c in ref_chunks]          # per-call output counts (chunk recurrence)
+        ref_pcm = np.concatenate(ref_chunks)
+        got_pcm = np.concatenate(pcm[i])
+        assert_bit_equal(got_pcm, ref_pcm, f"session pcm {i}")
+        T = orc.num_frames(len(ref_pcm))
+        got_vad = np.concatenate(vad[i])
+        got_lm = np.concatenate(lm[i])
+        assert len(got_vad) == T and got_lm.shape == (T, 80)
+        v = orc.VoiceActivityDetector()
+        st, _ = v.stream(ref_pcm, 400, 160)
+        assert_bit_equal(got_vad, st, f"session vad {i}")
+        assert_logmel_close(got_lm, orc.logmel(ref_pcm, orc.default_feat_config(80)), f"session logmel {i}")
+    fin = r["vad_final"][S - 1]
+    assert fin["state"] == v.state() and fin["speech_frames"] == v.speech_frame_count()
+
+
+def test_session_reset_and_20ms_vad(af, orc):
+    """resample + VAD on 20 ms frames only (the reference's intended loop), two passes separated by reset()."""
+    from audioflow import synth
+    S, tick, n_ticks = 3, 960, 25
+    xs = [synth.stream(80 + i, 0.6, 48000, 1)[: tick * n_ticks] for i in range(S)]
+    pipe = af.Pipeline(af.pipeline_config(n_mels=0, vad_frame_len=320, vad_hop=320))
+    ses = af.Session(pipe, S, 48000, 1, af.AF_FMT_F32, max_tick_samples=tick)
+    for rep in range(2):
+        vad = [[] for _ in range(S)]
+        for t in range(n_ticks):
+            r = ses.push(np.stack([x[t * tick:(t + 1) * tick] for x in xs]))
+            for i in range(S):
+                vad[i].append(r["vad"][i])
+        for i in range(S):
+            b = orc.BatchResampler(48000, 16000)
+            ref_pcm = np.concatenate([b.process(xs[i][t * tick:(t + 1) * tick]) for t in range(n_ticks)])
+            st, _ = orc.VoiceActivityDetector().stream(ref_pcm, 320, 320)
+            assert_bit_equal(np.concatenate(vad[i]), st, f"rep {rep} stream {i}")
+        ses.reset()
