@@ -35,10 +35,9 @@ constexpr int YBUF_FLOATS = ((ypad(YLEN + 32) + 31) / 32) * 32;
 
 constexpr int SCR_ROW = 18;                  // complex per transposed row (16 + 2 pad -> LDS.128 conflict free)
 constexpr int SCR_FLOATS_PER_FRAME = 16 * SCR_ROW * 2;   // 576 floats = 2304 B
+constexpr int PB_ROW = SF + 4;               // floats per power row: 16 frames + 4 pad (16-byte aligned rows)
+constexpr int PBUF_FLOATS = NBIN * PB_ROW;
 constexpr int STAGE_BYTES = 34816;           // TMA-staged raw input of one step (34 KB)
-// per-warp views inside its 2 x SCR_FLOATS_PER_FRAME scratch once the transposes are done:
-constexpr int WP_POWER = 0;                  // float2 power[257]: 4|X[k]|^2 of the warp's two frames
-constexpr int WP_LOGMEL = 520;               // float logmel[2][n_mels] (<= 256 floats)
 
 // formats / flags (mirror include/audioflow_gpu.h)
 enum : uint16_t { FMT_F32 = 0, FMT_I16 = 1 };
@@ -75,7 +74,6 @@ struct MelTables {
     uint16_t off[MAX_MELS];  // offset into w
     uint16_t n_w;
     uint16_t n_mels;
-    uint8_t sched[32][4];    // lane -> up to 4 filters (0xFF = none), balanced by nonzero count (LPT)
     float w[2 * NBIN + 2 * MAX_MELS];
 };
 

@@ -17,7 +17,8 @@ namespace af {
 struct __align__(128) FusedSmem {
     unsigned char stage[STAGE_BYTES];                // raw interleaved input of one step (bulk-copy target)
     float ybuf[YBUF_FLOATS];                         // padded 16 kHz samples of the current step
-    float scr[16 * SCR_FLOATS_PER_FRAME];            // per half-warp transpose scratch; then per-warp power + log-mel
+    float scr[16 * SCR_FLOATS_PER_FRAME];            // per half-warp transpose scratch / log-mel stage
+    float pbuf[PBUF_FLOATS];                         // 4*|X[k]|^2, [bin][frame]
     FftTables fft;
     MelTables mel;
     StreamDev stream;                                // descriptor of the tile's stream
@@ -66,6 +67,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  : "memory");
 }
 
+// shared-memory load the compiler cannot rematerialise at the use site: keeps per-lane constants in registers
+__device__ __forceinline__ float2 lds_f2_pinned(const void *p)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(smem_u32(p)));
+    return v;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int count)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -202,7 +210,9 @@ __device__ __forceinline__ void resample_step_fast(FusedSmem &sm, const StreamDe
         // is an 8-byte aligned float2 followed by three 16-byte aligned float4 of the stage (14 floats, 13 used)
         const float *stg = reinterpret_cast<const float *>(sm.stage);
         const int kbase = sm.tile_k + 3 * (int)tile_off - 1 - f_lo;
-        for (int i4 = i_begin + 4 * tid; i4 < YLEN; i4 += 4 * FUSED_THREADS) {
+        // start on a 32-sample boundary of the padded step buffer so that every quarter-warp stores 128 contiguous bytes
+        for (int i4 = (i_begin & ~31) + 4 * tid; i4 < YLEN; i4 += 4 * FUSED_THREADS) {
+            if (i4 < i_begin) continue;
             const float *px = stg + (kbase + 3 * i4);
             float v[14];
             const float2 h = *reinterpret_cast<const float2 *>(px);
@@ -319,28 +329,23 @@ __device__ __forceinline__ void resample_step(FusedSmem &sm, const StreamDev &s,
     }
 }
 
-// ---- phase 2a: one frame per half-warp: window, packed real FFT, power -> pw[bin][half] (warp private) ----
-__device__ __forceinline__ void fft_frame(FusedSmem &sm, float *__restrict__ scr, float *__restrict__ pw, int q, int l,
-                                          int lane)
+// ---- phase 2a: one frame per half-warp: window, packed real FFT, power -> pbuf[bin][q] ----
+__device__ __forceinline__ void fft_frame(FusedSmem &sm, float *__restrict__ scr, int q, int l, int lane,
+                                          const float2 (&tw2r)[8], const float2 (&winr)[13])
 {
     float xr[16], xi[16];
     const float *yb = sm.ybuf + 180 * q + 2 * l;      // ypad(160 q + 32 n1 + 2 l) = 180 q + 36 n1 + 2 l
-    const float *wb = sm.fft.window + 2 * l;
 #pragma unroll
     for (int n1 = 0; n1 < 12; ++n1) {
         const float2 v = *reinterpret_cast<const float2 *>(yb + 36 * n1);
-        const float2 w = *reinterpret_cast<const float2 *>(wb + 32 * n1);
-        xr[n1] = __fmul_rn(v.x, w.x);
-        xi[n1] = __fmul_rn(v.y, w.y);
+        xr[n1] = __fmul_rn(v.x, winr[n1].x);
+        xi[n1] = __fmul_rn(v.y, winr[n1].y);
     }
     {
-        float2 v = make_float2(0.0f, 0.0f), w = make_float2(0.0f, 0.0f);
-        if (l < 8) {                                   // samples 384 + 2l (+1) < 400
-            v = *reinterpret_cast<const float2 *>(yb + 36 * 12);
-            w = *reinterpret_cast<const float2 *>(wb + 32 * 12);
-        }
-        xr[12] = __fmul_rn(v.x, w.x);
-        xi[12] = __fmul_rn(v.y, w.y);
+        float2 v = make_float2(0.0f, 0.0f);
+        if (l < 8) v = *reinterpret_cast<const float2 *>(yb + 36 * 12);   // samples 384 + 2l (+1) < 400; winr[12] is 0 beyond
+        xr[12] = __fmul_rn(v.x, winr[12].x);
+        xi[12] = __fmul_rn(v.y, winr[12].y);
     }
 #pragma unroll
     for (int n1 = 13; n1 < 16; ++n1) { xr[n1] = 0.0f; xi[n1] = 0.0f; }
@@ -368,7 +373,7 @@ __device__ __forceinline__ void fft_frame(FusedSmem &sm, float *__restrict__ scr
     // Z[l + 16 k2] is in slot(k2).  Hermitian split: pair k = l + 16 r with 256 - k, which lives in
     // lane (16 - l) & 15 at k2 = 15 - r (lane 0 pairs with itself at k2 = (16 - r) & 15).
     const int src = ((16 - l) & 15) | (lane & 16);
-    float *pb = pw + (lane >> 4);                       // interleaved: power of frame `half` at pw[2 k + half]
+    float *pb = sm.pbuf + q;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const float zr = xr[fft16_slot(r)], zi = xi[fft16_slot(r)];
@@ -376,19 +381,19 @@ __device__ __forceinline__ void fft_frame(FusedSmem &sm, float *__restrict__ scr
         float pi = __shfl_sync(0xffffffffu, xi[fft16_slot(15 - r)], src);
         if (l == 0) { pr = xr[fft16_slot((16 - r) & 15)]; pi = xi[fft16_slot((16 - r) & 15)]; }
         const int k = l + 16 * r;
-        const float2 w = sm.fft.tw2[k];
+        const float2 w = tw2r[r];
         const float e2r = zr + pr, e2i = zi - pi;      // 2E = Z[k] + conj(Z[256-k])
         const float o2r = zi + pi, o2i = pr - zr;      // 2O = -i (Z[k] - conj(Z[256-k]))
         const float tr = w.x * o2r - w.y * o2i;
         const float ti = w.x * o2i + w.y * o2r;
         const float ar = e2r + tr, ai = e2i + ti;      // 2 X[k]
         const float br = e2r - tr, bi = e2i - ti;      // 2 conj(X[256-k])
-        pb[2 * k] = ar * ar + ai * ai;
-        pb[2 * (256 - k)] = br * br + bi * bi;
+        pb[k * PB_ROW] = ar * ar + ai * ai;
+        pb[(256 - k) * PB_ROW] = br * br + bi * bi;
     }
     if (l == 0) {                                       // k = 128 pairs with itself
         const float zr = xr[fft16_slot(8)], zi = xi[fft16_slot(8)];
-        pb[2 * 128] = 4.0f * (zr * zr + zi * zi);
+        pb[128 * PB_ROW] = 4.0f * (zr * zr + zi * zi);
     }
 }
 
@@ -444,6 +449,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
         if (blockIdx.x < P.n_tiles) issue_fill(sm, P, blockIdx.x, 0);
     }
     __syncthreads();
+    float2 tw2r[8];                                     // W512^(l + 16 r): this lane's post-twiddles, register resident
+#pragma unroll
+    for (int r = 0; r < 8; ++r) tw2r[r] = lds_f2_pinned(&sm.fft.tw2[l + 16 * r]);
+    float2 winr[13];                                    // this lane's window samples w[32 n1 + 2 l], w[32 n1 + 2 l + 1]
+#pragma unroll
+    for (int n1 = 0; n1 < 13; ++n1) winr[n1] = lds_f2_pinned(sm.fft.window + 32 * n1 + 2 * l);
     const float log_mul = P.log_scale;
     uint32_t fill_parity = 0;
 
@@ -529,56 +540,50 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
                         }
                     }
                 }
-                float *wscr = sm.scr + warp * 2 * SCR_FLOATS_PER_FRAME;        // this warp's 4.5 KB
-                const bool do_fft = M && warp * 2 < n_valid;                  // warp-uniform: skip fully invalid pairs
-                if (do_fft) fft_frame(sm, wscr + half * SCR_FLOATS_PER_FRAME, wscr + WP_POWER, warp * 2 + half, l, lane);
+                if (M && warp * 2 < n_valid) {                        // warp-uniform: skip fully invalid pairs
+                    const int hw = warp * 2 + half;
+                    fft_frame(sm, sm.scr + hw * SCR_FLOATS_PER_FRAME, hw, l, lane, tw2r, winr);
+                }
                 __syncwarp();
                 named_bar_arrive(2, FUSED_THREADS);                   // ybuf no longer needed by this warp
+                named_bar_sync(1, FFT_WARPS * 32);                    // pbuf complete
 
-                // ---- phase 3 (warp local): mel + log of the warp's two frames; lane = balanced set of filters ----
-                if (do_fft) {
-                    const float2 *pw = reinterpret_cast<const float2 *>(wscr + WP_POWER);
-                    float *lmw = wscr + WP_LOGMEL;
-#pragma unroll 1
-                    for (int t = 0; t < 4; ++t) {
-                        const int m = sm.mel.sched[lane][t];
-                        if (m == 0xFF) break;
-                        const int cnt = sm.mel.cnt[m];
+                // ---- phase 3: mel + log into the stage (thread = filter x 4 frames) ----
+                if (M && n_valid > 0) {
+                    const int n_items = (int)M * (SF / 4);
+                    for (int item = tid; item < n_items; item += FFT_WARPS * 32) {
+                        const int m = item >> 2, fq = item & 3;
+                        if (fq * 4 >= n_valid) continue;
+                        const int lo = sm.mel.lo[m], cnt = sm.mel.cnt[m];
                         const float *w = sm.mel.w + sm.mel.off[m];
-                        const float2 *pp = pw + sm.mel.lo[m];
-                        float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
+                        const float *pp = sm.pbuf + lo * PB_ROW + 4 * fq;
+                        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
                         int j = 0;
                         for (; j + 2 <= cnt; j += 2) {
                             const float w0 = w[j], w1 = w[j + 1];
-                            const float2 p0 = pp[j], p1 = pp[j + 1];
-                            a0 = fmaf(w0, p0.x, a0); a1 = fmaf(w0, p0.y, a1);
-                            b0 = fmaf(w1, p1.x, b0); b1 = fmaf(w1, p1.y, b1);
+                            const float4 p0 = *reinterpret_cast<const float4 *>(pp + j * PB_ROW);
+                            const float4 p1 = *reinterpret_cast<const float4 *>(pp + (j + 1) * PB_ROW);
+                            a0 = fmaf(w0, p0.x, a0); a1 = fmaf(w0, p0.y, a1); a2 = fmaf(w0, p0.z, a2); a3 = fmaf(w0, p0.w, a3);
+                            a0 = fmaf(w1, p1.x, a0); a1 = fmaf(w1, p1.y, a1); a2 = fmaf(w1, p1.z, a2); a3 = fmaf(w1, p1.w, a3);
                         }
                         if (j < cnt) {
                             const float w0 = w[j];
-                            const float2 p0 = pp[j];
-                            a0 = fmaf(w0, p0.x, a0); a1 = fmaf(w0, p0.y, a1);
+                            const float4 p0 = *reinterpret_cast<const float4 *>(pp + j * PB_ROW);
+                            a0 = fmaf(w0, p0.x, a0); a1 = fmaf(w0, p0.y, a1); a2 = fmaf(w0, p0.z, a2); a3 = fmaf(w0, p0.w, a3);
                         }
-                        lmw[m] = __log2f(fmaxf(a0 + b0, P.log_floor)) * log_mul;
-                        lmw[M + m] = __log2f(fmaxf(a1 + b1, P.log_floor)) * log_mul;
-                    }
-                    __syncwarp();
-                    // ---- phase 4 (warp local): the warp's rows are contiguous in the [frame][mel] output ----
-                    if (lm_row) {
-                        const int rows = min(2, n_valid - warp * 2);
-                        float *dst = lm_row + (uint64_t)(f0 + warp * 2) * M;
-                        const int total = rows * (int)M;
-                        if ((M & 3) == 0) {
-                            for (int i = lane; i < (total >> 2); i += 32)
-                                reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(lmw)[i];
-                        } else {
-                            for (int i = lane; i < total; i += 32) dst[i] = lmw[i];
+                        // the 8 consecutive filters of a quarter-warp fill one 32-byte sector per frame row
+                        if (lm_row) {
+                            float *dst = lm_row + (uint64_t)(f0 + 4 * fq) * M + m;
+                            const int nv = n_valid - 4 * fq;
+                            dst[0] = __log2f(fmaxf(a0, P.log_floor)) * log_mul;
+                            if (nv > 1) dst[M] = __log2f(fmaxf(a1, P.log_floor)) * log_mul;
+                            if (nv > 2) dst[2 * M] = __log2f(fmaxf(a2, P.log_floor)) * log_mul;
+                            if (nv > 3) dst[3 * M] = __log2f(fmaxf(a3, P.log_floor)) * log_mul;
                         }
                     }
-                    __syncwarp();
                 }
             }
-            __syncthreads();        // ybuf carried, log-mel stage consumed: the next phase 1 may overwrite both
+            __syncthreads();        // ybuf carried, pbuf consumed: the next phase 1 / FFT may overwrite them
         }
         __syncthreads();
     }

@@ -94,18 +94,6 @@ bool build_mel_tables(uint32_t n_mels, float f_min, float f_max, MelTables *t)
         for (int k = lo; k < hi; ++k) t->w[off++] = w[k] * 0.25f;    // pbuf holds 4 |X|^2
     }
     t->n_w = (uint16_t)off; t->n_mels = (uint16_t)n_mels;
-    // lane schedule: longest-processing-time-first over the filters' nonzero counts, at most 4 per lane
-    std::memset(t->sched, 0xFF, sizeof(t->sched));
-    std::vector<uint32_t> order(n_mels), load(32, 0), used(32, 0);
-    for (uint32_t m = 0; m < n_mels; ++m) order[m] = m;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return t->cnt[a] > t->cnt[b]; });
-    for (uint32_t m : order) {
-        int best = -1;
-        for (int l = 0; l < 32; ++l)
-            if (used[l] < 4 && (best < 0 || load[l] < load[best])) best = l;
-        t->sched[best][used[best]++] = (uint8_t)m;
-        load[best] += t->cnt[m] + 4;            // + fixed per-filter overhead (log, stores)
-    }
     return true;
 }
 

@@ -15,3 +15,5 @@ CMD="python bench.py --steps 3 --warmup 3 --e2e-steps 0 --no-cpu-baseline"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:af_fused -s 3 -c 1 -f -o gpurun_out/prof_fused $CMD > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+grep -E "af_" gpurun_out/launches.csv | awk -F'","' '{print $5, $NF}' | sort | uniq -c | sort -rn | head -12
