@@ -25,8 +25,10 @@ constexpr int YLEN = STEP_SAMPLES + CARRY;   // 2800 samples live per step
 constexpr int TILE_FRAMES = 128;             // frames per tile (work unit of one CTA)
 constexpr int TILE_SAMPLES = TILE_FRAMES * HOP;   // 20480
 constexpr int FFT_WARPS = 8;
-constexpr int FUSED_WARPS = FFT_WARPS + 1;   // + 1 VAD warp
-constexpr int FUSED_THREADS = FUSED_WARPS * 32;   // 288
+constexpr int VAD_WARP = FFT_WARPS;          // warp 8: stage fills (TMA) + sequential frame energies
+constexpr int AUX_WARP = FFT_WARPS + 1;      // warp 9: PCM write-out + overlap carry
+constexpr int FUSED_WARPS = FFT_WARPS + 2;
+constexpr int FUSED_THREADS = FUSED_WARPS * 32;   // 320: 640 resample quads, 640 PCM float4, 320 mel items per step
 
 // padded index of 16 kHz sample i inside the step buffer: 4 pad words after every 32 samples so
 // that the 32 VAD lanes (frame starts 160 apart) hit distinct bank quads with LDS.128

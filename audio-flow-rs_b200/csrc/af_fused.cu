@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l = lane & 15, half = lane >> 4;
     const uint32_t M = P.n_mels;
-    const bool is_filler = (tid == FUSED_THREADS - 1);              // last lane of the VAD warp (it has no frame)
+    const bool is_filler = (tid == VAD_WARP * 32 + 31);             // last lane of the VAD warp (it has no frame)
 
     // constant tables -> shared memory (once per CTA)
     {
@@ -511,24 +511,23 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
             }
             __syncthreads();
 
-            if (warp == FFT_WARPS) {
-                // ================= VAD warp: runs beside phases 2-4 of the FFT warps =================
-                if (is_filler) {                                      // next stage fill (async bulk copy)
+            // mel participants: everyone, except the VAD warp while it runs its sequential energy chains
+            const bool vad_busy = P.do_energy && en_row;
+            const int mel_threads = vad_busy ? FUSED_THREADS - 32 : FUSED_THREADS;
+            if (warp == VAD_WARP) {
+                // ===== warp 8: next stage fill (async bulk copy), then one 400-term energy chain per lane =====
+                if (is_filler) {
                     if (g + 1 < n_steps) issue_fill(sm, P, tile, g + 1);
                     else if (tile + gridDim.x < P.n_tiles) issue_fill(sm, P, tile + gridDim.x, 0);
                 }
-                if (P.do_energy && en_row && lane < n_valid) en_row[f0 + lane] = frame_energy_smem(sm.ybuf, lane);
+                if (vad_busy && lane < n_valid) en_row[f0 + lane] = frame_energy_smem(sm.ybuf, lane);
                 __syncwarp();
-                named_bar_sync(2, FUSED_THREADS);                     // every FFT warp is done reading ybuf
-                if (g + 1 < n_steps) {                                // carry the 240-sample overlap forward
-                    for (int i = lane; i < CARRY; i += 32) sm.ybuf[ypad(i)] = sm.ybuf[ypad(i) + ypad(STEP_SAMPLES)];
-                }
-            } else {
-                // ================= FFT warps (256 threads) =================
-                // ---- phase 2: PCM write-out, one frame per half-warp ----
+                named_bar_arrive(2, FUSED_THREADS);                   // done reading ybuf
+            } else if (warp == AUX_WARP) {
+                // ===== warp 9: PCM write-out of the step, then carry the 240-sample overlap forward =====
                 if (pcm_row) {
                     const uint32_t own_end = min(base + (uint32_t)STEP_SAMPLES, tile_end);
-                    for (uint32_t i4 = tid * 4; base + i4 < own_end; i4 += FFT_WARPS * 32 * 4) {
+                    for (uint32_t i4 = lane * 4; base + i4 < own_end; i4 += 32 * 4) {
                         const float4 v = *reinterpret_cast<const float4 *>(sm.ybuf + ypad((int)i4));
                         const uint32_t n = base + i4;
                         if (n + 4 <= own_end) {
@@ -540,18 +539,28 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
                         }
                     }
                 }
+                __syncwarp();
+                named_bar_sync(2, FUSED_THREADS);                     // FFT warps and the VAD warp are done reading ybuf
+                if (g + 1 < n_steps) {
+                    for (int i = lane; i < CARRY; i += 32) sm.ybuf[ypad(i)] = sm.ybuf[ypad(i) + ypad(STEP_SAMPLES)];
+                }
+            } else {
+                // ===== warps 0..7: one frame per half-warp =====
                 if (M && warp * 2 < n_valid) {                        // warp-uniform: skip fully invalid pairs
                     const int hw = warp * 2 + half;
                     fft_frame(sm, sm.scr + hw * SCR_FLOATS_PER_FRAME, hw, l, lane, tw2r, winr);
                 }
                 __syncwarp();
                 named_bar_arrive(2, FUSED_THREADS);                   // ybuf no longer needed by this warp
-                named_bar_sync(1, FFT_WARPS * 32);                    // pbuf complete
+            }
+            if (!(vad_busy && warp == VAD_WARP)) {
+                const int mtid = (vad_busy && warp == AUX_WARP) ? tid - 32 : tid;   // dense ids without the VAD warp
+                named_bar_sync(1, mel_threads);                       // pbuf complete
 
                 // ---- phase 3: mel + log into the stage (thread = filter x 4 frames) ----
                 if (M && n_valid > 0) {
                     const int n_items = (int)M * (SF / 4);
-                    for (int item = tid; item < n_items; item += FFT_WARPS * 32) {
+                    for (int item = mtid; item < n_items; item += mel_threads) {
                         const int m = item >> 2, fq = item & 3;
                         if (fq * 4 >= n_valid) continue;
                         const int lo = sm.mel.lo[m], cnt = sm.mel.cnt[m];

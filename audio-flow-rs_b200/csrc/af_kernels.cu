@@ -103,25 +103,24 @@ cudaError_t launch_frame_energy(const EnergyJob &job, cudaStream_t st)
 // minimal and run side by side: the EMA chain (fmul, fadd per frame) of block b+1 is interleaved with the
 // branch-free integer state machine of block b.  Energies arrive 16 frames ahead as 4 x float4, states
 // leave as one 16-byte store per 16 frames.
-struct VadMachine {
-    int st;
-    unsigned long long sil, spk;
+struct VadMachine {        // 32-bit working copy of (state, silence_frames, speech_frames); see the overflow guard below
+    uint32_t st, sil, spk;
 };
 
-__device__ __forceinline__ uint32_t vad_machine_step(VadMachine &m, bool sp, unsigned long long timeout,
-                                                     unsigned long long min_speech)
+// vad.rs:121-153 with the comparisons moved onto the OLD counters so that the dependent path per frame is
+// cmp -> and -> select (tm1 = timeout - 1, t0 = timeout == 0):
+//   Speech & !sp: silence+1 >= timeout  <=>  silence >= timeout-1 ; speech_frames is unchanged on that path
+__device__ __forceinline__ uint32_t vad_machine_step(VadMachine &m, uint32_t sp, uint32_t tm1, bool t0, uint32_t min_speech)
 {
-    // vad.rs:121-153, branch free
-    const bool is0 = m.st == 0, is1 = m.st == 1;
-    const unsigned long long sil1 = sp ? 0ull : m.sil + 1ull;
-    const unsigned long long spk1 = sp ? m.spk + 1ull : m.spk;
-    const bool to = is1 && !sp && sil1 >= timeout;
-    const int st1 = to ? (spk1 >= min_speech ? 2 : 0) : 1;
-    const int st_new = is0 ? (sp ? 1 : 0) : (is1 ? st1 : 0);
-    const unsigned long long spk_new = is0 ? (sp ? 1ull : m.spk) : (is1 ? (to ? 0ull : spk1) : m.spk);
-    const unsigned long long sil_new = is0 ? (sp ? 0ull : m.sil) : (is1 ? sil1 : 0ull);
-    m.st = st_new; m.spk = spk_new; m.sil = sil_new;
-    return (uint32_t)st_new;
+    const bool is0 = m.st == 0u, is1 = m.st == 1u, spb = sp != 0u;
+    const bool to = is1 && !spb && (t0 || m.sil >= tm1);
+    const bool big = m.spk >= min_speech;
+    const uint32_t st_speech = to ? (big ? 2u : 0u) : 1u;
+    const uint32_t st_new = is0 ? sp : (is1 ? st_speech : 0u);
+    const uint32_t sil_new = is1 ? (spb ? 0u : m.sil + 1u) : ((is0 && !spb) ? m.sil : 0u);
+    const uint32_t spk_new = is0 ? (spb ? 1u : m.spk) : (is1 ? (to ? 0u : m.spk + sp) : m.spk);
+    m.st = st_new; m.sil = sil_new; m.spk = spk_new;
+    return st_new;
 }
 
 __global__ void af_vad_scan_kernel(const ScanJob J)
@@ -138,55 +137,69 @@ __global__ void af_vad_scan_kernel(const ScanJob J)
     const float alpha = prm.alpha, beta = __fsub_rn(1.0f, prm.alpha), e_min = prm.e_min;
     const bool use_smoothed = alpha > 0.0f;
     float sm = v.smoothed;
-    VadMachine m{v.state, v.silence_frames, v.speech_frames};
     uint32_t f = 0;
+    // the fast path keeps the counters in 32 bits; fall back to the plain 64-bit step when they could overflow
+    const bool small = v.silence_frames < 0x40000000ull && v.speech_frames < 0x40000000ull && T < 0x40000000u &&
+                       prm.silence_timeout < 0x80000000ull && prm.min_speech < 0x80000000ull;
+    if (!small) {
+        for (; f < T; ++f) {
+            const int stv = vad_step(v, prm, e[f]);
+            if (out) out[f] = (uint8_t)stv;
+        }
+        if (J.state_io) J.state_io[s] = v;
+        if (J.final_out) J.final_out[s] = v;
+        return;
+    }
+    VadMachine m{(uint32_t)v.state, (uint32_t)v.silence_frames, (uint32_t)v.speech_frames};
+    const uint32_t timeout = (uint32_t)prm.silence_timeout, minsp = (uint32_t)prm.min_speech;
+    const bool t0 = timeout == 0u;
+    const uint32_t tm1 = t0 ? 0u : timeout - 1u;
     const bool vec_in = ((reinterpret_cast<uintptr_t>(e) & 15) == 0);
     const bool vec_out = out && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     if (vec_in && T >= 16) {
         const float4 *e4 = reinterpret_cast<const float4 *>(e);
         const uint32_t n_blocks = T / 16;
         float eb[16];
-        {
-            const float4 a = e4[0], b = e4[1], c = e4[2], d = e4[3];
-            eb[0] = a.x; eb[1] = a.y; eb[2] = a.z; eb[3] = a.w; eb[4] = b.x; eb[5] = b.y; eb[6] = b.z; eb[7] = b.w;
-            eb[8] = c.x; eb[9] = c.y; eb[10] = c.z; eb[11] = c.w; eb[12] = d.x; eb[13] = d.y; eb[14] = d.z; eb[15] = d.w;
-        }
-        uint32_t bits_cur = 0;                       // is_speech bits of the block whose machine steps are pending
-        for (uint32_t b = 0; b <= n_blocks; ++b) {
-            float4 nx[4];
-            const bool have_next = b + 1 < n_blocks;
-            if (have_next) {
+        auto unpack = [&](const float4 *src) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) nx[j] = e4[(b + 1) * 4 + j];       // prefetch
+            for (int j = 0; j < 4; ++j) { const float4 t = src[j]; eb[4 * j] = t.x; eb[4 * j + 1] = t.y; eb[4 * j + 2] = t.z; eb[4 * j + 3] = t.w; }
+        };
+        auto store16 = [&](uint32_t f0, const uint32_t (&packed)[4]) {
+            if (vec_out) {
+                *reinterpret_cast<uint4 *>(out + f0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            } else if (out) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) out[f0 + j] = (uint8_t)(packed[j >> 2] >> (8 * (j & 3)));
             }
+        };
+        // prologue: EMA chain of block 0 (vad.rs:101-118)
+        unpack(e4);
+        uint32_t bits_cur = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            sm = __fadd_rn(__fmul_rn(alpha, eb[j]), __fmul_rn(beta, sm));
+            bits_cur |= ((use_smoothed ? sm : eb[j]) >= e_min ? 1u : 0u) << j;
+        }
+        // steady state: EMA chain of block b beside the state machine of block b - 1 (two independent chains)
+        for (uint32_t b = 1; b < n_blocks; ++b) {
+            unpack(e4 + b * 4);
             uint32_t bits_new = 0, packed[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                if (b < n_blocks) {                  // EMA chain of block b (vad.rs:101-118)
-                    sm = __fadd_rn(__fmul_rn(alpha, eb[j]), __fmul_rn(beta, sm));
-                    const float det = use_smoothed ? sm : eb[j];
-                    bits_new |= (det >= e_min ? 1u : 0u) << j;
-                }
-                if (b > 0) {                         // state machine of block b - 1
-                    const uint32_t stv = vad_machine_step(m, (bits_cur >> j) & 1u, prm.silence_timeout, prm.min_speech);
-                    packed[j >> 2] |= stv << (8 * (j & 3));
-                }
+                sm = __fadd_rn(__fmul_rn(alpha, eb[j]), __fmul_rn(beta, sm));
+                bits_new |= ((use_smoothed ? sm : eb[j]) >= e_min ? 1u : 0u) << j;
+                packed[j >> 2] |= vad_machine_step(m, (bits_cur >> j) & 1u, tm1, t0, minsp) << (8 * (j & 3));
             }
-            if (b > 0) {
-                const uint32_t f0 = (b - 1) * 16;
-                if (vec_out) {
-                    *reinterpret_cast<uint4 *>(out + f0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                } else if (out) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) out[f0 + j] = (uint8_t)(packed[j >> 2] >> (8 * (j & 3)));
-                }
-            }
+            store16((b - 1) * 16, packed);
             bits_cur = bits_new;
-            if (have_next) {
-                eb[0] = nx[0].x; eb[1] = nx[0].y; eb[2] = nx[0].z; eb[3] = nx[0].w; eb[4] = nx[1].x; eb[5] = nx[1].y;
-                eb[6] = nx[1].z; eb[7] = nx[1].w; eb[8] = nx[2].x; eb[9] = nx[2].y; eb[10] = nx[2].z; eb[11] = nx[2].w;
-                eb[12] = nx[3].x; eb[13] = nx[3].y; eb[14] = nx[3].z; eb[15] = nx[3].w;
-            }
+        }
+        // epilogue: state machine of the last block
+        {
+            uint32_t packed[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                packed[j >> 2] |= vad_machine_step(m, (bits_cur >> j) & 1u, tm1, t0, minsp) << (8 * (j & 3));
+            store16((n_blocks - 1) * 16, packed);
         }
         f = n_blocks * 16;
     }
@@ -194,10 +207,10 @@ __global__ void af_vad_scan_kernel(const ScanJob J)
         const float ev = e[f];
         sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
         const float det = use_smoothed ? sm : ev;
-        const uint32_t stv = vad_machine_step(m, det >= e_min, prm.silence_timeout, prm.min_speech);
+        const uint32_t stv = vad_machine_step(m, det >= e_min ? 1u : 0u, tm1, t0, minsp);
         if (out) out[f] = (uint8_t)stv;
     }
-    v.smoothed = sm; v.state = m.st; v.silence_frames = m.sil; v.speech_frames = m.spk;
+    v.smoothed = sm; v.state = (int)m.st; v.silence_frames = m.sil; v.speech_frames = m.spk;
     if (J.state_io) J.state_io[s] = v;
     if (J.final_out) J.final_out[s] = v;
 }
