@@ -527,15 +527,28 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
                 // ===== warp 9: PCM write-out of the step, then carry the 240-sample overlap forward =====
                 if (pcm_row) {
                     const uint32_t own_end = min(base + (uint32_t)STEP_SAMPLES, tile_end);
-                    for (uint32_t i4 = lane * 4; base + i4 < own_end; i4 += 32 * 4) {
-                        const float4 v = *reinterpret_cast<const float4 *>(sm.ybuf + ypad((int)i4));
-                        const uint32_t n = base + i4;
-                        if (n + 4 <= own_end) {
-                            *reinterpret_cast<float4 *>(pcm_row + n) = v;
-                        } else {
-                            if (n < own_end) pcm_row[n] = v.x;
-                            if (n + 1 < own_end) pcm_row[n + 1] = v.y;
-                            if (n + 2 < own_end) pcm_row[n + 2] = v.z;
+                    if (own_end == base + (uint32_t)STEP_SAMPLES) {
+                        // full step: 640 float4, 20 per lane, loads batched ahead of the stores
+                        float4 *dst = reinterpret_cast<float4 *>(pcm_row + base);
+#pragma unroll
+                        for (int it = 0; it < 20; it += 5) {
+                            float4 v[5];
+#pragma unroll
+                            for (int u = 0; u < 5; ++u) v[u] = *reinterpret_cast<const float4 *>(sm.ybuf + ypad(4 * (lane + 32 * (it + u))));
+#pragma unroll
+                            for (int u = 0; u < 5; ++u) dst[lane + 32 * (it + u)] = v[u];
+                        }
+                    } else {
+                        for (uint32_t i4 = lane * 4; base + i4 < own_end; i4 += 32 * 4) {
+                            const float4 v = *reinterpret_cast<const float4 *>(sm.ybuf + ypad((int)i4));
+                            const uint32_t n = base + i4;
+                            if (n + 4 <= own_end) {
+                                *reinterpret_cast<float4 *>(pcm_row + n) = v;
+                            } else {
+                                if (n < own_end) pcm_row[n] = v.x;
+                                if (n + 1 < own_end) pcm_row[n + 1] = v.y;
+                                if (n + 2 < own_end) pcm_row[n + 2] = v.z;
+                            }
                         }
                     }
                 }
