@@ -511,9 +511,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
             }
             __syncthreads();
 
-            // mel participants: everyone, except the VAD warp while it runs its sequential energy chains
+            // the 400-term energy chains of the VAD warp (>= 1600 cycles) run beside the FFT phase of warps 0..7
             const bool vad_busy = P.do_energy && en_row;
-            const int mel_threads = vad_busy ? FUSED_THREADS - 32 : FUSED_THREADS;
+            const int mel_threads = FUSED_THREADS;
             if (warp == VAD_WARP) {
                 // ===== warp 8: next stage fill (async bulk copy), then one 400-term energy chain per lane =====
                 if (is_filler) {
@@ -566,8 +566,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
                 __syncwarp();
                 named_bar_arrive(2, FUSED_THREADS);                   // ybuf no longer needed by this warp
             }
-            if (!(vad_busy && warp == VAD_WARP)) {
-                const int mtid = (vad_busy && warp == AUX_WARP) ? tid - 32 : tid;   // dense ids without the VAD warp
+            {
+                const int mtid = tid;
                 named_bar_sync(1, mel_threads);                       // pbuf complete
 
                 // ---- phase 3: mel + log into the stage (thread = filter x 4 frames) ----
