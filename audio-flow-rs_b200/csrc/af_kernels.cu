@@ -99,28 +99,65 @@ cudaError_t launch_frame_energy(const EnergyJob &job, cudaStream_t st)
 }
 
 // ---- detect() EMA + threshold + state machine (vad.rs:101-153): strictly sequential per stream ----
-// One thread per stream; the kernel is bound by the latency of two dependent chains, so they are kept
-// minimal and run side by side: the EMA chain (fmul, fadd per frame) of block b+1 is interleaved with the
-// branch-free integer state machine of block b.  Energies arrive 16 frames ahead as 4 x float4, states
-// leave as one 16-byte store per 16 frames.
+// One thread per stream; latency bound.  Per 32 frames: (1) the EMA chain (fmul, fadd per frame, the only
+// floating-point recurrence) produces a word of is_speech bits, (2) the state machine consumes the word
+// RUN BY RUN (ffs on the bit word) instead of frame by frame: a run of equal decisions changes the state at
+// most once (Silence->Speech on the first 1, Speech->Ending/Silence on the zero that reaches the timeout).
 struct VadMachine {        // 32-bit working copy of (state, silence_frames, speech_frames); see the overflow guard below
     uint32_t st, sil, spk;
 };
 
-// vad.rs:121-153 with the comparisons moved onto the OLD counters so that the dependent path per frame is
-// cmp -> and -> select (tm1 = timeout - 1, t0 = timeout == 0):
-//   Speech & !sp: silence+1 >= timeout  <=>  silence >= timeout-1 ; speech_frames is unchanged on that path
-__device__ __forceinline__ uint32_t vad_machine_step(VadMachine &m, uint32_t sp, uint32_t tm1, bool t0, uint32_t min_speech)
+__device__ __forceinline__ void vad_emit(uint8_t *out, uint32_t f, uint32_t count, uint32_t v)
 {
-    const bool is0 = m.st == 0u, is1 = m.st == 1u, spb = sp != 0u;
-    const bool to = is1 && !spb && (t0 || m.sil >= tm1);
-    const bool big = m.spk >= min_speech;
-    const uint32_t st_speech = to ? (big ? 2u : 0u) : 1u;
-    const uint32_t st_new = is0 ? sp : (is1 ? st_speech : 0u);
-    const uint32_t sil_new = is1 ? (spb ? 0u : m.sil + 1u) : ((is0 && !spb) ? m.sil : 0u);
-    const uint32_t spk_new = is0 ? (spb ? 1u : m.spk) : (is1 ? (to ? 0u : m.spk + sp) : m.spk);
-    m.st = st_new; m.sil = sil_new; m.spk = spk_new;
-    return st_new;
+    if (!out) return;
+    for (uint32_t i = 0; i < count; ++i) out[f + i] = (uint8_t)v;     // independent byte stores
+}
+
+// consumes n (<= 32) decisions, bit j of `bits` = frame f0 + j; exact vad.rs:121-153 semantics
+__device__ __forceinline__ void vad_machine_word(VadMachine &m, uint32_t bits, uint32_t n, uint32_t f0, uint8_t *out,
+                                                 uint32_t timeout, uint32_t min_speech)
+{
+    uint32_t j = 0;
+    while (j < n) {
+        const uint32_t rem = bits >> j;                   // bit 0 = decision of frame j (bits above n are zero)
+        if (m.st == 0u) {                                 // Silence: zeros keep it; the first 1 enters Speech
+            if (rem == 0u) { vad_emit(out, f0 + j, n - j, 0u); j = n; break; }
+            const uint32_t z = (uint32_t)__ffs((int)rem) - 1u;
+            vad_emit(out, f0 + j, z, 0u);
+            m.st = 1u; m.spk = 1u; m.sil = 0u;
+            vad_emit(out, f0 + j + z, 1u, 1u);
+            j += z + 1u;
+        } else if (m.st == 1u) {
+            if (rem & 1u) {                               // run of speech frames
+                uint32_t r = (uint32_t)__ffs((int)~rem) - 1u;        // ~rem != 0 or ffs gives 0 -> r = 0xffffffff
+                if (~rem == 0u) r = 32u;
+                r = min(r, n - j);
+                m.spk += r; m.sil = 0u;
+                vad_emit(out, f0 + j, r, 1u);
+                j += r;
+            } else {                                      // run of non-speech frames
+                uint32_t r = rem ? (uint32_t)__ffs((int)rem) - 1u : 32u;
+                r = min(r, n - j);
+                const uint32_t need = timeout > m.sil ? timeout - m.sil : 1u;   // zeros until silence_frames >= timeout
+                if (r < need) {
+                    m.sil += r;
+                    vad_emit(out, f0 + j, r, 1u);
+                    j += r;
+                } else {
+                    vad_emit(out, f0 + j, need - 1u, 1u);
+                    m.sil += need;
+                    m.st = m.spk >= min_speech ? 2u : 0u;
+                    m.spk = 0u;
+                    vad_emit(out, f0 + j + need - 1u, 1u, m.st);
+                    j += need;
+                }
+            }
+        } else {                                          // Ending: one frame, whatever it is
+            m.st = 0u; m.sil = 0u;
+            vad_emit(out, f0 + j, 1u, 0u);
+            j += 1u;
+        }
+    }
 }
 
 __global__ void af_vad_scan_kernel(const ScanJob J)
@@ -134,15 +171,11 @@ __global__ void af_vad_scan_kernel(const ScanJob J)
     if (J.state_io) v = J.state_io[s];
     else { v.smoothed = 0.0f; v.state = 0; v.silence_frames = 0; v.speech_frames = 0; }
     const VadParams prm = J.prm;
-    const float alpha = prm.alpha, beta = __fsub_rn(1.0f, prm.alpha), e_min = prm.e_min;
-    const bool use_smoothed = alpha > 0.0f;
-    float sm = v.smoothed;
-    uint32_t f = 0;
     // the fast path keeps the counters in 32 bits; fall back to the plain 64-bit step when they could overflow
     const bool small = v.silence_frames < 0x40000000ull && v.speech_frames < 0x40000000ull && T < 0x40000000u &&
-                       prm.silence_timeout < 0x80000000ull && prm.min_speech < 0x80000000ull;
+                       prm.silence_timeout < 0x40000000ull && prm.min_speech < 0x80000000ull;
     if (!small) {
-        for (; f < T; ++f) {
+        for (uint32_t f = 0; f < T; ++f) {
             const int stv = vad_step(v, prm, e[f]);
             if (out) out[f] = (uint8_t)stv;
         }
@@ -150,65 +183,50 @@ __global__ void af_vad_scan_kernel(const ScanJob J)
         if (J.final_out) J.final_out[s] = v;
         return;
     }
+    const float alpha = prm.alpha, beta = __fsub_rn(1.0f, prm.alpha), e_min = prm.e_min;
+    const bool use_smoothed = alpha > 0.0f;
+    float sm = v.smoothed;
     VadMachine m{(uint32_t)v.state, (uint32_t)v.silence_frames, (uint32_t)v.speech_frames};
     const uint32_t timeout = (uint32_t)prm.silence_timeout, minsp = (uint32_t)prm.min_speech;
-    const bool t0 = timeout == 0u;
-    const uint32_t tm1 = t0 ? 0u : timeout - 1u;
+    uint32_t f = 0;
     const bool vec_in = ((reinterpret_cast<uintptr_t>(e) & 15) == 0);
-    const bool vec_out = out && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    if (vec_in && T >= 16) {
+    if (vec_in && T >= 32) {
         const float4 *e4 = reinterpret_cast<const float4 *>(e);
-        const uint32_t n_blocks = T / 16;
-        float eb[16];
-        auto unpack = [&](const float4 *src) {
+        const uint32_t n_words = T / 32;
+        float4 cur[8], nxt[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { const float4 t = src[j]; eb[4 * j] = t.x; eb[4 * j + 1] = t.y; eb[4 * j + 2] = t.z; eb[4 * j + 3] = t.w; }
-        };
-        auto store16 = [&](uint32_t f0, const uint32_t (&packed)[4]) {
-            if (vec_out) {
-                *reinterpret_cast<uint4 *>(out + f0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            } else if (out) {
+        for (int j = 0; j < 8; ++j) cur[j] = e4[j];
+        for (uint32_t w = 0; w < n_words; ++w) {
+            if (w + 1 < n_words) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) out[f0 + j] = (uint8_t)(packed[j >> 2] >> (8 * (j & 3)));
+                for (int j = 0; j < 8; ++j) nxt[j] = e4[(w + 1) * 8 + j];       // prefetch the next 32 energies
             }
-        };
-        // prologue: EMA chain of block 0 (vad.rs:101-118)
-        unpack(e4);
-        uint32_t bits_cur = 0;
+            uint32_t bits = 0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            sm = __fadd_rn(__fmul_rn(alpha, eb[j]), __fmul_rn(beta, sm));
-            bits_cur |= ((use_smoothed ? sm : eb[j]) >= e_min ? 1u : 0u) << j;
-        }
-        // steady state: EMA chain of block b beside the state machine of block b - 1 (two independent chains)
-        for (uint32_t b = 1; b < n_blocks; ++b) {
-            unpack(e4 + b * 4);
-            uint32_t bits_new = 0, packed[4] = {0, 0, 0, 0};
+            for (int j = 0; j < 8; ++j) {                 // EMA chain (vad.rs:101-118)
+                const float ev[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                sm = __fadd_rn(__fmul_rn(alpha, eb[j]), __fmul_rn(beta, sm));
-                bits_new |= ((use_smoothed ? sm : eb[j]) >= e_min ? 1u : 0u) << j;
-                packed[j >> 2] |= vad_machine_step(m, (bits_cur >> j) & 1u, tm1, t0, minsp) << (8 * (j & 3));
+                for (int c = 0; c < 4; ++c) {
+                    sm = __fadd_rn(__fmul_rn(alpha, ev[c]), __fmul_rn(beta, sm));
+                    bits |= ((use_smoothed ? sm : ev[c]) >= e_min ? 1u : 0u) << (4 * j + c);
+                }
             }
-            store16((b - 1) * 16, packed);
-            bits_cur = bits_new;
-        }
-        // epilogue: state machine of the last block
-        {
-            uint32_t packed[4] = {0, 0, 0, 0};
+            vad_machine_word(m, bits, 32u, w * 32u, out, timeout, minsp);
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                packed[j >> 2] |= vad_machine_step(m, (bits_cur >> j) & 1u, tm1, t0, minsp) << (8 * (j & 3));
-            store16((n_blocks - 1) * 16, packed);
+            for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
         }
-        f = n_blocks * 16;
+        f = n_words * 32;
     }
-    for (; f < T; ++f) {
-        const float ev = e[f];
-        sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
-        const float det = use_smoothed ? sm : ev;
-        const uint32_t stv = vad_machine_step(m, det >= e_min ? 1u : 0u, tm1, t0, minsp);
-        if (out) out[f] = (uint8_t)stv;
+    while (f < T) {                                       // tail (and unaligned rows): up to 32 frames at a time
+        const uint32_t n = min(32u, T - f);
+        uint32_t bits = 0;
+        for (uint32_t j = 0; j < n; ++j) {
+            const float ev = e[f + j];
+            sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
+            bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
+        }
+        vad_machine_word(m, bits, n, f, out, timeout, minsp);
+        f += n;
     }
     v.smoothed = sm; v.state = (int)m.st; v.silence_frames = m.sil; v.speech_frames = m.spk;
     if (J.state_io) J.state_io[s] = v;
