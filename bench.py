@@ -181,6 +181,139 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------
+# the other BASELINE.json configs (reported beside the contract line, never instead of it)
+# ---------------------------------------------------------------------------------------------
+def run_other_workload(args, af, synth, torch, dist, dev, rank, world, local_rank):
+    from audioflow import shard
+    peak, peak_src = measured_peak_gbs()
+    stream = torch.cuda.current_stream()
+
+    def time_steps(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    if args.workload == "cfg3":
+        # 4096 x 30 s mixed 44.1/48 kHz mono f32, full pipeline (PCM + 80 mel + VAD), stream-sharded, strong scaling
+        S_total = 4096
+        rates = [44100 if i % 2 else 48000 for i in range(S_total)]
+        costs = [int(SECONDS * r) * 4 for r in rates]
+        lo, hi = shard.partition(costs, world)[rank]
+        mine = list(range(lo, hi))
+        x48 = synth.torch_batch(sum(1 for i in mine if rates[i] == 48000), SECONDS, 48000, 1, dev, seed=2 * rank)
+        x44 = synth.torch_batch(sum(1 for i in mine if rates[i] == 44100), SECONDS, 44100, 1, dev, seed=2 * rank + 1)
+        descs, i48, i44 = [], 0, 0
+        for i in mine:
+            if rates[i] == 48000:
+                descs.append((x48[i48].data_ptr(), x48.shape[1], 48000, 1, af.AF_FMT_F32)); i48 += 1
+            else:
+                descs.append((x44[i44].data_ptr(), x44.shape[1], 44100, 1, af.AF_FMT_F32)); i44 += 1
+        pipe = af.Pipeline(af.pipeline_config(n_mels=N_MELS, vad_enable=True))
+        b = pipe.batch(descs, af.AF_MEM_DEVICE)
+        S = len(mine)
+        pcm = torch.empty((S, b.pcm_stride), device=dev)
+        lm = torch.empty((S, b.logmel_stride), device=dev)
+        vad = torch.zeros((S, b.vad_stride), device=dev, dtype=torch.uint8)
+        o = b.outputs_struct(pcm.data_ptr(), b.pcm_stride, lm.data_ptr(), b.logmel_stride, vad.data_ptr(), b.vad_stride, 0, 0, 0)
+        nfr = torch.tensor(b.n_vad[:S].astype(np.int32), device=dev)
+
+        def step_nogather():
+            b.run_device(o, stream.cuda_stream)
+
+        def step_gather():
+            b.run_device(o, stream.cuda_stream)
+            if world > 1:
+                shard.gather_vad(vad, nfr)           # VAD states + frame counts of every stream to every rank (NCCL)
+
+        ms0 = time_steps(step_nogather, args.steps, args.warmup)
+        ms1 = time_steps(step_gather, args.steps, args.warmup)
+        audio_s = S_total * SECONDS
+        alg = sum((r * 4 + 16000 * 4 + 100 * N_MELS * 4 + 100) * SECONDS for r in rates)
+        if rank == 0:
+            print(json.dumps({"workload": "cfg3: 4096 x 30 s mixed 44.1/48 kHz mono f32 -> PCM + 80-mel + VAD, stream-sharded",
+                              "metric": "audio_seconds_per_second", "unit": "audio-s/s", "n_gpus": world, "scaling": "strong",
+                              "value": audio_s / (ms1 * 1e-3), "ms_per_step": ms1,
+                              "value_without_gather": audio_s / (ms0 * 1e-3), "ms_per_step_without_gather": ms0,
+                              "gather": "VAD states u8 + frame counts, all_gather_into_tensor (NCCL)" if world > 1 else "none (1 GPU)",
+                              "hbm_gbs_per_gpu": alg / world / (ms0 * 1e-3) / 1e9, "hbm_frac_per_gpu": alg / world / (ms0 * 1e-3) / 1e9 / peak,
+                              "steps": args.steps, "warmup": args.warmup, "data": "synthetic"}), flush=True)
+    elif args.workload == "cfg4":
+        # one 1-hour 48 kHz stereo recording -> PCM + 128-mel + VAD + segmentation (does not shard: replicas only)
+        sec = 3600.0
+        x = synth.torch_batch(1, sec, 48000, 2, dev, seed=rank)
+        pipe = af.Pipeline(af.pipeline_config(n_mels=128, vad_enable=True))
+        b = pipe.batch([(x[0].data_ptr(), x.shape[1], 48000, 2, af.AF_FMT_F32)], af.AF_MEM_DEVICE)
+        pcm = torch.empty((1, b.pcm_stride), device=dev)
+        lm = torch.empty((1, b.logmel_stride), device=dev)
+        vad = torch.zeros((1, b.vad_stride), device=dev, dtype=torch.uint8)
+        seg = torch.zeros((1, 65536, 2), device=dev, dtype=torch.int32)
+        nseg = torch.zeros(1, device=dev, dtype=torch.int32)
+        nfr = torch.tensor(b.n_vad[:1].astype(np.int32), device=dev)
+        o = b.outputs_struct(pcm.data_ptr(), b.pcm_stride, lm.data_ptr(), b.logmel_stride, vad.data_ptr(), b.vad_stride, 0, 0, 0)
+        L = af.load_library()
+
+        def step():
+            b.run_device(o, stream.cuda_stream)
+            L.af_vad_segments(vad.data_ptr(), b.vad_stride, nfr.data_ptr(), 1, seg.data_ptr(), 65536, nseg.data_ptr(), stream.cuda_stream)
+
+        ms = time_steps(step, args.steps, args.warmup)
+        alg = (48000 * 2 * 4 + 16000 * 4 + 100 * 128 * 4 + 100) * sec
+        if rank == 0:
+            print(json.dumps({"workload": "cfg4: 1 x 3600 s 48 kHz stereo f32 -> PCM + 128-mel + VAD + segmentation (replicas only)",
+                              "metric": "audio_seconds_per_second", "unit": "audio-s/s", "n_gpus": world,
+                              "value": world * sec / (ms * 1e-3), "ms_per_step": ms, "segments": int(nseg[0]),
+                              "hbm_gbs_per_gpu": alg / (ms * 1e-3) / 1e9, "hbm_frac_per_gpu": alg / (ms * 1e-3) / 1e9 / peak,
+                              "steps": args.steps, "warmup": args.warmup, "data": "synthetic"}), flush=True)
+    else:
+        # cfg5: 1024 concurrent 20 ms-chunk 48 kHz mono streams, persistent state, latency bound
+        S, tick = 1024, 960
+        n_ticks = max(args.steps, 500)
+        pipe = af.Pipeline(af.pipeline_config(n_mels=N_MELS, vad_enable=True))
+        L = af.load_library()
+        h = C.c_void_p()
+        af._check(L.af_session_create(pipe._h, S, 48000, 1, af.AF_FMT_F32, tick, C.byref(h)))
+        x = synth.torch_batch(S, 2.0, 48000, 1, dev, seed=rank)
+        pcm = torch.empty((S, 512), device=dev)
+        lm = torch.empty((S, 8 * N_MELS), device=dev)
+        vad = torch.zeros((S, 16), device=dev, dtype=torch.uint8)
+        o = af.OutputsC(pcm.data_ptr(), 512, lm.data_ptr(), 8 * N_MELS, vad.data_ptr(), 16, None, 0, None)
+        lat = []
+        for t in range(n_ticks + 20):
+            off = (t % 100) * tick
+            t0 = time.perf_counter()
+            af._check(L.af_session_push(h, x.data_ptr() + off * 4, x.shape[1], tick, af.AF_MEM_DEVICE, C.byref(o), None, None, None))
+            if t >= 20:
+                lat.append(time.perf_counter() - t0)
+        L.af_session_destroy(h)
+        lat = np.array(lat) * 1e3
+        if rank == 0:
+            print(json.dumps({"workload": "cfg5: 1024 x 20 ms ticks (960 samples @ 48 kHz mono f32), persistent state, PCM + 80-mel + VAD per tick",
+                              "metric": "tick_latency_ms", "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
+                              "mean_ms": float(lat.mean()), "ticks": int(len(lat)), "n_gpus": world,
+                              "realtime_factor": 20.0 / float(np.percentile(lat, 99)),
+                              "max_realtime_streams_per_gpu": int(S * 20.0 / float(np.percentile(lat, 99))),
+                              "audio_seconds_per_second": world * S * 0.02 / (float(lat.mean()) * 1e-3), "data": "synthetic"}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def main():
@@ -192,6 +325,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="auto")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="cfg2 is the contract line; cfg3/4/5 are the other BASELINE.json configs (extra reports)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -214,6 +349,8 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     af.init(local_rank)
     af.set_kernel_variant(args.variant)
+    if args.workload != "cfg2":
+        return run_other_workload(args, af, synth, torch, dist, dev, rank, world, local_rank)
 
     S, n = STREAMS_PER_GPU, int(SECONDS * RATE)
     x = synth.torch_batch(S, SECONDS, RATE, 1, dev, seed=rank)             # resident in HBM before timing
