@@ -94,10 +94,10 @@ __device__ __forceinline__ void issue_fill(FusedSmem &sm, const FusedParams &P, 
     unsigned long long lo = 0, hi = 0;
     uint32_t bytes = 0, interior = 0;
     const char *src = reinterpret_cast<const char *>(sp->data);
-    if (P.use_stage && sp->staged) {
-        const unsigned long long n_first = (unsigned long long)td.tile * TILE_SAMPLES + (unsigned long long)g * STEP_SAMPLES +
-                                           (g == 0 ? 0 : CARRY);
-        unsigned long long n_last = (unsigned long long)td.tile * TILE_SAMPLES + (unsigned long long)g * STEP_SAMPLES + YLEN;
+    {
+        const unsigned long long step0 = (unsigned long long)td.tile * TILE_SAMPLES + (unsigned long long)g * STEP_SAMPLES;
+        const unsigned long long n_first = step0 + (g == 0 ? 0 : CARRY);
+        unsigned long long n_last = step0 + YLEN;
         if (n_last > n_out) n_last = n_out;
         if (n_first < n_last) {
             long long k0, k1;
@@ -107,10 +107,14 @@ __device__ __forceinline__ void issue_fill(FusedSmem &sm, const FusedParams &P, 
                 resample_pos(n_first, p, q, &k0, &r);
                 resample_pos(n_last - 1, p, q, &k1, &r);
             }
-            long long i_lo = k0 - 2, i_hi = k1 + 3;              // taps k-1..k+2, and k-1 when the recurrence sits below an integer
+            // interior step: no tap (k-2 .. k+2) leaves the stream, no output beyond n_out, whole channel frames
+            const bool geom = (k0 - 2 >= 0) && (k1 + 3 <= (long long)n_in) && ((unsigned long long)(k1 + 3) * ch <= n_samples) &&
+                              (n_last == step0 + YLEN) && ch <= 2;
+            if (geom) interior = 2;                              // unchecked taps straight from global memory
+            long long i_lo = k0 - 2, i_hi = k1 + 3;
             if (i_lo < 0) i_lo = 0;
             if (i_hi > (long long)n_in) i_hi = (long long)n_in;
-            if (i_lo < i_hi) {
+            if (P.use_stage && sp->staged && i_lo < i_hi) {
                 unsigned long long b_lo = ((unsigned long long)i_lo * ch * bps) & ~15ull;
                 unsigned long long e_hi = (unsigned long long)i_hi * ch;
                 if (e_hi > n_samples) e_hi = n_samples;
@@ -121,10 +125,7 @@ __device__ __forceinline__ void issue_fill(FusedSmem &sm, const FusedParams &P, 
                     bytes = (uint32_t)(b_hi - b_lo);
                     lo = b_lo / bps; hi = b_hi / bps;
                     src += b_lo;
-                    // interior step: no tap leaves the stream or the stage, no output beyond n_out
-                    interior = (k0 - 2 >= 0) && (k1 + 3 <= (long long)n_in) &&
-                               ((unsigned long long)(k1 + 3) * ch <= hi) && ((unsigned long long)(k1 + 3) * ch <= n_samples) &&
-                               (n_last == (unsigned long long)td.tile * TILE_SAMPLES + (unsigned long long)g * STEP_SAMPLES + YLEN);
+                    if (geom && (unsigned long long)(k1 + 3) * ch <= hi) interior = 1;   // ... and from the stage
                 }
             }
         }
@@ -191,24 +192,26 @@ __device__ __forceinline__ float tap_fast(const unsigned char *stage, int off)
 }
 
 // ---- phase 1, interior steps: every tap comes unchecked from the stage ----
-template <int KIND>
+template <int KIND, bool STAGED>
 __device__ __forceinline__ void resample_step_fast(FusedSmem &sm, const StreamDev &s, uint32_t tile_off, uint32_t base,
                                                    int i_begin)
 {
+    // taps come from the shared-memory stage (first staged mono frame f_lo) or, when the step does not fit the
+    // stage (e.g. stereo f32), unchecked from the stream in global memory (f_lo = 0)
+    const unsigned char *__restrict__ srcp = STAGED ? sm.stage : reinterpret_cast<const unsigned char *>(s.data);
+    const int f_lo = STAGED ? (int)((uint32_t)sm.st_lo / ((KIND == K_F32_2 || KIND == K_I16_2) ? 2u : 1u)) : 0;
     const int tid = threadIdx.x;
     const uint32_t mode = s.mode;
-    const int ch = (KIND == K_F32_2 || KIND == K_I16_2) ? 2 : 1;
-    const int f_lo = (int)((uint32_t)sm.st_lo / ch);                 // first staged mono frame
     int i = i_begin + tid;
     if (mode == RS_PASSTHROUGH) {
-        for (; i < YLEN; i += FUSED_THREADS) sm.ybuf[ypad(i)] = tap_fast<KIND>(sm.stage, (int)(base + i) - f_lo);
+        for (; i < YLEN; i += FUSED_THREADS) sm.ybuf[ypad(i)] = tap_fast<KIND>(srcp, (int)(base + i) - f_lo);
         return;
     }
     const uint32_t q = s.q;
     if (KIND == K_F32_1 && q == 1 && s.p == 3) {
         // 48 kHz -> 16 kHz mono f32, four outputs per thread: output n reads x[3n-2 .. 3n+1]; for n = 0 mod 4 that
         // is an 8-byte aligned float2 followed by three 16-byte aligned float4 of the stage (14 floats, 13 used)
-        const float *stg = reinterpret_cast<const float *>(sm.stage);
+        const float *stg = reinterpret_cast<const float *>(srcp);
         const int kbase = sm.tile_k + 3 * (int)tile_off - 1 - f_lo;
         // start on a 32-sample boundary of the padded step buffer so that every quarter-warp stores 128 contiguous bytes
         for (int i4 = (i_begin & ~31) + 4 * tid; i4 < YLEN; i4 += 4 * FUSED_THREADS) {
@@ -242,8 +245,8 @@ __device__ __forceinline__ void resample_step_fast(FusedSmem &sm, const StreamDe
         int o = sm.tile_k + (int)a - 1 - f_lo;
         const int inc = (int)sm.inc_k;
         for (; i < YLEN; i += FUSED_THREADS, o += inc) {
-            const float y0 = tap_fast<KIND>(sm.stage, o), y1 = tap_fast<KIND>(sm.stage, o + 1);
-            const float y2 = tap_fast<KIND>(sm.stage, o + 2), y3 = tap_fast<KIND>(sm.stage, o + 3);
+            const float y0 = tap_fast<KIND>(srcp, o), y1 = tap_fast<KIND>(srcp, o + 1);
+            const float y2 = tap_fast<KIND>(srcp, o + 2), y3 = tap_fast<KIND>(srcp, o + 3);
             const float big = (fabsf(y0) + fabsf(y1)) + (fabsf(y2) + fabsf(y3));   // NaN / Inf propagate
             float v = y1;
             if (!(y1 != 0.0f && big < 1e30f)) v = interp_cubic(0.0f, y0, y1, y2, y3);
@@ -265,8 +268,8 @@ __device__ __forceinline__ void resample_step_fast(FusedSmem &sm, const StreamDe
         } else {
             frac = (float)rem * inv_q;                                // q is a power of two: exact
         }
-        const float y0 = tap_fast<KIND>(sm.stage, o), y1 = tap_fast<KIND>(sm.stage, o + 1);
-        const float y2 = tap_fast<KIND>(sm.stage, o + 2), y3 = tap_fast<KIND>(sm.stage, o + 3);
+        const float y0 = tap_fast<KIND>(srcp, o), y1 = tap_fast<KIND>(srcp, o + 1);
+        const float y2 = tap_fast<KIND>(srcp, o + 2), y3 = tap_fast<KIND>(srcp, o + 3);
         sm.ybuf[ypad(i)] = interp_cubic(frac, y0, y1, y2, y3);
         k += (int)inc_k;
         rem += inc_rem;
@@ -276,7 +279,7 @@ __device__ __forceinline__ void resample_step_fast(FusedSmem &sm, const StreamDe
 
 // ---- phase 1: resample the 16 kHz samples [base + i_begin, base + YLEN) of the stream into ybuf ----
 template <int KIND>
-__device__ __forceinline__ void resample_step(FusedSmem &sm, const StreamDev &s, uint32_t tile_off, uint32_t base,
+__device__ __noinline__ void resample_step(FusedSmem &sm, const StreamDev &s, uint32_t tile_off, uint32_t base,
                                               int i_begin)
 {
     const int tid = threadIdx.x;
@@ -493,12 +496,21 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedP
             fill_parity ^= 1u;
             const int i_begin = g == 0 ? 0 : CARRY;
             const uint32_t toff = g * STEP_SAMPLES;
-            if (sm.st_interior) {
-                switch (kind) {
-                case K_F32_1: resample_step_fast<K_F32_1>(sm, s, toff, base, i_begin); break;
-                case K_I16_1: resample_step_fast<K_I16_1>(sm, s, toff, base, i_begin); break;
-                case K_F32_2: resample_step_fast<K_F32_2>(sm, s, toff, base, i_begin); break;
-                default: resample_step_fast<K_I16_2>(sm, s, toff, base, i_begin); break;
+            if (sm.st_interior && kind != K_GENERIC) {
+                if (sm.st_interior == 1) {
+                    switch (kind) {
+                    case K_F32_1: resample_step_fast<K_F32_1, true>(sm, s, toff, base, i_begin); break;
+                    case K_I16_1: resample_step_fast<K_I16_1, true>(sm, s, toff, base, i_begin); break;
+                    case K_F32_2: resample_step_fast<K_F32_2, true>(sm, s, toff, base, i_begin); break;
+                    default: resample_step_fast<K_I16_2, true>(sm, s, toff, base, i_begin); break;
+                    }
+                } else {
+                    switch (kind) {
+                    case K_F32_1: resample_step_fast<K_F32_1, false>(sm, s, toff, base, i_begin); break;
+                    case K_I16_1: resample_step_fast<K_I16_1, false>(sm, s, toff, base, i_begin); break;
+                    case K_F32_2: resample_step_fast<K_F32_2, false>(sm, s, toff, base, i_begin); break;
+                    default: resample_step_fast<K_I16_2, false>(sm, s, toff, base, i_begin); break;
+                    }
                 }
             } else {
                 switch (kind) {

@@ -356,38 +356,60 @@ cudaError_t launch_pcm16(const float *in, uint64_t n, int16_t *out, cudaStream_t
 }
 
 // ---- VAD segmentation: runs from the first Speech frame to Ending (inclusive) / Silence (exclusive) ----
+// One CTA per stream.  A segment starts at every frame with state Speech whose predecessor is not Speech, and
+// ends at the first later frame that is not Speech; starts and ends alternate, so the k-th start pairs with
+// the k-th end.  Each thread owns a contiguous span of frames: count, block-wide exclusive scan, write.
 __global__ void af_vad_segments_kernel(const uint8_t *__restrict__ states, uint64_t stride,
                                        const uint32_t *__restrict__ n_frames, uint32_t n_streams,
                                        uint32_t *__restrict__ seg, uint32_t seg_cap, uint32_t *__restrict__ n_seg)
 {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t s_starts[1024], s_ends[1024];
+    const uint32_t s = blockIdx.x;
     if (s >= n_streams) return;
     const uint8_t *st = states + (uint64_t)s * stride;
     uint32_t *sg = seg + (uint64_t)s * seg_cap * 2;
     const uint32_t T = n_frames[s];
-    uint32_t ns = 0, start = 0;
-    bool in_seg = false;
-    for (uint32_t f = 0; f < T; ++f) {
+    const uint32_t nt = blockDim.x, t = threadIdx.x;
+    const uint32_t span = (T + nt - 1) / nt;
+    const uint32_t lo = min(t * span, T), hi = min(lo + span, T);
+    uint32_t ns = 0, ne = 0;
+    uint8_t prev = lo > 0 ? st[lo - 1] : (uint8_t)0;
+    for (uint32_t f = lo; f < hi; ++f) {
         const uint8_t v = st[f];
-        if (!in_seg) {
-            if (v == 1) { in_seg = true; start = f; }
-        } else if (v != 1) {
-            if (ns < seg_cap) { sg[2 * ns] = start; sg[2 * ns + 1] = v == 2 ? f + 1 : f; }
-            ns++; in_seg = false;
-        }
+        ns += (v == 1 && prev != 1);
+        ne += (v != 1 && prev == 1);
+        prev = v;
     }
-    if (in_seg) {
-        if (ns < seg_cap) { sg[2 * ns] = start; sg[2 * ns + 1] = T; }
-        ns++;
+    s_starts[t] = ns; s_ends[t] = ne;
+    __syncthreads();
+    // exclusive scan (Hillis-Steele on both arrays)
+    for (uint32_t d = 1; d < nt; d <<= 1) {
+        uint32_t a = 0, b = 0;
+        if (t >= d) { a = s_starts[t - d]; b = s_ends[t - d]; }
+        __syncthreads();
+        s_starts[t] += a; s_ends[t] += b;
+        __syncthreads();
     }
-    n_seg[s] = ns;
+    uint32_t ks = s_starts[t] - ns, ke = s_ends[t] - ne;      // index of this span's first start / end
+    const uint32_t total = s_starts[nt - 1], total_ends = s_ends[nt - 1];
+    prev = lo > 0 ? st[lo - 1] : (uint8_t)0;
+    for (uint32_t f = lo; f < hi; ++f) {
+        const uint8_t v = st[f];
+        if (v == 1 && prev != 1) { if (ks < seg_cap) sg[2 * ks] = f; ks++; }
+        if (v != 1 && prev == 1) { if (ke < seg_cap) sg[2 * ke + 1] = v == 2 ? f + 1 : f; ke++; }
+        prev = v;
+    }
+    if (t == 0) {
+        if (total > total_ends && total - 1 < seg_cap) sg[2 * (total - 1) + 1] = T;    // still speaking at the end
+        n_seg[s] = total;
+    }
 }
 
 cudaError_t launch_vad_segments(const uint8_t *states, uint64_t stride, const uint32_t *n_frames, uint32_t n_streams,
                                 uint32_t *seg, uint32_t seg_cap, uint32_t *n_seg, cudaStream_t st)
 {
     if (n_streams == 0) return cudaSuccess;
-    af_vad_segments_kernel<<<(n_streams + 31) / 32, 32, 0, st>>>(states, stride, n_frames, n_streams, seg, seg_cap, n_seg);
+    af_vad_segments_kernel<<<n_streams, 256, 0, st>>>(states, stride, n_frames, n_streams, seg, seg_cap, n_seg);
     return cudaGetLastError();
 }
 
