@@ -17,7 +17,8 @@ from enum import IntEnum
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libaudioflow_gpu.so")
+# AF_GPU_LIB selects another build of the same library (e.g. the `make STATS=1` debugging build)
+LIB_PATH = os.environ.get("AF_GPU_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libaudioflow_gpu.so")
 
 AF_OK, AF_ERR_INVALID, AF_ERR_RESAMPLING_FAILED, AF_ERR_CUDA, AF_ERR_NO_DEVICE, AF_ERR_CAPACITY = range(6)
 AF_FMT_F32, AF_FMT_I16 = 0, 1
@@ -82,6 +83,7 @@ def load_library():
         "af_init": (C.c_int, [C.c_int]), "af_shutdown": (C.c_int, []),
         "af_last_error": (sz, [C.c_char_p, sz]), "af_device_count": (C.c_int, [C.POINTER(C.c_int)]),
         "af_version": (C.c_char_p, []), "af_kernel_launch_count": (C.c_uint64, []),
+        "af_debug_pipe_stats": (C.c_int, [C.POINTER(C.c_uint64)]),
         "af_host_alloc": (C.c_int, [C.POINTER(vp), sz]), "af_host_free": (C.c_int, [vp]),
         "af_to_mono": (C.c_int, [fp, sz, C.c_uint16, fp, sz, szp]),
         "af_resampler_create": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(vp)]),

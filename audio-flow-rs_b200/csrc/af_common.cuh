@@ -1,5 +1,6 @@
 // af_common.cuh -- constants and device-visible tables shared by the kernels and the host runtime.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -17,18 +18,23 @@ constexpr int MAX_MELS = 128;
 constexpr int RS_CHUNK = 128;     // chunk_size
 constexpr int RS_POLY = 8;        // rubato POLYNOMIAL_LEN
 
-// ---- fused kernel tiling ----
-constexpr int SF = 16;                       // frames per step: one per half-warp of the 8 FFT warps
-constexpr int STEP_SAMPLES = SF * HOP;       // 2560 new 16 kHz samples per step
+// ---- fused kernel tiling (one persistent CTA per SM, warp-specialised pipeline) ----
+constexpr int SF = 32;                       // frames per step: one per half-warp of the 16 FFT warps
+constexpr int STEP_SAMPLES = SF * HOP;       // 5120 new 16 kHz samples per step
 constexpr int CARRY = WIN - HOP;             // 240 samples shared with the next step
-constexpr int YLEN = STEP_SAMPLES + CARRY;   // 2800 samples live per step
+constexpr int YLEN = STEP_SAMPLES + CARRY;   // 5360 samples live per step
+constexpr int HALF_SPLIT = 2688;             // a step's raw input is staged in two fills: outputs [.., 2688) and [2688, YLEN)
 constexpr int TILE_FRAMES = 128;             // frames per tile (work unit of one CTA)
 constexpr int TILE_SAMPLES = TILE_FRAMES * HOP;   // 20480
-constexpr int FFT_WARPS = 8;
-constexpr int VAD_WARP = FFT_WARPS;          // warp 8: stage fills (TMA) + sequential frame energies
-constexpr int AUX_WARP = FFT_WARPS + 1;      // warp 9: PCM write-out + overlap carry
-constexpr int FUSED_WARPS = FFT_WARPS + 2;
-constexpr int FUSED_THREADS = FUSED_WARPS * 32;   // 320: 640 resample quads, 640 PCM float4, 320 mel items per step
+constexpr int FFT_WARPS = 16;                // warps 0..15: window + FFT + power, one frame per half-warp
+constexpr int MEL_WARPS = 4;                 // warps 16..19: mel projection + log, lane = frame
+constexpr int MEL_WARP0 = FFT_WARPS;
+constexpr int VAD_WARP = MEL_WARP0 + MEL_WARPS;   // warp 20: stage fills (TMA bulk copies) + sequential frame energies
+constexpr int RS_WARP0 = VAD_WARP + 1;       // warps 21..27: downmix + resample + PCM write-out
+constexpr int RS_WARPS = 7;
+constexpr int RS_THREADS = RS_WARPS * 32;
+constexpr int FUSED_WARPS = RS_WARP0 + RS_WARPS;  // 28
+constexpr int FUSED_THREADS = FUSED_WARPS * 32;   // 896
 
 // padded index of 16 kHz sample i inside the step buffer: 4 pad words after every 32 samples so
 // that the 32 VAD lanes (frame starts 160 apart) hit distinct bank quads with LDS.128
@@ -37,9 +43,10 @@ constexpr int YBUF_FLOATS = ((ypad(YLEN + 32) + 31) / 32) * 32;
 
 constexpr int SCR_ROW = 18;                  // complex per transposed row (16 + 2 pad -> LDS.128 conflict free)
 constexpr int SCR_FLOATS_PER_FRAME = 16 * SCR_ROW * 2;   // 576 floats = 2304 B
-constexpr int PB_ROW = SF + 4;               // floats per power row: 16 frames + 4 pad (16-byte aligned rows)
-constexpr int PBUF_FLOATS = NBIN * PB_ROW;
-constexpr int STAGE_BYTES = 34816;           // TMA-staged raw input of one step (34 KB)
+constexpr int PB_ROW = SF + 1;               // floats per power row: 32 frames + 1 pad (conflict-free column stores)
+constexpr int PB_ROWS = NBIN + 3;            // 3 zero rows behind bin 256 for the 4-padded mel weights
+constexpr int PBUF_FLOATS = PB_ROWS * PB_ROW;
+constexpr int STAGE_BYTES = 32384;           // one TMA-staged half step of raw input (2688 outputs x 3 x 4 B + halo), two of them
 
 // formats / flags (mirror include/audioflow_gpu.h)
 enum : uint16_t { FMT_F32 = 0, FMT_I16 = 1 };
@@ -69,15 +76,27 @@ struct TileDev {
     uint32_t tile;           // tile index inside the stream
 };
 
-// mel filterbank in compact form (weights already carry the 1/4 of the unscaled power)
+// mel filterbank in compact form (weights already carry the 1/4 of the unscaled power).  The mel warps work
+// lane = frame and walk FOUR adjacent filters (a "quad": one 16-byte store per frame) at a time, eight
+// independent FMA chains: the quad's weights are zero padded to a common number of quadruples and interleaved
+// [a0..a3][b0..b3][c0..c3][d0..d3] per step so that four warp-uniform LDS.128 feed sixteen FMAs.  The quads are
+// split over the MEL_WARPS warps by weight count.
+struct MelQuad {
+    uint16_t lo[4];          // first bin read for each of the four filters (padded reads stay below PB_ROWS)
+    uint16_t c4;             // number of weight quadruples per filter
+    uint16_t off16;          // offset of the quad's weights in w, in units of 16 floats
+    uint16_t pad_[2];
+};
 struct MelTables {
-    uint16_t lo[MAX_MELS];   // first nonzero bin
-    uint16_t cnt[MAX_MELS];  // number of nonzero bins
-    uint16_t off[MAX_MELS];  // offset into w
+    MelQuad quad[MAX_MELS / 4];
     uint16_t n_w;
     uint16_t n_mels;
-    float w[2 * NBIN + 2 * MAX_MELS];
+    uint16_t quad_begin[MEL_WARPS + 1];   // mel warp j owns filter quads [quad_begin[j], quad_begin[j + 1])
+    uint16_t pad_[1];
+    float w[1280];
 };
+static_assert(sizeof(MelQuad) == 16, "MelQuad is read with one LDS.128");
+static_assert(offsetof(MelTables, w) % 16 == 0, "mel weights must be 16-byte aligned");
 
 // constant tables of the FFT, filled by the host in f64 and rounded once
 struct FftTables {

@@ -1,11 +1,17 @@
-// af_fused.cu -- the fused hot-path kernel for sm_100a:
-//   K1 downmix + cubic (rubato FastFixedIn) resample  -> 16 kHz step buffer in shared memory; the raw
-//      input of the NEXT step is staged into shared memory by a TMA bulk copy (cp.async.bulk +
-//      mbarrier) while the current step is in its FFT phase
-//   K2 Hann window + 512-point real FFT (packed 256-point complex, 16x16 in registers,
-//      one half-warp per frame, transposed through shared memory, Hermitian split by shuffles)
-//   K3 sparse banded mel projection + log
-//   K4 (energy part) bit-exact sequential mean-square per frame on a dedicated VAD warp
+// af_fused.cu -- the fused hot-path kernel for sm_100a: one persistent CTA per SM, 28 warps in four
+// roles that run concurrently on different steps (32 frames) of the CTA's tiles and hand buffers to
+// each other through mbarriers -- there is no CTA-wide barrier after start-up:
+//
+//   warp 20      "V"  issues the TMA bulk copies (cp.async.bulk + mbarrier complete_tx) that stage the raw
+//                     interleaved input of each half step in shared memory, two fills ahead; then K4's
+//                     energy part: one bit-exact 400-term sequential mean-square chain per lane (= frame)
+//   warps 21-27  "R"  K1: downmix + cubic (rubato FastFixedIn) resample from the stage into the padded
+//                     16 kHz step buffer (double buffered), PCM written to HBM straight from registers
+//   warps 0-15   "F"  K2: Hann window + 512-point real FFT (packed 256-point complex, 16 x 16 in registers,
+//                     one half-warp per frame, transposed through shared memory, Hermitian split by
+//                     shuffles), power into pbuf[bin][frame]
+//   warps 16-19  "M"  K3: sparse banded mel projection + log, lane = frame, warp-uniform weight quads
+//
 // Replaces capture.rs:30-42, resampler.rs:71-93/132-166 (+ rubato) and the O(len) part of
 // vad.rs:157-168; the STFT/mel stages are spec-defined.  The sequential EMA/state
 // machine of vad.rs:101-153 runs in af_vad_scan_kernel (af_kernels.cu).
@@ -15,27 +21,35 @@
 namespace af {
 
 struct __align__(128) FusedSmem {
-    unsigned char stage[STAGE_BYTES];                // raw interleaved input of one step (bulk-copy target)
-    float ybuf[YBUF_FLOATS];                         // padded 16 kHz samples of the current step
-    float scr[16 * SCR_FLOATS_PER_FRAME];            // per half-warp transpose scratch / log-mel stage
+    unsigned char stage[2][STAGE_BYTES];             // raw interleaved input of the two halves of a step (bulk-copy targets)
+    float ybuf[2][YBUF_FLOATS];                      // padded 16 kHz samples of two consecutive steps
+    float scr[SF * SCR_FLOATS_PER_FRAME];            // per half-warp transpose scratch
     float pbuf[PBUF_FLOATS];                         // 4*|X[k]|^2, [bin][frame]
-    FftTables fft;
+    float2 tw1[16 * 16];                             // exp(-2 pi i l k1 / 256)
+    float2 tw2[128];                                 // exp(-2 pi i k / 512)
+    float window[416];                               // periodic Hann, zero beyond 400
     MelTables mel;
-    StreamDev stream;                                // descriptor of the tile's stream
-    unsigned long long mbar;                         // completion barrier of the in-flight stage fill
-    unsigned long long st_lo, st_hi;                 // interleaved element range [lo, hi) held by the stage
-    uint32_t st_interior;                            // 1: every tap of the step is inside the stage and the stream
+    // pipeline barriers (mbarriers): full = data ready for the consumer, empty = buffer may be overwritten
+    unsigned long long stage_full[2], stage_empty[2];
+    unsigned long long y_full[2], y_empty[2];
+    unsigned long long p_full, p_empty;
+    // metadata of the fill held by stage[h], written by the issuing thread before its arrive
+    unsigned long long st_lo[2], st_hi[2];           // interleaved element range [lo, hi) held by the stage
+    uint32_t st_interior[2];                         // 1: every tap of the half step is inside the stage and the stream;
+                                                     // 2: inside the stream but not staged (unchecked global loads)
+    // resampler role: descriptor of the tile's stream and the exact position of the tile's first output
+    StreamDev stream;
     int tile_k;                                      // floor(position) of the tile's first output
     uint32_t tile_rem;                               // and its remainder (numerator units)
-    uint32_t inc_k, inc_rem;                         // position increment for FUSED_THREADS outputs
+    uint32_t inc_k, inc_rem;                         // position increment for RS_THREADS outputs
 };
+static_assert(sizeof(FusedSmem) <= 232448, "FusedSmem exceeds the 227 KB a CTA may use");
 
 // ---- mbarrier / bulk-copy wrappers (PTX; SASS: SYNCS.*, UBLKCP) ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 {
@@ -49,12 +63,16 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, u
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
 {
+    // try_wait suspends for a short hardware-defined time; back off between polls so that waiting warps do not
+    // take issue slots from the working ones
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
+        "WAIT_%=:\n\t"
+        "nanosleep.u32 40;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
@@ -66,76 +84,139 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-
-// shared-memory load the compiler cannot rematerialise at the use site: keeps per-lane constants in registers
-__device__ __forceinline__ float2 lds_f2_pinned(const void *p)
+// warp-level arrive: every lane's earlier shared-memory accesses are ordered before lane 0's arrive
+__device__ __forceinline__ void warp_arrive(unsigned long long *bar, int lane)
+{
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+// global load the compiler cannot rematerialise at the use site: keeps per-lane constants in registers
+__device__ __forceinline__ float2 ldg_f2_pinned(const void *p)
 {
     float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(smem_u32(p)));
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
     return v;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
-__device__ __forceinline__ void named_bar_arrive(int id, int count)
-{
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
+// optional pipeline statistics (make STATS=1): cycles each role spends in each of its waits, summed over warps
+#ifdef AF_PIPE_STATS
+__device__ unsigned long long g_pipe_stats[32];
+#define AF_STATS_DECL long long ws_[7] = {0, 0, 0, 0, 0, 0, 0}; const long long ws_t0_ = clock64();
+#define AF_WAIT(bar, parity, id) do { const long long t0_ = clock64(); mbar_wait(bar, parity); ws_[id] += clock64() - t0_; } while (0)
+#define AF_TIC long long tic_ = clock64();
+#define AF_TIC2 tic_ = clock64();
+#define AF_TOC(id) ws_[id] += clock64() - tic_;
+#define AF_STATS_FLUSH(role, lane) do { if ((lane) == 0) { atomicAdd(&g_pipe_stats[8 * (role)], (unsigned long long)(clock64() - ws_t0_)); \
+    for (int i_ = 0; i_ < 7; ++i_) atomicAdd(&g_pipe_stats[8 * (role) + 1 + i_], (unsigned long long)ws_[i_]); } } while (0)
+#else
+#define AF_STATS_DECL
+#define AF_TIC
+#define AF_TIC2
+#define AF_TOC(id)
+#define AF_WAIT(bar, parity, id) mbar_wait(bar, parity)
+#define AF_STATS_FLUSH(role, lane)
+#endif
 
-// ---- stage fill: issued by ONE thread for the step (tile, g); always completes one mbarrier phase ----
-__device__ __forceinline__ void issue_fill(FusedSmem &sm, const FusedParams &P, uint32_t tile, uint32_t g)
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// ---- geometry of a tile, recomputed by every role from the same tables ----
+struct TileGeo {
+    uint32_t stream, n_tile0, tile_end, f_tile0, n_steps;
+};
+__device__ __forceinline__ TileGeo tile_geo(const FusedParams &P, uint32_t tile, uint32_t *n_frames)
 {
     const TileDev td = P.tiles[tile];
     const StreamDev *sp = P.streams + td.stream;
-    const uint32_t n_out = sp->n_out, n_in = sp->n_in, mode = sp->mode, p = sp->p, q = sp->q;
-    const uint32_t ch = sp->channels, bps = sp->format == FMT_I16 ? 2u : 4u;
-    const unsigned long long n_samples = sp->n_samples;
+    const uint32_t n_out = sp->n_out;
+    if (n_frames) *n_frames = sp->n_frames;
+    TileGeo t;
+    t.stream = td.stream;
+    t.n_tile0 = td.tile * TILE_SAMPLES;
+    t.tile_end = min(t.n_tile0 + (uint32_t)TILE_SAMPLES, n_out);
+    t.f_tile0 = td.tile * TILE_FRAMES;
+    t.n_steps = (t.tile_end - t.n_tile0 + STEP_SAMPLES - 1) / STEP_SAMPLES;
+    return t;
+}
+__device__ __forceinline__ int half_lo(uint32_t g, int h) { return h == 0 ? (g == 0 ? 0 : CARRY) : HALF_SPLIT; }
+__device__ __forceinline__ int half_hi(int h) { return h == 0 ? HALF_SPLIT : YLEN; }
+
+// ---- stage fill: issued by ONE thread for the half step (tile, g, h); always completes one mbarrier phase ----
+// what the issuing thread keeps about the current tile (one 64-bit division per tile, 32-bit arithmetic per fill)
+struct FillTile {
+    const char *data;
+    unsigned long long n_samples;
+    uint32_t n_in, n_out, n_tile0;
+    uint32_t p, q, mode, ch, bps, staged;
+    long long k0;            // floor(position) of the tile's first output
+    uint32_t rem0;           // and its remainder
+};
+__device__ __forceinline__ FillTile fill_tile(const FusedParams &P, uint32_t tile)
+{
+    const TileDev td = P.tiles[tile];
+    const StreamDev *sp = P.streams + td.stream;
+    FillTile f;
+    f.data = reinterpret_cast<const char *>(sp->data);
+    f.n_samples = sp->n_samples; f.n_in = sp->n_in; f.n_out = sp->n_out;
+    f.n_tile0 = td.tile * TILE_SAMPLES;
+    f.p = sp->p; f.q = sp->q; f.mode = sp->mode; f.ch = sp->channels; f.bps = sp->format == FMT_I16 ? 2u : 4u;
+    f.staged = sp->staged;
+    f.k0 = 0; f.rem0 = 0;
+    if (f.mode != RS_PASSTHROUGH) resample_pos(f.n_tile0, f.p, f.q, &f.k0, &f.rem0);
+    return f;
+}
+// floor(position) of output n_tile0 + d (the host guarantees (TILE_SAMPLES + YLEN) * p + q < 2^32)
+__device__ __forceinline__ long long fill_pos(const FillTile &f, uint32_t d)
+{
+    if (f.mode == RS_PASSTHROUGH) return (long long)f.n_tile0 + d;
+    const uint32_t a = f.rem0 + d * f.p;
+    return f.k0 + (long long)(f.q == 1 ? a : a / f.q);
+}
+__device__ __forceinline__ void issue_fill(FusedSmem &sm, const FusedParams &P, const FillTile &f, uint32_t g, int h)
+{
+    const uint32_t ch = f.ch, bps = f.bps;
     unsigned long long lo = 0, hi = 0;
     uint32_t bytes = 0, interior = 0;
-    const char *src = reinterpret_cast<const char *>(sp->data);
+    const char *src = f.data;
     {
-        const unsigned long long step0 = (unsigned long long)td.tile * TILE_SAMPLES + (unsigned long long)g * STEP_SAMPLES;
-        const unsigned long long n_first = step0 + (g == 0 ? 0 : CARRY);
-        unsigned long long n_last = step0 + YLEN;
-        if (n_last > n_out) n_last = n_out;
-        if (n_first < n_last) {
-            long long k0, k1;
-            if (mode == RS_PASSTHROUGH) { k0 = (long long)n_first; k1 = (long long)n_last - 1; }
-            else {
-                uint32_t r;
-                resample_pos(n_first, p, q, &k0, &r);
-                resample_pos(n_last - 1, p, q, &k1, &r);
-            }
-            // interior step: no tap (k-2 .. k+2) leaves the stream, no output beyond n_out, whole channel frames
-            const bool geom = (k0 - 2 >= 0) && (k1 + 3 <= (long long)n_in) && ((unsigned long long)(k1 + 3) * ch <= n_samples) &&
-                              (n_last == step0 + YLEN) && ch <= 2;
+        const uint32_t d_first = g * STEP_SAMPLES + (uint32_t)half_lo(g, h);
+        const uint32_t d_full = g * STEP_SAMPLES + (uint32_t)half_hi(h);
+        const uint32_t left = f.n_out - f.n_tile0;                 // outputs from the tile start to the stream end
+        const uint32_t d_last = min(d_full, left);
+        if (d_first < d_last) {
+            const long long k0 = fill_pos(f, d_first), k1 = fill_pos(f, d_last - 1);
+            // interior half step: no tap (k-2 .. k+2) leaves the stream, no output beyond n_out, whole channel frames
+            const bool geom = (k0 - 2 >= 0) && (k1 + 3 <= (long long)f.n_in) &&
+                              ((unsigned long long)(k1 + 3) * ch <= f.n_samples) && (d_last == d_full) && ch <= 2;
             if (geom) interior = 2;                              // unchecked taps straight from global memory
             long long i_lo = k0 - 2, i_hi = k1 + 3;
             if (i_lo < 0) i_lo = 0;
-            if (i_hi > (long long)n_in) i_hi = (long long)n_in;
-            if (P.use_stage && sp->staged && i_lo < i_hi) {
+            if (i_hi > (long long)f.n_in) i_hi = (long long)f.n_in;
+            if (P.use_stage && f.staged && i_lo < i_hi) {
                 unsigned long long b_lo = ((unsigned long long)i_lo * ch * bps) & ~15ull;
                 unsigned long long e_hi = (unsigned long long)i_hi * ch;
-                if (e_hi > n_samples) e_hi = n_samples;
+                if (e_hi > f.n_samples) e_hi = f.n_samples;
                 unsigned long long b_hi = (e_hi * bps + 15ull) & ~15ull;
-                const unsigned long long b_end = (n_samples * bps) & ~15ull;   // never read past the stream's last full 16 bytes
+                const unsigned long long b_end = (f.n_samples * bps) & ~15ull;   // never read past the stream's last full 16 bytes
                 if (b_hi > b_end) b_hi = b_end;
                 if (b_hi > b_lo && b_hi - b_lo <= (unsigned long long)STAGE_BYTES) {
                     bytes = (uint32_t)(b_hi - b_lo);
-                    lo = b_lo / bps; hi = b_hi / bps;
+                    lo = bps == 2 ? b_lo >> 1 : b_lo >> 2; hi = bps == 2 ? b_hi >> 1 : b_hi >> 2;
                     src += b_lo;
                     if (geom && (unsigned long long)(k1 + 3) * ch <= hi) interior = 1;   // ... and from the stage
                 }
             }
         }
     }
-    sm.st_lo = lo; sm.st_hi = hi; sm.st_interior = interior;
+    sm.st_lo[h] = lo; sm.st_hi[h] = hi; sm.st_interior[h] = interior;
     if (bytes) {
-        mbar_arrive_expect_tx(&sm.mbar, bytes);
-        bulk_g2s(sm.stage, src, bytes, &sm.mbar);
+        mbar_arrive_expect_tx(&sm.stage_full[h], bytes);
+        bulk_g2s(sm.stage[h], src, bytes, &sm.stage_full[h]);
     } else {
-        mbar_arrive(&sm.mbar);
+        mbar_arrive(&sm.stage_full[h]);
     }
 }
 
@@ -143,30 +224,31 @@ __device__ __forceinline__ void issue_fill(FusedSmem &sm, const FusedParams &P, 
 enum { K_F32_1 = 0, K_I16_1 = 1, K_F32_2 = 2, K_I16_2 = 3, K_GENERIC = 4 };
 
 template <int KIND>
-__device__ __forceinline__ float tap(const FusedSmem &sm, const StreamDev &s, uint32_t st_lo, uint32_t st_hi, int idx)
+__device__ __forceinline__ float tap(const unsigned char *__restrict__ stage, const StreamDev &s, uint32_t st_lo,
+                                     uint32_t st_hi, int idx)
 {
     if ((uint32_t)idx >= s.n_in) return 0.0f;                        // also covers idx < 0
     if (KIND == K_F32_1) {
         const uint32_t e = (uint32_t)idx;
-        if (e >= st_lo && e < st_hi) return reinterpret_cast<const float *>(sm.stage)[e - st_lo];
+        if (e >= st_lo && e < st_hi) return reinterpret_cast<const float *>(stage)[e - st_lo];
         return __ldg(reinterpret_cast<const float *>(s.data) + e);
     } else if (KIND == K_I16_1) {
         const uint32_t e = (uint32_t)idx;
         short v;
-        if (e >= st_lo && e < st_hi) v = reinterpret_cast<const short *>(sm.stage)[e - st_lo];
+        if (e >= st_lo && e < st_hi) v = reinterpret_cast<const short *>(stage)[e - st_lo];
         else v = __ldg(reinterpret_cast<const short *>(s.data) + e);
         return (float)v * (1.0f / 32768.0f);
     } else if (KIND == K_F32_2) {
         const uint32_t e = 2u * (uint32_t)idx;
         if (e >= st_lo && e + 2 <= st_hi) {
-            const float2 v = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(sm.stage) + (e - st_lo));
+            const float2 v = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(stage) + (e - st_lo));
             return __fmul_rn(__fadd_rn(__fadd_rn(0.0f, v.x), v.y), 0.5f);
         }
         return load_mono(s.data, s.n_samples, s.n_in, 2, FMT_F32, idx);
     } else if (KIND == K_I16_2) {
         const uint32_t e = 2u * (uint32_t)idx;
         if (e >= st_lo && e + 2 <= st_hi) {
-            const short2 v = *reinterpret_cast<const short2 *>(reinterpret_cast<const short *>(sm.stage) + (e - st_lo));
+            const short2 v = *reinterpret_cast<const short2 *>(reinterpret_cast<const short *>(stage) + (e - st_lo));
             const float l = (float)v.x * (1.0f / 32768.0f), r = (float)v.y * (1.0f / 32768.0f);
             return __fmul_rn(__fadd_rn(__fadd_rn(0.0f, l), r), 0.5f);
         }
@@ -191,66 +273,112 @@ __device__ __forceinline__ float tap_fast(const unsigned char *stage, int off)
     return __fmul_rn(__fadd_rn(__fadd_rn(0.0f, l), r), 0.5f);
 }
 
-// ---- phase 1, interior steps: every tap comes unchecked from the stage ----
+// one resampled sample leaves its producer twice: into the step buffer and (its owner tile only) to HBM
+struct YSink {
+    float *__restrict__ yb;       // step buffer
+    float *__restrict__ pcm;      // stream's PCM row or nullptr
+    uint32_t base;                // stream index of step-buffer sample 0
+    uint32_t wr_end;              // the tile owns stream samples < wr_end
+    __device__ __forceinline__ void put(int i, float v) const
+    {
+        yb[ypad(i)] = v;
+        const uint32_t n = base + (uint32_t)i;
+        if (pcm && n < wr_end) __stcs(pcm + n, v);
+    }
+    __device__ __forceinline__ void put4(int i4, float4 y) const
+    {
+        *reinterpret_cast<float4 *>(yb + ypad(i4)) = y;
+        const uint32_t n = base + (uint32_t)i4;
+        if (pcm) {
+            if (n + 4 <= wr_end) __stcs(reinterpret_cast<float4 *>(pcm + n), y);
+            else {
+                if (n < wr_end) __stcs(pcm + n, y.x);
+                if (n + 1 < wr_end) __stcs(pcm + n + 1, y.y);
+                if (n + 2 < wr_end) __stcs(pcm + n + 2, y.z);
+            }
+        }
+    }
+};
+
+// ---- resampling, interior half steps: every tap comes unchecked from the stage (or the stream) ----
 template <int KIND, bool STAGED>
-__device__ __forceinline__ void resample_step_fast(FusedSmem &sm, const StreamDev &s, uint32_t tile_off, uint32_t base,
-                                                   int i_begin)
+__device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, int h, const StreamDev &s, const YSink &out,
+                                                   uint32_t tile_off, int i_lo, int i_hi, int rtid)
 {
-    // taps come from the shared-memory stage (first staged mono frame f_lo) or, when the step does not fit the
+    // taps come from the shared-memory stage (first staged mono frame f_lo) or, when the half step does not fit the
     // stage (e.g. stereo f32), unchecked from the stream in global memory (f_lo = 0)
-    const unsigned char *__restrict__ srcp = STAGED ? sm.stage : reinterpret_cast<const unsigned char *>(s.data);
-    const int f_lo = STAGED ? (int)((uint32_t)sm.st_lo / ((KIND == K_F32_2 || KIND == K_I16_2) ? 2u : 1u)) : 0;
-    const int tid = threadIdx.x;
+    const unsigned char *__restrict__ srcp = STAGED ? sm.stage[h] : reinterpret_cast<const unsigned char *>(s.data);
+    const int f_lo = STAGED ? (int)((uint32_t)sm.st_lo[h] / ((KIND == K_F32_2 || KIND == K_I16_2) ? 2u : 1u)) : 0;
     const uint32_t mode = s.mode;
-    int i = i_begin + tid;
+    int i = i_lo + rtid;
     if (mode == RS_PASSTHROUGH) {
-        for (; i < YLEN; i += FUSED_THREADS) sm.ybuf[ypad(i)] = tap_fast<KIND>(srcp, (int)(base + i) - f_lo);
+        for (; i < i_hi; i += RS_THREADS) out.put(i, tap_fast<KIND>(srcp, (int)(out.base + i) - f_lo));
         return;
     }
     const uint32_t q = s.q;
     if (KIND == K_F32_1 && q == 1 && s.p == 3) {
-        // 48 kHz -> 16 kHz mono f32, four outputs per thread: output n reads x[3n-2 .. 3n+1]; for n = 0 mod 4 that
-        // is an 8-byte aligned float2 followed by three 16-byte aligned float4 of the stage (14 floats, 13 used)
-        const float *stg = reinterpret_cast<const float *>(srcp);
-        const int kbase = sm.tile_k + 3 * (int)tile_off - 1 - f_lo;
-        // start on a 32-sample boundary of the padded step buffer so that every quarter-warp stores 128 contiguous bytes
-        for (int i4 = (i_begin & ~31) + 4 * tid; i4 < YLEN; i4 += 4 * FUSED_THREADS) {
-            if (i4 < i_begin) continue;
-            const float *px = stg + (kbase + 3 * i4);
-            float v[14];
-            const float2 h = *reinterpret_cast<const float2 *>(px);
-            const float4 a4 = *reinterpret_cast<const float4 *>(px + 2);
-            const float4 b4 = *reinterpret_cast<const float4 *>(px + 6);
-            const float4 c4 = *reinterpret_cast<const float4 *>(px + 10);
-            v[0] = h.x; v[1] = h.y; v[2] = a4.x; v[3] = a4.y; v[4] = a4.z; v[5] = a4.w; v[6] = b4.x; v[7] = b4.y;
-            v[8] = b4.z; v[9] = b4.w; v[10] = c4.x; v[11] = c4.y; v[12] = c4.z; v[13] = c4.w;
-            float big = 0.0f;
-#pragma unroll
-            for (int t = 0; t < 13; ++t) big += fabsf(v[t]);                      // NaN / Inf propagate
-            float4 y = make_float4(v[1], v[4], v[7], v[10]);
-            if (!(big < 1e30f && y.x != 0.0f && y.y != 0.0f && y.z != 0.0f && y.w != 0.0f)) {
-                y.x = interp_cubic(0.0f, v[0], v[1], v[2], v[3]);
-                y.y = interp_cubic(0.0f, v[3], v[4], v[5], v[6]);
-                y.z = interp_cubic(0.0f, v[6], v[7], v[8], v[9]);
-                y.w = interp_cubic(0.0f, v[9], v[10], v[11], v[12]);
+        // 48 kHz -> 16 kHz mono f32, four outputs per thread and quad: output n reads x[3n-2 .. 3n+1]; for n = 0 mod 4
+        // that is an 8-byte aligned float2 followed by three 16-byte aligned float4 of the stage (14 floats, 13 used).
+        // Two quads per iteration (independent instruction streams), all pointers advanced by constants.
+        // Quads start on a 32-sample boundary of the padded step buffer: every quarter-warp stores 128 contiguous bytes.
+        constexpr int QS = 4 * RS_THREADS;                       // outputs per sweep of the resampler warps (12 x 32)
+        static_assert(QS % 32 == 0, "a sweep must keep the 32-sample padding phase");
+        int i4 = (i_lo & ~31) + 4 * rtid;
+        if (i4 < i_lo) i4 += QS;
+        const float *px = reinterpret_cast<const float *>(srcp) + (sm.tile_k + 3 * (int)tile_off - 1 - f_lo) + 3 * i4;
+        float *yq = out.yb + ypad(i4);
+        float *pq = out.pcm + out.base + i4;
+        // a quad at i is stored whole when i + 4 <= (samples of this step the tile owns); never without a PCM output
+        const int lim4 = out.pcm ? (int)min((uint32_t)YLEN, out.wr_end - min(out.wr_end, out.base)) - 4 : -(1 << 30);
+        auto quad = [&](const float *p, float *ydst, float *pdst, int i) {
+            const float2 hh = *reinterpret_cast<const float2 *>(p);
+            const float4 a4 = *reinterpret_cast<const float4 *>(p + 2);
+            const float4 b4 = *reinterpret_cast<const float4 *>(p + 6);
+            const float4 c4 = *reinterpret_cast<const float4 *>(p + 10);
+            // frac == 0: the cubic returns y1 bit for bit when y1 != 0 and every tap is finite with |x| < 2 (exponent
+            // bit 30 clear in the OR of the 13 words: covers Inf / NaN); anything else takes the polynomial
+            const uint32_t orx = (__float_as_uint(hh.x) | __float_as_uint(hh.y) | __float_as_uint(a4.x)) |
+                                 (__float_as_uint(a4.y) | __float_as_uint(a4.z) | __float_as_uint(a4.w)) |
+                                 (__float_as_uint(b4.x) | __float_as_uint(b4.y) | __float_as_uint(b4.z)) |
+                                 (__float_as_uint(b4.w) | __float_as_uint(c4.x) | __float_as_uint(c4.y)) | __float_as_uint(c4.z);
+            float4 y = make_float4(hh.y, a4.z, b4.y, c4.x);
+            if (!((orx & 0x40000000u) == 0u && y.x != 0.0f && y.y != 0.0f && y.z != 0.0f && y.w != 0.0f)) {
+                y.x = interp_cubic(0.0f, hh.x, hh.y, a4.x, a4.y);
+                y.y = interp_cubic(0.0f, a4.y, a4.z, a4.w, b4.x);
+                y.z = interp_cubic(0.0f, b4.x, b4.y, b4.z, b4.w);
+                y.w = interp_cubic(0.0f, b4.w, c4.x, c4.y, c4.z);
             }
-            *reinterpret_cast<float4 *>(sm.ybuf + ypad(i4)) = y;
+            *reinterpret_cast<float4 *>(ydst) = y;
+            if (i <= lim4) __stcs(reinterpret_cast<float4 *>(pdst), y);
+            else {                                                // the quad straddles (or lies beyond) the end of the owner tile
+                const int left = lim4 + 4 - i;
+                if (left > 0) __stcs(pdst, y.x);
+                if (left > 1) __stcs(pdst + 1, y.y);
+                if (left > 2) __stcs(pdst + 2, y.z);
+            }
+        };
+        for (; i4 + QS < i_hi; i4 += 2 * QS) {
+            quad(px, yq, pq, i4);
+            quad(px + 3 * QS, yq + ypad(QS), pq + QS, i4 + QS);
+            px += 6 * QS; yq += 2 * ypad(QS); pq += 2 * QS;
         }
+        if (i4 < i_hi) quad(px, yq, pq, i4);
         return;
     }
     const uint32_t a = sm.tile_rem + (tile_off + (uint32_t)i) * s.p;
     if (q == 1) {
         // integer step (48 kHz -> 16 kHz): frac == 0 exactly; the cubic returns y1 bit for bit whenever y1 != 0 and
-        // the coefficients are finite -- checked per sample, everything else takes the polynomial
+        // the taps are finite with |x| < 2 -- checked per sample, everything else takes the polynomial
         int o = sm.tile_k + (int)a - 1 - f_lo;
         const int inc = (int)sm.inc_k;
-        for (; i < YLEN; i += FUSED_THREADS, o += inc) {
+#pragma unroll 2
+        for (; i < i_hi; i += RS_THREADS, o += inc) {
             const float y0 = tap_fast<KIND>(srcp, o), y1 = tap_fast<KIND>(srcp, o + 1);
             const float y2 = tap_fast<KIND>(srcp, o + 2), y3 = tap_fast<KIND>(srcp, o + 3);
-            const float big = (fabsf(y0) + fabsf(y1)) + (fabsf(y2) + fabsf(y3));   // NaN / Inf propagate
+            const uint32_t orx = __float_as_uint(y0) | __float_as_uint(y1) | __float_as_uint(y2) | __float_as_uint(y3);
             float v = y1;
-            if (!(y1 != 0.0f && big < 1e30f)) v = interp_cubic(0.0f, y0, y1, y2, y3);
-            sm.ybuf[ypad(i)] = v;
+            if (!(y1 != 0.0f && (orx & 0x40000000u) == 0u)) v = interp_cubic(0.0f, y0, y1, y2, y3);
+            out.put(i, v);
         }
         return;
     }
@@ -258,38 +386,52 @@ __device__ __forceinline__ void resample_step_fast(FusedSmem &sm, const StreamDe
     int k = sm.tile_k + (int)dk - 1 - f_lo;
     const uint32_t inc_k = sm.inc_k, inc_rem = sm.inc_rem;
     const float inv_q = 1.0f / (float)q;
-    const float *__restrict__ frac_tab = s.frac + base;
-    for (; i < YLEN; i += FUSED_THREADS) {
-        int o = k;
-        float frac;
-        if (mode == RS_TABLE) {
-            frac = __ldg(frac_tab + i);
-            o += __float2int_rn((float)rem * inv_q - frac);           // -1 when the f64 recurrence sits just below an integer
-        } else {
-            frac = (float)rem * inv_q;                                // q is a power of two: exact
+    const float *__restrict__ frac_tab = s.frac + out.base;
+    // batches of four outputs: the table fractions (L2) and the 16 taps are loaded before the first cubic
+    while (i < i_hi) {
+        int o[4], ii[4];
+        float frac[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            ii[u] = i + u * RS_THREADS;
+            o[u] = k;
+            frac[u] = (float)rem * inv_q;                                 // RS_EXACT: q is a power of two, exact
+            if (mode == RS_TABLE && ii[u] < i_hi) {
+                const float ft = __ldg(frac_tab + ii[u]);
+                o[u] += __float2int_rn(frac[u] - ft);                     // -1 when the f64 recurrence sits just below an integer
+                frac[u] = ft;
+            }
+            k += (int)inc_k;
+            rem += inc_rem;
+            if (rem >= q) { rem -= q; k += 1; }
         }
-        const float y0 = tap_fast<KIND>(srcp, o), y1 = tap_fast<KIND>(srcp, o + 1);
-        const float y2 = tap_fast<KIND>(srcp, o + 2), y3 = tap_fast<KIND>(srcp, o + 3);
-        sm.ybuf[ypad(i)] = interp_cubic(frac, y0, y1, y2, y3);
-        k += (int)inc_k;
-        rem += inc_rem;
-        if (rem >= q) { rem -= q; k += 1; }
+        float y[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int ou = ii[u] < i_hi ? o[u] : o[0];                    // keep the unused lanes of a partial batch in range
+#pragma unroll
+            for (int t = 0; t < 4; ++t) y[u][t] = tap_fast<KIND>(srcp, ou + t);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (ii[u] < i_hi) out.put(ii[u], interp_cubic(frac[u], y[u][0], y[u][1], y[u][2], y[u][3]));
+        i += 4 * RS_THREADS;
     }
 }
 
-// ---- phase 1: resample the 16 kHz samples [base + i_begin, base + YLEN) of the stream into ybuf ----
+// ---- resampling, checked: samples [base + i_lo, base + i_hi) of the stream, zero beyond n_out ----
 template <int KIND>
-__device__ __noinline__ void resample_step(FusedSmem &sm, const StreamDev &s, uint32_t tile_off, uint32_t base,
-                                              int i_begin)
+__device__ __noinline__ void resample_half(const FusedSmem &sm, int h, const StreamDev &s, const YSink out,
+                                           uint32_t tile_off, int i_lo, int i_hi, int rtid)
 {
-    const int tid = threadIdx.x;
-    const uint32_t st_lo = (uint32_t)sm.st_lo, st_hi = (uint32_t)sm.st_hi;
+    const unsigned char *__restrict__ stage = sm.stage[h];
+    const uint32_t st_lo = (uint32_t)sm.st_lo[h], st_hi = (uint32_t)sm.st_hi[h];
     const uint32_t n_out = s.n_out, mode = s.mode;
-    int i = i_begin + tid;
+    int i = i_lo + rtid;
     if (mode == RS_PASSTHROUGH) {
-        for (; i < YLEN; i += FUSED_THREADS) {
-            const uint32_t n = base + i;
-            sm.ybuf[ypad(i)] = n < n_out ? tap<KIND>(sm, s, st_lo, st_hi, (int)n) : 0.0f;
+        for (; i < i_hi; i += RS_THREADS) {
+            const uint32_t n = out.base + i;
+            out.put(i, n < n_out ? tap<KIND>(stage, s, st_lo, st_hi, (int)n) : 0.0f);
         }
         return;
     }
@@ -303,8 +445,8 @@ __device__ __noinline__ void resample_step(FusedSmem &sm, const StreamDev &s, ui
     const uint32_t inc_k = sm.inc_k, inc_rem = sm.inc_rem;
     const float inv_q = 1.0f / (float)q;
     const float *__restrict__ frac_tab = s.frac;
-    for (; i < YLEN; i += FUSED_THREADS) {
-        const uint32_t n = base + i;
+    for (; i < i_hi; i += RS_THREADS) {
+        const uint32_t n = out.base + i;
         float v = 0.0f;
         if (n < n_out) {
             int kk = k;
@@ -315,51 +457,69 @@ __device__ __noinline__ void resample_step(FusedSmem &sm, const StreamDev &s, ui
             } else {
                 frac = (float)rem * inv_q;                            // q is a power of two: exact
             }
-            const float y0 = tap<KIND>(sm, s, st_lo, st_hi, kk - 1);
-            const float y1 = tap<KIND>(sm, s, st_lo, st_hi, kk);
-            const float y2 = tap<KIND>(sm, s, st_lo, st_hi, kk + 1);
-            const float y3 = tap<KIND>(sm, s, st_lo, st_hi, kk + 2);
+            const float y0 = tap<KIND>(stage, s, st_lo, st_hi, kk - 1);
+            const float y1 = tap<KIND>(stage, s, st_lo, st_hi, kk);
+            const float y2 = tap<KIND>(stage, s, st_lo, st_hi, kk + 1);
+            const float y3 = tap<KIND>(stage, s, st_lo, st_hi, kk + 2);
             // frac == 0 (48 kHz -> 16 kHz): a0 + a1*0 + a2*0 + a3*0 == y1 bit for bit whenever y1 != 0 and the
             // coefficients are finite; only then skip the polynomial
-            const float big = (fabsf(y0) + fabsf(y1)) + (fabsf(y2) + fabsf(y3));   // NaN / Inf propagate
-            if (frac == 0.0f && y1 != 0.0f && big < 1e30f) v = y1;
+            const uint32_t orx = __float_as_uint(y0) | __float_as_uint(y1) | __float_as_uint(y2) | __float_as_uint(y3);
+            if (frac == 0.0f && y1 != 0.0f && (orx & 0x40000000u) == 0u) v = y1;
             else v = interp_cubic(frac, y0, y1, y2, y3);
         }
-        sm.ybuf[ypad(i)] = v;
+        out.put(i, v);
         k += (int)inc_k;
         rem += inc_rem;
         if (rem >= q) { rem -= q; k += 1; }
     }
 }
 
-// ---- phase 2a: one frame per half-warp: window, packed real FFT, power -> pbuf[bin][q] ----
-__device__ __forceinline__ void fft_frame(FusedSmem &sm, float *__restrict__ scr, int q, int l, int lane,
-                                          const float2 (&tw2r)[8], const float2 (&winr)[13])
+template <int KIND>
+__device__ __forceinline__ void resample_dispatch(const FusedSmem &sm, int h, const StreamDev &s, const YSink &out,
+                                                  uint32_t tile_off, int i_lo, int i_hi, int rtid)
 {
-    float xr[16], xi[16];
-    const float *yb = sm.ybuf + 180 * q + 2 * l;      // ypad(160 q + 32 n1 + 2 l) = 180 q + 36 n1 + 2 l
+    const uint32_t interior = sm.st_interior[h];
+    if (KIND != K_GENERIC && interior == 1) resample_half_fast<KIND, true>(sm, h, s, out, tile_off, i_lo, i_hi, rtid);
+    else if (KIND != K_GENERIC && interior == 2) resample_half_fast<KIND, false>(sm, h, s, out, tile_off, i_lo, i_hi, rtid);
+    else resample_half<KIND>(sm, h, s, out, tile_off, i_lo, i_hi, rtid);
+}
+
+// ---- F role: one frame per half-warp ----
+// window + pack: this lane holds z[16 n1 + l] = x[32 n1 + 2 l] + i x[32 n1 + 2 l + 1] of frame q
+__device__ __forceinline__ void fft_load(const float *__restrict__ ybuf, const float *__restrict__ window, int q, int l,
+                                         float (&xr)[16], float (&xi)[16])
+{
+    const float *yb = ybuf + 180 * q + 2 * l;      // ypad(160 q + 32 n1 + 2 l) = 180 q + 36 n1 + 2 l
+    const float *wp = window + 2 * l;              // both half-warps read the same window words: one wavefront
 #pragma unroll
     for (int n1 = 0; n1 < 12; ++n1) {
         const float2 v = *reinterpret_cast<const float2 *>(yb + 36 * n1);
-        xr[n1] = __fmul_rn(v.x, winr[n1].x);
-        xi[n1] = __fmul_rn(v.y, winr[n1].y);
+        const float2 w = *reinterpret_cast<const float2 *>(wp + 32 * n1);
+        xr[n1] = __fmul_rn(v.x, w.x);
+        xi[n1] = __fmul_rn(v.y, w.y);
     }
     {
         float2 v = make_float2(0.0f, 0.0f);
-        if (l < 8) v = *reinterpret_cast<const float2 *>(yb + 36 * 12);   // samples 384 + 2l (+1) < 400; winr[12] is 0 beyond
-        xr[12] = __fmul_rn(v.x, winr[12].x);
-        xi[12] = __fmul_rn(v.y, winr[12].y);
+        if (l < 8) v = *reinterpret_cast<const float2 *>(yb + 36 * 12);   // samples 384 + 2l (+1) < 400; the window is 0 beyond
+        const float2 w = *reinterpret_cast<const float2 *>(wp + 32 * 12);
+        xr[12] = __fmul_rn(v.x, w.x);
+        xi[12] = __fmul_rn(v.y, w.y);
     }
 #pragma unroll
     for (int n1 = 13; n1 < 16; ++n1) { xr[n1] = 0.0f; xi[n1] = 0.0f; }
+}
 
+// the two 16-point passes of the packed 256-point transform; leaves Z[l + 16 k2] in slot(k2)
+__device__ __forceinline__ void fft_passes(const float2 *__restrict__ tw1, float *__restrict__ scr, int l, float (&xr)[16],
+                                           float (&xi)[16])
+{
     // pass 1: 16-point FFT over n1 (this lane is n2 = l), twiddle W256^(l k1), transposed store
     fft16<true>(xr, xi);
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
         float ar = xr[fft16_slot(k1)], ai = xi[fft16_slot(k1)];
         if (k1 > 0) {
-            const float2 w = sm.fft.tw1[k1 * 16 + l];
+            const float2 w = tw1[k1 * 16 + l];
             AF_CMUL(ar, ai, w.x, w.y);
         }
         *reinterpret_cast<float2 *>(scr + (k1 * SCR_ROW + l) * 2) = make_float2(ar, ai);
@@ -373,10 +533,15 @@ __device__ __forceinline__ void fft_frame(FusedSmem &sm, float *__restrict__ scr
     }
     __syncwarp();
     fft16<false>(xr, xi);
-    // Z[l + 16 k2] is in slot(k2).  Hermitian split: pair k = l + 16 r with 256 - k, which lives in
-    // lane (16 - l) & 15 at k2 = 15 - r (lane 0 pairs with itself at k2 = (16 - r) & 15).
+}
+
+// Hermitian split + power -> pbuf[bin][q].  Pair k = l + 16 r with 256 - k, which lives in lane (16 - l) & 15 at
+// k2 = 15 - r (lane 0 pairs with itself at k2 = (16 - r) & 15).
+__device__ __forceinline__ void fft_power(float *__restrict__ pbuf, const float2 *__restrict__ tw2, int q, int l, int lane,
+                                          const float (&xr)[16], const float (&xi)[16])
+{
     const int src = ((16 - l) & 15) | (lane & 16);
-    float *pb = sm.pbuf + q;
+    float *pb = pbuf + q;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const float zr = xr[fft16_slot(r)], zi = xi[fft16_slot(r)];
@@ -384,7 +549,7 @@ __device__ __forceinline__ void fft_frame(FusedSmem &sm, float *__restrict__ scr
         float pi = __shfl_sync(0xffffffffu, xi[fft16_slot(15 - r)], src);
         if (l == 0) { pr = xr[fft16_slot((16 - r) & 15)]; pi = xi[fft16_slot((16 - r) & 15)]; }
         const int k = l + 16 * r;
-        const float2 w = tw2r[r];
+        const float2 w = tw2[l + 16 * r];
         const float e2r = zr + pr, e2i = zi - pi;      // 2E = Z[k] + conj(Z[256-k])
         const float o2r = zi + pi, o2i = pr - zr;      // 2O = -i (Z[k] - conj(Z[256-k]))
         const float tr = w.x * o2r - w.y * o2i;
@@ -400,12 +565,12 @@ __device__ __forceinline__ void fft_frame(FusedSmem &sm, float *__restrict__ scr
     }
 }
 
-// ---- phase 2b: VAD warp, lane = frame: calculate_energy (vad.rs:157-168), strictly sequential ----
+// ---- V role, lane = frame: calculate_energy (vad.rs:157-168), strictly sequential ----
 __device__ __forceinline__ float frame_energy_smem(const float *__restrict__ ybuf, int q)
 {
     const float4 *yp = reinterpret_cast<const float4 *>(ybuf) + 45 * q;   // ypad(160 q) / 4
     float sum = 0.0f;
-#pragma unroll 4
+#pragma unroll 2
     for (int s8 = 0; s8 < 12; ++s8) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -427,203 +592,288 @@ __device__ __forceinline__ float frame_energy_smem(const float *__restrict__ ybu
     return __fdiv_rn(sum, (float)WIN);
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS, 2) af_fused_kernel(const FusedParams P)
+// =============================================================================================
+// role bodies
+// =============================================================================================
+__device__ __forceinline__ void role_fft(FusedSmem &sm, const FusedParams &P, int warp, int lane)
+{
+    const int l = lane & 15, half = lane >> 4;
+    const int q = warp * 2 + half;                      // this half-warp's frame inside the step
+    float *scr = sm.scr + q * SCR_FLOATS_PER_FRAME;
+    const bool on = P.n_mels != 0;
+    uint32_t it = 0;
+    AF_STATS_DECL
+    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        uint32_t n_frames;
+        const TileGeo t = tile_geo(P, tile, &n_frames);
+        for (uint32_t g = 0; g < t.n_steps; ++g, ++it) {
+            const uint32_t f0 = t.f_tile0 + g * SF;
+            const int n_valid = f0 < n_frames ? (int)min((uint32_t)SF, n_frames - f0) : 0;
+            const bool work = on && warp * 2 < n_valid;         // warp-uniform: skip fully invalid pairs
+            const int b = (int)(it & 1u);
+            float xr[16], xi[16];
+            AF_WAIT(&sm.y_full[b], (it >> 1) & 1u, 0);
+            if (work) fft_load(sm.ybuf[b], sm.window, q, l, xr, xi);
+            warp_arrive(&sm.y_empty[b], lane);                  // the step buffer is no longer needed by this warp
+            if (work) fft_passes(sm.tw1, scr, l, xr, xi);
+            AF_WAIT(&sm.p_empty, (it & 1u) ^ 1u, 1);             // the mel warps are done with the previous step's power
+            if (work) fft_power(sm.pbuf, sm.tw2, q, l, lane, xr, xi);
+            warp_arrive(&sm.p_full, lane);
+        }
+    }
+    AF_STATS_FLUSH(0, lane);
+}
+
+__device__ __forceinline__ void role_mel(FusedSmem &sm, const FusedParams &P, int mw, int lane)
+{
+    const uint32_t M = P.n_mels;
+    const float log_mul = P.log_scale, log_floor = P.log_floor;
+    const int q0 = sm.mel.quad_begin[mw], q1 = sm.mel.quad_begin[mw + 1];
+    const bool vec = (M & 3u) == 0 && (P.logmel_stride & 3ull) == 0 && ((reinterpret_cast<uintptr_t>(P.logmel) & 15) == 0);
+    uint32_t it = 0;
+    AF_STATS_DECL
+    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        uint32_t n_frames;
+        const TileGeo t = tile_geo(P, tile, &n_frames);
+        float *lm_row = P.logmel ? P.logmel + (uint64_t)t.stream * P.logmel_stride : nullptr;
+        for (uint32_t g = 0; g < t.n_steps; ++g, ++it) {
+            const uint32_t f0 = t.f_tile0 + g * SF;
+            const int n_valid = f0 < n_frames ? (int)min((uint32_t)SF, n_frames - f0) : 0;
+            AF_WAIT(&sm.p_full, it & 1u, 0);
+            if (M && lm_row && n_valid > 0) {
+                const bool valid = lane < n_valid;
+                float *dst = lm_row + (uint64_t)(f0 + lane) * M;
+                const float *pcol = sm.pbuf + lane;
+                for (int qd = q0; qd < q1; ++qd) {
+                    // four adjacent filters at a time: eight independent FMA chains, weights by warp-uniform LDS.128
+                    const uint4 dq = *reinterpret_cast<const uint4 *>(&sm.mel.quad[qd]);
+                    const int c4 = (int)(dq.z & 0xffffu);
+                    const float4 *w4 = reinterpret_cast<const float4 *>(sm.mel.w) + 4 * (dq.z >> 16);
+                    const float *pa = pcol + (dq.x & 0xffffu) * PB_ROW, *pb = pcol + (dq.x >> 16) * PB_ROW;
+                    const float *pc = pcol + (dq.y & 0xffffu) * PB_ROW, *pd = pcol + (dq.y >> 16) * PB_ROW;
+                    float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f, c0 = 0.0f, c1 = 0.0f, d0 = 0.0f, d1 = 0.0f;
+#pragma unroll 1
+                    for (int j = 0; j < c4; ++j) {
+                        const float4 wa = w4[0], wb = w4[1], wc = w4[2], wd = w4[3];
+                        a0 = fmaf(wa.x, pa[0], a0); a1 = fmaf(wa.y, pa[PB_ROW], a1);
+                        b0 = fmaf(wb.x, pb[0], b0); b1 = fmaf(wb.y, pb[PB_ROW], b1);
+                        c0 = fmaf(wc.x, pc[0], c0); c1 = fmaf(wc.y, pc[PB_ROW], c1);
+                        d0 = fmaf(wd.x, pd[0], d0); d1 = fmaf(wd.y, pd[PB_ROW], d1);
+                        a0 = fmaf(wa.z, pa[2 * PB_ROW], a0); a1 = fmaf(wa.w, pa[3 * PB_ROW], a1);
+                        b0 = fmaf(wb.z, pb[2 * PB_ROW], b0); b1 = fmaf(wb.w, pb[3 * PB_ROW], b1);
+                        c0 = fmaf(wc.z, pc[2 * PB_ROW], c0); c1 = fmaf(wc.w, pc[3 * PB_ROW], c1);
+                        d0 = fmaf(wd.z, pd[2 * PB_ROW], d0); d1 = fmaf(wd.w, pd[3 * PB_ROW], d1);
+                        w4 += 4; pa += 4 * PB_ROW; pb += 4 * PB_ROW; pc += 4 * PB_ROW; pd += 4 * PB_ROW;
+                    }
+                    float o[4];
+                    o[0] = __log2f(fmaxf(a0 + a1, log_floor)) * log_mul;
+                    o[1] = __log2f(fmaxf(b0 + b1, log_floor)) * log_mul;
+                    o[2] = __log2f(fmaxf(c0 + c1, log_floor)) * log_mul;
+                    o[3] = __log2f(fmaxf(d0 + d1, log_floor)) * log_mul;
+                    if (valid) {
+                        if (vec) __stcs(reinterpret_cast<float4 *>(dst + 4 * qd), make_float4(o[0], o[1], o[2], o[3]));
+                        else {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (4 * qd + u < (int)M) dst[4 * qd + u] = o[u];
+                        }
+                    }
+                }
+            }
+            warp_arrive(&sm.p_empty, lane);
+        }
+    }
+    AF_STATS_FLUSH(1, lane);
+}
+
+__device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, int lane)
+{
+    // fills run one step ahead of the resamplers; the energies of a step are computed once its buffer is full
+    const bool chains = P.do_energy && P.energy;
+    uint32_t it = 0;
+    bool have_prev = false;
+    uint32_t prev_f0 = 0, prev_nf = 0, prev_stream = 0, prev_it = 0;
+    AF_STATS_DECL
+    for (uint32_t tile = blockIdx.x;; tile += gridDim.x) {
+        const bool live = tile < P.n_tiles;
+        TileGeo t{};
+        uint32_t n_frames = 0;
+        FillTile ft{};
+        if (live) {
+            t = tile_geo(P, tile, &n_frames);
+            if (lane == 0) ft = fill_tile(P, tile);
+        }
+        const uint32_t n_steps = live ? t.n_steps : 1u;        // one drain iteration after the last tile
+        for (uint32_t g = 0; g < n_steps; ++g) {
+            if (live) {
+                if (lane == 0) {
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        AF_WAIT(&sm.stage_empty[h], (it & 1u) ^ 1u, 0);
+                        AF_TIC
+                        issue_fill(sm, P, ft, g, h);
+                        AF_TOC(2)
+                    }
+                }
+                __syncwarp();
+            }
+            if (have_prev) {
+                const int b = (int)(prev_it & 1u);
+                AF_WAIT(&sm.y_full[b], (prev_it >> 1) & 1u, 1);
+                if (chains) {
+                    const int n_valid = prev_f0 < prev_nf ? (int)min((uint32_t)SF, prev_nf - prev_f0) : 0;
+                    if (lane < n_valid)
+                        P.energy[(uint64_t)prev_stream * P.energy_stride + prev_f0 + lane] = frame_energy_smem(sm.ybuf[b], lane);
+                }
+                warp_arrive(&sm.y_empty[b], lane);
+            }
+            if (live) {
+                have_prev = true;
+                prev_f0 = t.f_tile0 + g * SF; prev_nf = n_frames; prev_stream = t.stream; prev_it = it;
+                ++it;
+            } else {
+                have_prev = false;
+            }
+        }
+        if (!live) break;
+    }
+    AF_STATS_FLUSH(2, lane);
+}
+
+__device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &P, int rtid, int lane)
+{
+    uint32_t it = 0;
+    AF_STATS_DECL
+    // the descriptor of a tile's stream is fetched one tile ahead into registers: threads 0..15 hold one word of
+    // the StreamDev each, thread 32 the exact position of the tile's first output
+    uint32_t nx_word = 0, nx_rem = 0, nx_inck = 0, nx_incr = 0;
+    int nx_k = 0;
+    TileGeo nx_t{};
+    auto prefetch = [&](uint32_t tile) {
+        if (tile >= P.n_tiles) return;
+        const TileDev td = P.tiles[tile];
+        const StreamDev *sp = P.streams + td.stream;
+        nx_t.stream = td.stream;
+        nx_t.n_tile0 = td.tile * TILE_SAMPLES;
+        nx_t.tile_end = min(nx_t.n_tile0 + (uint32_t)TILE_SAMPLES, sp->n_out);
+        nx_t.n_steps = (nx_t.tile_end - nx_t.n_tile0 + STEP_SAMPLES - 1) / STEP_SAMPLES;
+        if (rtid < (int)(sizeof(StreamDev) / 4)) nx_word = reinterpret_cast<const uint32_t *>(sp)[rtid];
+        if (rtid == 32) {
+            const uint32_t p = sp->p, q = sp->q;
+            if (sp->mode != RS_PASSTHROUGH) {
+                long long k; uint32_t rem;
+                resample_pos((uint64_t)td.tile * TILE_SAMPLES, p, q, &k, &rem);
+                nx_k = (int)k; nx_rem = rem;
+                const uint32_t inc = (uint32_t)RS_THREADS * p;
+                nx_inck = inc / q; nx_incr = inc % q;
+            }
+        }
+    };
+    prefetch(blockIdx.x);
+    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        AF_TIC
+        const TileGeo t = nx_t;
+        named_bar_sync(1, RS_THREADS);                  // every resampler thread is done with the previous tile's descriptor
+        if (rtid < (int)(sizeof(StreamDev) / 4)) reinterpret_cast<uint32_t *>(&sm.stream)[rtid] = nx_word;
+        if (rtid == 32) { sm.tile_k = nx_k; sm.tile_rem = nx_rem; sm.inc_k = nx_inck; sm.inc_rem = nx_incr; }
+        named_bar_sync(1, RS_THREADS);
+        prefetch(tile + gridDim.x);
+        AF_TOC(2)
+        const StreamDev &s = sm.stream;
+        int kind = K_GENERIC;
+        if (s.channels == 1) kind = s.format == FMT_F32 ? K_F32_1 : K_I16_1;
+        else if (s.channels == 2) kind = s.format == FMT_F32 ? K_F32_2 : K_I16_2;
+        float *pcm_row = P.pcm ? P.pcm + (uint64_t)t.stream * P.pcm_stride : nullptr;
+
+        for (uint32_t g = 0; g < t.n_steps; ++g, ++it) {
+            const int b = (int)(it & 1u);
+            const uint32_t toff = g * STEP_SAMPLES;
+            YSink out{sm.ybuf[b], pcm_row, t.n_tile0 + toff, t.tile_end};
+            AF_WAIT(&sm.y_empty[b], ((it >> 1) & 1u) ^ 1u, 0);   // FFT and VAD warps are done with this buffer
+            AF_TIC2
+            if (g > 0) {
+                // the 240-sample overlap with the previous step (written by all resampler threads: sync first)
+                named_bar_sync(1, RS_THREADS);
+                const float *prev = sm.ybuf[b ^ 1];
+                for (int i = rtid; i < CARRY; i += RS_THREADS) out.yb[ypad(i)] = prev[ypad(STEP_SAMPLES + i)];
+            }
+            AF_TOC(3)
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                AF_WAIT(&sm.stage_full[h], it & 1u, 1);
+                const int i_lo = half_lo(g, h), i_hi = half_hi(h);
+                AF_TIC2
+                switch (kind) {
+                case K_F32_1: resample_dispatch<K_F32_1>(sm, h, s, out, toff, i_lo, i_hi, rtid); break;
+                case K_I16_1: resample_dispatch<K_I16_1>(sm, h, s, out, toff, i_lo, i_hi, rtid); break;
+                case K_F32_2: resample_dispatch<K_F32_2>(sm, h, s, out, toff, i_lo, i_hi, rtid); break;
+                case K_I16_2: resample_dispatch<K_I16_2>(sm, h, s, out, toff, i_lo, i_hi, rtid); break;
+                default: resample_dispatch<K_GENERIC>(sm, h, s, out, toff, i_lo, i_hi, rtid); break;
+                }
+                AF_TOC(4)
+                warp_arrive(&sm.stage_empty[h], lane);          // this warp no longer reads stage[h] or its metadata
+            }
+            warp_arrive(&sm.y_full[b], lane);
+        }
+    }
+    AF_STATS_FLUSH(3, lane);
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int l = lane & 15, half = lane >> 4;
-    const uint32_t M = P.n_mels;
-    const bool is_filler = (tid == VAD_WARP * 32 + 31);             // last lane of the VAD warp (it has no frame)
 
-    // constant tables -> shared memory (once per CTA)
+    // constant tables -> shared memory, barriers (once per CTA)
     {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(P.fft);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&sm.fft);
-        for (int i = tid; i < (int)(sizeof(FftTables) / 4); i += FUSED_THREADS) dst[i] = src[i];
-        if (M) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(P.fft->tw1);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(sm.tw1);
+        for (int i = tid; i < (int)(sizeof(sm.tw1) / 4); i += FUSED_THREADS) dst[i] = src[i];
+        for (int i = tid; i < 256; i += FUSED_THREADS) reinterpret_cast<float *>(sm.tw2)[i] = reinterpret_cast<const float *>(P.fft->tw2)[i];
+        for (int i = tid; i < 416; i += FUSED_THREADS) sm.window[i] = P.fft->window[i];
+        if (P.n_mels) {
             const uint32_t *ms = reinterpret_cast<const uint32_t *>(P.mel);
             uint32_t *md = reinterpret_cast<uint32_t *>(&sm.mel);
             for (int i = tid; i < (int)(sizeof(MelTables) / 4); i += FUSED_THREADS) md[i] = ms[i];
         }
+        for (int i = tid; i < PBUF_FLOATS; i += FUSED_THREADS) sm.pbuf[i] = 0.0f;   // incl. the zero rows behind bin 256
     }
-    if (is_filler) {
-        mbar_init(&sm.mbar, 1);
-        if (blockIdx.x < P.n_tiles) issue_fill(sm, P, blockIdx.x, 0);
+    if (tid == 0) {
+        for (int h = 0; h < 2; ++h) {
+            mbar_init(&sm.stage_full[h], 1);
+            mbar_init(&sm.stage_empty[h], RS_WARPS);
+            mbar_init(&sm.y_full[h], RS_WARPS);
+            mbar_init(&sm.y_empty[h], FFT_WARPS + 1);
+        }
+        mbar_init(&sm.p_full, FFT_WARPS);
+        mbar_init(&sm.p_empty, MEL_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    float2 tw2r[8];                                     // W512^(l + 16 r): this lane's post-twiddles, register resident
-#pragma unroll
-    for (int r = 0; r < 8; ++r) tw2r[r] = lds_f2_pinned(&sm.fft.tw2[l + 16 * r]);
-    float2 winr[13];                                    // this lane's window samples w[32 n1 + 2 l], w[32 n1 + 2 l + 1]
-#pragma unroll
-    for (int n1 = 0; n1 < 13; ++n1) winr[n1] = lds_f2_pinned(sm.fft.window + 32 * n1 + 2 * l);
-    const float log_mul = P.log_scale;
-    uint32_t fill_parity = 0;
 
-    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        const TileDev td = P.tiles[tile];
-        if (tid < (int)(sizeof(StreamDev) / 4))
-            reinterpret_cast<uint32_t *>(&sm.stream)[tid] = reinterpret_cast<const uint32_t *>(P.streams + td.stream)[tid];
-        __syncthreads();
-        const StreamDev &s = sm.stream;
-        const uint32_t n_tile0 = td.tile * TILE_SAMPLES;
-        const uint32_t tile_end = min(n_tile0 + (uint32_t)TILE_SAMPLES, s.n_out);
-        const uint32_t f_tile0 = td.tile * TILE_FRAMES;
-        const uint32_t n_steps = (tile_end - n_tile0 + STEP_SAMPLES - 1) / STEP_SAMPLES;
-        if (tid == 0 && s.mode != RS_PASSTHROUGH) {
-            long long k; uint32_t rem;
-            resample_pos(n_tile0, s.p, s.q, &k, &rem);
-            sm.tile_k = (int)k; sm.tile_rem = rem;
-            const uint32_t inc = (uint32_t)FUSED_THREADS * s.p;
-            sm.inc_k = inc / s.q; sm.inc_rem = inc % s.q;
-        }
-        __syncthreads();
-        int kind = K_GENERIC;
-        if (s.channels == 1) kind = s.format == FMT_F32 ? K_F32_1 : K_I16_1;
-        else if (s.channels == 2) kind = s.format == FMT_F32 ? K_F32_2 : K_I16_2;
-        float *pcm_row = P.pcm ? P.pcm + (uint64_t)td.stream * P.pcm_stride : nullptr;
-        float *lm_row = P.logmel ? P.logmel + (uint64_t)td.stream * P.logmel_stride : nullptr;
-        float *en_row = P.energy ? P.energy + (uint64_t)td.stream * P.energy_stride : nullptr;
-
-        for (uint32_t g = 0; g < n_steps; ++g) {
-            const uint32_t base = n_tile0 + g * STEP_SAMPLES;       // stream index of ybuf sample 0
-            const uint32_t f0 = f_tile0 + g * SF;                   // first frame of the step
-            const int n_valid = f0 < s.n_frames ? (int)min((uint32_t)SF, s.n_frames - f0) : 0;
-
-            // ---- phase 1: wait for the staged input, resample (first step of a tile also recomputes the halo) ----
-            mbar_wait(&sm.mbar, fill_parity);
-            fill_parity ^= 1u;
-            const int i_begin = g == 0 ? 0 : CARRY;
-            const uint32_t toff = g * STEP_SAMPLES;
-            if (sm.st_interior && kind != K_GENERIC) {
-                if (sm.st_interior == 1) {
-                    switch (kind) {
-                    case K_F32_1: resample_step_fast<K_F32_1, true>(sm, s, toff, base, i_begin); break;
-                    case K_I16_1: resample_step_fast<K_I16_1, true>(sm, s, toff, base, i_begin); break;
-                    case K_F32_2: resample_step_fast<K_F32_2, true>(sm, s, toff, base, i_begin); break;
-                    default: resample_step_fast<K_I16_2, true>(sm, s, toff, base, i_begin); break;
-                    }
-                } else {
-                    switch (kind) {
-                    case K_F32_1: resample_step_fast<K_F32_1, false>(sm, s, toff, base, i_begin); break;
-                    case K_I16_1: resample_step_fast<K_I16_1, false>(sm, s, toff, base, i_begin); break;
-                    case K_F32_2: resample_step_fast<K_F32_2, false>(sm, s, toff, base, i_begin); break;
-                    default: resample_step_fast<K_I16_2, false>(sm, s, toff, base, i_begin); break;
-                    }
-                }
-            } else {
-                switch (kind) {
-                case K_F32_1: resample_step<K_F32_1>(sm, s, toff, base, i_begin); break;
-                case K_I16_1: resample_step<K_I16_1>(sm, s, toff, base, i_begin); break;
-                case K_F32_2: resample_step<K_F32_2>(sm, s, toff, base, i_begin); break;
-                case K_I16_2: resample_step<K_I16_2>(sm, s, toff, base, i_begin); break;
-                default: resample_step<K_GENERIC>(sm, s, toff, base, i_begin); break;
-                }
-            }
-            __syncthreads();
-
-            // the 400-term energy chains of the VAD warp (>= 1600 cycles) run beside the FFT phase of warps 0..7
-            const bool vad_busy = P.do_energy && en_row;
-            const int mel_threads = FUSED_THREADS;
-            if (warp == VAD_WARP) {
-                // ===== warp 8: next stage fill (async bulk copy), then one 400-term energy chain per lane =====
-                if (is_filler) {
-                    if (g + 1 < n_steps) issue_fill(sm, P, tile, g + 1);
-                    else if (tile + gridDim.x < P.n_tiles) issue_fill(sm, P, tile + gridDim.x, 0);
-                }
-                if (vad_busy && lane < n_valid) en_row[f0 + lane] = frame_energy_smem(sm.ybuf, lane);
-                __syncwarp();
-                named_bar_arrive(2, FUSED_THREADS);                   // done reading ybuf
-            } else if (warp == AUX_WARP) {
-                // ===== warp 9: PCM write-out of the step, then carry the 240-sample overlap forward =====
-                if (pcm_row) {
-                    const uint32_t own_end = min(base + (uint32_t)STEP_SAMPLES, tile_end);
-                    if (own_end == base + (uint32_t)STEP_SAMPLES) {
-                        // full step: 640 float4, 20 per lane, loads batched ahead of the stores
-                        float4 *dst = reinterpret_cast<float4 *>(pcm_row + base);
-#pragma unroll
-                        for (int it = 0; it < 20; it += 5) {
-                            float4 v[5];
-#pragma unroll
-                            for (int u = 0; u < 5; ++u) v[u] = *reinterpret_cast<const float4 *>(sm.ybuf + ypad(4 * (lane + 32 * (it + u))));
-#pragma unroll
-                            for (int u = 0; u < 5; ++u) dst[lane + 32 * (it + u)] = v[u];
-                        }
-                    } else {
-                        for (uint32_t i4 = lane * 4; base + i4 < own_end; i4 += 32 * 4) {
-                            const float4 v = *reinterpret_cast<const float4 *>(sm.ybuf + ypad((int)i4));
-                            const uint32_t n = base + i4;
-                            if (n + 4 <= own_end) {
-                                *reinterpret_cast<float4 *>(pcm_row + n) = v;
-                            } else {
-                                if (n < own_end) pcm_row[n] = v.x;
-                                if (n + 1 < own_end) pcm_row[n + 1] = v.y;
-                                if (n + 2 < own_end) pcm_row[n + 2] = v.z;
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                named_bar_sync(2, FUSED_THREADS);                     // FFT warps and the VAD warp are done reading ybuf
-                if (g + 1 < n_steps) {
-                    for (int i = lane; i < CARRY; i += 32) sm.ybuf[ypad(i)] = sm.ybuf[ypad(i) + ypad(STEP_SAMPLES)];
-                }
-            } else {
-                // ===== warps 0..7: one frame per half-warp =====
-                if (M && warp * 2 < n_valid) {                        // warp-uniform: skip fully invalid pairs
-                    const int hw = warp * 2 + half;
-                    fft_frame(sm, sm.scr + hw * SCR_FLOATS_PER_FRAME, hw, l, lane, tw2r, winr);
-                }
-                __syncwarp();
-                named_bar_arrive(2, FUSED_THREADS);                   // ybuf no longer needed by this warp
-            }
-            {
-                const int mtid = tid;
-                named_bar_sync(1, mel_threads);                       // pbuf complete
-
-                // ---- phase 3: mel + log into the stage (thread = filter x 4 frames) ----
-                if (M && n_valid > 0) {
-                    const int n_items = (int)M * (SF / 4);
-                    for (int item = mtid; item < n_items; item += mel_threads) {
-                        const int m = item >> 2, fq = item & 3;
-                        if (fq * 4 >= n_valid) continue;
-                        const int lo = sm.mel.lo[m], cnt = sm.mel.cnt[m];
-                        const float *w = sm.mel.w + sm.mel.off[m];
-                        const float *pp = sm.pbuf + lo * PB_ROW + 4 * fq;
-                        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-                        int j = 0;
-                        for (; j + 2 <= cnt; j += 2) {
-                            const float w0 = w[j], w1 = w[j + 1];
-                            const float4 p0 = *reinterpret_cast<const float4 *>(pp + j * PB_ROW);
-                            const float4 p1 = *reinterpret_cast<const float4 *>(pp + (j + 1) * PB_ROW);
-                            a0 = fmaf(w0, p0.x, a0); a1 = fmaf(w0, p0.y, a1); a2 = fmaf(w0, p0.z, a2); a3 = fmaf(w0, p0.w, a3);
-                            a0 = fmaf(w1, p1.x, a0); a1 = fmaf(w1, p1.y, a1); a2 = fmaf(w1, p1.z, a2); a3 = fmaf(w1, p1.w, a3);
-                        }
-                        if (j < cnt) {
-                            const float w0 = w[j];
-                            const float4 p0 = *reinterpret_cast<const float4 *>(pp + j * PB_ROW);
-                            a0 = fmaf(w0, p0.x, a0); a1 = fmaf(w0, p0.y, a1); a2 = fmaf(w0, p0.z, a2); a3 = fmaf(w0, p0.w, a3);
-                        }
-                        // the 8 consecutive filters of a quarter-warp fill one 32-byte sector per frame row
-                        if (lm_row) {
-                            float *dst = lm_row + (uint64_t)(f0 + 4 * fq) * M + m;
-                            const int nv = n_valid - 4 * fq;
-                            dst[0] = __log2f(fmaxf(a0, P.log_floor)) * log_mul;
-                            if (nv > 1) dst[M] = __log2f(fmaxf(a1, P.log_floor)) * log_mul;
-                            if (nv > 2) dst[2 * M] = __log2f(fmaxf(a2, P.log_floor)) * log_mul;
-                            if (nv > 3) dst[3 * M] = __log2f(fmaxf(a3, P.log_floor)) * log_mul;
-                        }
-                    }
-                }
-            }
-            __syncthreads();        // ybuf carried, pbuf consumed: the next phase 1 / FFT may overwrite them
-        }
-        __syncthreads();
-    }
+    // 896 threads x 72 registers: every role fits (or nearly fits) that budget, so no setmaxnreg rebalancing
+    if (warp < FFT_WARPS) role_fft(sm, P, warp, lane);
+    else if (warp < VAD_WARP) role_mel(sm, P, warp - MEL_WARP0, lane);
+    else if (warp == VAD_WARP) role_vad(sm, P, lane);
+    else role_resample(sm, P, tid - RS_WARP0 * 32, lane);
 }
 
 size_t fused_smem_bytes() { return sizeof(FusedSmem); }
+
+// debugging aid: copies (and clears) the pipeline statistics; all zero unless built with -DAF_PIPE_STATS
+cudaError_t fused_pipe_stats(unsigned long long out[32])
+{
+#ifdef AF_PIPE_STATS
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_pipe_stats, sizeof(unsigned long long) * 32);
+    if (e != cudaSuccess) return e;
+    unsigned long long zero[32] = {};
+    return cudaMemcpyToSymbol(g_pipe_stats, zero, sizeof(zero));
+#else
+    for (int i = 0; i < 32; ++i) out[i] = 0;
+    return cudaSuccess;
+#endif
+}
 
 cudaError_t launch_fused(const FusedParams &P, int n_ctas, cudaStream_t st)
 {

@@ -75,7 +75,9 @@ bool build_mel_tables(uint32_t n_mels, float f_min, float f_max, MelTables *t)
     const double m_lo = hz_to_mel_htk((double)f_min), m_hi = hz_to_mel_htk((double)f_max);
     for (uint32_t i = 0; i < n_mels + 2; ++i)
         pts[i] = mel_to_hz_htk(m_lo + (m_hi - m_lo) * (double)i / (double)(n_mels + 1));
-    uint32_t off = 0;
+    // per-filter nonzero ranges
+    std::vector<std::vector<float>> wts(n_mels);
+    std::vector<int> los(n_mels, 0);
     for (uint32_t m = 0; m < n_mels; ++m) {
         int lo = -1, hi = -1;
         std::vector<float> w(NBIN, 0.0f);
@@ -89,11 +91,51 @@ bool build_mel_tables(uint32_t n_mels, float f_min, float f_max, MelTables *t)
             if (w[k] != 0.0f) { if (lo < 0) lo = k; hi = k + 1; }
         }
         if (lo < 0) { lo = 0; hi = 0; }
-        if (off + (uint32_t)(hi - lo) > sizeof(t->w) / sizeof(float)) return false;
-        t->lo[m] = (uint16_t)lo; t->cnt[m] = (uint16_t)(hi - lo); t->off[m] = (uint16_t)off;
-        for (int k = lo; k < hi; ++k) t->w[off++] = w[k] * 0.25f;    // pbuf holds 4 |X|^2
+        los[m] = lo;
+        for (int k = lo; k < hi; ++k) wts[m].push_back(w[k] * 0.25f);    // pbuf holds 4 |X|^2
     }
-    t->n_w = (uint16_t)off; t->n_mels = (uint16_t)n_mels;
+    // quads of adjacent filters share a trip count; weights interleaved per step: [a0..a3][b0..b3][c0..c3][d0..d3]
+    const uint32_t cap16 = sizeof(t->w) / sizeof(float) / 16;
+    const uint32_t n_quads = (n_mels + 3) / 4;
+    uint32_t off16 = 0;
+    std::vector<uint32_t> cost(n_quads, 0);
+    uint32_t total = 0;
+    for (uint32_t qd = 0; qd < n_quads; ++qd) {
+        size_t longest = 0;
+        for (uint32_t u = 0; u < 4; ++u)
+            if (4 * qd + u < n_mels) longest = std::max(longest, wts[4 * qd + u].size());
+        const uint32_t c4 = (uint32_t)((longest + 3) / 4);
+        if (off16 + c4 > cap16) return false;
+        MelQuad &Q = t->quad[qd];
+        Q.c4 = (uint16_t)c4; Q.off16 = (uint16_t)off16;
+        for (uint32_t u = 0; u < 4; ++u) {
+            const uint32_t m = 4 * qd + u;
+            if (m >= n_mels) { Q.lo[u] = 0; continue; }                   // all-zero weights
+            // the padded reads must stay inside the power buffer (PB_ROWS rows): start earlier with zero weights in front
+            const int excess = los[m] + 4 * (int)c4 - PB_ROWS;
+            if (excess > 0) {
+                if (excess > los[m]) return false;
+                wts[m].insert(wts[m].begin(), (size_t)excess, 0.0f);
+                los[m] -= excess;
+                if (wts[m].size() > 4 * (size_t)c4) return false;
+            }
+            Q.lo[u] = (uint16_t)los[m];
+            for (size_t k = 0; k < wts[m].size(); ++k) t->w[16 * (off16 + k / 4) + 4 * u + (k & 3)] = wts[m][k];
+        }
+        off16 += c4;
+        cost[qd] = 40u * c4 + 30u;
+        total += cost[qd];
+    }
+    t->n_w = (uint16_t)(16 * off16); t->n_mels = (uint16_t)n_mels;
+    // split the filter quads over the mel warps by cost (greedy prefix split)
+    uint32_t q = 0, acc = 0;
+    t->quad_begin[0] = 0;
+    for (int j = 1; j < MEL_WARPS; ++j) {
+        const uint32_t target = (uint32_t)(((uint64_t)total * (uint64_t)j) / MEL_WARPS);
+        while (q < n_quads && acc + cost[q] / 2 < target) acc += cost[q++];
+        t->quad_begin[j] = (uint16_t)q;
+    }
+    t->quad_begin[MEL_WARPS] = (uint16_t)n_quads;
     return true;
 }
 

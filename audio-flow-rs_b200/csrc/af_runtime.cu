@@ -165,6 +165,16 @@ AF_API int af_device_count(int *count)
 
 AF_API uint64_t af_kernel_launch_count(void) { return g_launches.load(); }
 
+AF_API int af_debug_pipe_stats(uint64_t out[32])
+{
+    if (!out) return fail(AF_ERR_INVALID, "null output");
+    unsigned long long tmp[32];
+    AF_CUDA(cudaDeviceSynchronize());
+    AF_CUDA(fused_pipe_stats(tmp));
+    for (int i = 0; i < 32; ++i) out[i] = tmp[i];
+    return AF_OK;
+}
+
 AF_API int af_init(int device)
 {
     std::lock_guard<std::mutex> lk(g_ctx.mu);
@@ -682,7 +692,8 @@ int build_sub(af_batch *b, SubBatch &sb, const void *slot_in_base)
         d.frac = hs.table ? hs.table->d : nullptr;
         {   // does the raw input of one step fit the shared-memory stage of the fused kernel?
             const uint64_t bps = hs.desc.format == AF_FMT_I16 ? 2 : 4;
-            const uint64_t frames = hs.mode == RS_PASSTHROUGH ? (uint64_t)YLEN : ((uint64_t)YLEN * hs.p + hs.q - 1) / hs.q;
+            // (a step is staged in two fills of at most HALF_SPLIT outputs each)
+            const uint64_t frames = hs.mode == RS_PASSTHROUGH ? (uint64_t)HALF_SPLIT : ((uint64_t)HALF_SPLIT * hs.p + hs.q - 1) / hs.q;
             d.staged = hs.desc.channels <= 2 && (frames + 8) * hs.desc.channels * bps + 32 <= (uint64_t)STAGE_BYTES;
         }
         d.tile_begin = (uint32_t)sb.h_tiles.size();
@@ -724,7 +735,7 @@ int run_sub(af_batch *b, SubBatch &sb, float *pcm, uint64_t pcm_stride, float *l
         P.log_floor = cfg.log_floor;
         P.log_scale = cfg.log10 ? 0.30102999566398120f : 0.69314718055994531f;   // log10(2) : ln(2)
         P.use_stage = g_ctx.variant == "sync" ? 0u : 1u;
-        const int n_ctas = (int)std::min<size_t>(sb.h_tiles.size(), (size_t)g_ctx.sm_count * 2);
+        const int n_ctas = (int)std::min<size_t>(sb.h_tiles.size(), (size_t)g_ctx.sm_count);   // one persistent CTA per SM
         AF_CUDA(launch_fused(P, n_ctas, st));
         count_launch();
     }
@@ -1276,7 +1287,7 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
             P.log_scale = cfg.log10 ? 0.30102999566398120f : 0.69314718055994531f;
             P.use_stage = g_ctx.variant == "sync" ? 0u : 1u;
             if (P.n_mels || P.do_energy) {
-                AF_CUDA(launch_fused(P, (int)std::min<size_t>(S, (size_t)g_ctx.sm_count * 2), st));
+                AF_CUDA(launch_fused(P, (int)std::min<size_t>(S, (size_t)g_ctx.sm_count), st));
                 count_launch(2);
             }
         } else {

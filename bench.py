@@ -325,6 +325,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="auto")
+    ap.add_argument("--pipe-stats", action="store_true",
+                    help="print the fused kernel's per-role wait cycles (needs AF_GPU_LIB=.../libaudioflow_gpu_stats.so)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
                     help="cfg2 is the contract line; cfg3/4/5 are the other BASELINE.json configs (extra reports)")
     args = ap.parse_args()
@@ -406,8 +408,21 @@ def main():
             ms = float(t.item())
         return ms, launches, sampler.summary()
 
+    if args.pipe_stats:
+        buf = (C.c_uint64 * 32)()
+        af._check(af.load_library().af_debug_pipe_stats(buf))          # clear what the warm-up accumulated
     ms, launches, clocks = timed(batch, outs, args.steps)
     ms_per_step = ms / args.steps
+    if args.pipe_stats:
+        af._check(af.load_library().af_debug_pipe_stats(buf))
+        names = {"fft": ("wait y_full", "wait p_empty"), "mel": ("wait p_full",),
+                 "vad": ("wait stage_empty", "wait y_full", "issue_fill"),
+                 "resample": ("wait y_empty", "wait stage_full", "tile setup", "carry+sync", "resample loops")}
+        for r, (role, waits) in enumerate(names.items()):
+            tot = max(int(buf[8 * r]), 1)
+            print(f"[pipe-stats] {role:9s} warp-cycles {tot:.3e}  " +
+                  "  ".join(f"{w}: {100.0 * int(buf[8 * r + 1 + i]) / tot:5.1f}%" for i, w in enumerate(waits) if w != "-"),
+                  file=sys.stderr)
     value = world * audio_s_per_step_rank / (ms_per_step * 1e-3)
 
     # the same step with the VAD on (energies fused into the kernel + sequential scan kernel)

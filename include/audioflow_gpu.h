@@ -51,6 +51,10 @@ AF_API int af_device_count(int *count);
 AF_API const char *af_version(void);
 /* Number of kernels this library has launched since af_init (bench.py's gpu_launches). */
 AF_API uint64_t af_kernel_launch_count(void);
+/* Debugging aid: cycles the fused kernel's warp roles spent waiting on each pipeline barrier since the last
+ * call ([role][total, t0 .. t6], roles FFT / mel / VAD / resample).  All zero unless the library
+ * was built with `make STATS=1`. */
+AF_API int af_debug_pipe_stats(uint64_t out[32]);
 
 /* pinned host memory for the host-buffer entry points (optional but much faster) */
 AF_API int af_host_alloc(void **ptr, size_t bytes);
