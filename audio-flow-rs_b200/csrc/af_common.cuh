@@ -27,11 +27,11 @@ constexpr int HALF_SPLIT = 2688;             // a step's raw input is staged in 
 constexpr int TILE_FRAMES = 128;             // frames per tile (work unit of one CTA)
 constexpr int TILE_SAMPLES = TILE_FRAMES * HOP;   // 20480
 constexpr int FFT_WARPS = 16;                // warps 0..15: window + FFT + power, one frame per half-warp
-constexpr int MEL_WARPS = 4;                 // warps 16..19: mel projection + log, lane = frame
+constexpr int MEL_WARPS = 5;                 // warps 16..22: mel projection + log, lane = frame
 constexpr int MEL_WARP0 = FFT_WARPS;
-constexpr int VAD_WARP = MEL_WARP0 + MEL_WARPS;   // warp 20: stage fills (TMA bulk copies) + sequential frame energies
-constexpr int RS_WARP0 = VAD_WARP + 1;       // warps 21..27: downmix + resample + PCM write-out
-constexpr int RS_WARPS = 7;
+constexpr int VAD_WARP = MEL_WARP0 + MEL_WARPS;   // warp 23: stage fills (TMA bulk copies) + sequential frame energies
+constexpr int RS_WARP0 = VAD_WARP + 1;       // warps 24..27: downmix + resample + PCM write-out
+constexpr int RS_WARPS = 6;
 constexpr int RS_THREADS = RS_WARPS * 32;
 constexpr int FUSED_WARPS = RS_WARP0 + RS_WARPS;  // 28
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;   // 896
@@ -41,11 +41,20 @@ constexpr int FUSED_THREADS = FUSED_WARPS * 32;   // 896
 __host__ __device__ constexpr int ypad(int i) { return i + 4 * (i >> 5); }
 constexpr int YBUF_FLOATS = ((ypad(YLEN + 32) + 31) / 32) * 32;
 
-constexpr int SCR_ROW = 18;                  // complex per transposed row (16 + 2 pad -> LDS.128 conflict free)
-constexpr int SCR_FLOATS_PER_FRAME = 16 * SCR_ROW * 2;   // 576 floats = 2304 B
-constexpr int PB_ROW = SF + 1;               // floats per power row: 32 frames + 1 pad (conflict-free column stores)
-constexpr int PB_ROWS = NBIN + 3;            // 3 zero rows behind bin 256 for the 4-padded mel weights
-constexpr int PBUF_FLOATS = PB_ROWS * PB_ROW;
+// transpose scratch of one FFT warp (two frames): element (half h, row k1, column c) at k1 * 36 + 16 h + c, so the two
+// half-warps store to disjoint bank halves and the row reads (LDS.128) are conflict free; the real and the
+// imaginary parts go through the same scratch in turn
+constexpr int SCR_ROW = 36;
+constexpr int SCR_FLOATS_PER_WARP = 16 * SCR_ROW;        // 576 floats = 2304 B
+// power buffer of one step: one row of PB_ROW floats per frame (bins 0..256, then zeros that the 4-padded mel
+// weights may touch), read by the mel warps with LDS.128 (lane = row).  Frame q = 2 w + h of FFT warp w sits in row
+// pb_row(q): the two frames of a warp are 16 banks apart (conflict-free column stores) and eight consecutive rows
+// start in distinct 16-byte bank groups (conflict-free LDS.128), because PB_ROW / 4 is odd.
+constexpr int PB_ROW = 260;
+constexpr int PB_COLS = PB_ROW;              // bins a padded weight quadruple may read: [0, PB_COLS)
+constexpr int PBUF_FLOATS = SF * PB_ROW;
+__host__ __device__ constexpr int pb_row(int q) { return ((q >> 1) & 3) + 8 * (q >> 3) + 4 * (q & 1); }
+__host__ __device__ constexpr int pb_frame(int row) { return 2 * ((row & 3) + 4 * (row >> 3)) + ((row >> 2) & 1); }
 constexpr int STAGE_BYTES = 32384;           // one TMA-staged half step of raw input (2688 outputs x 3 x 4 B + halo), two of them
 
 // formats / flags (mirror include/audioflow_gpu.h)
@@ -82,7 +91,7 @@ struct TileDev {
 // [a0..a3][b0..b3][c0..c3][d0..d3] per step so that four warp-uniform LDS.128 feed sixteen FMAs.  The quads are
 // split over the MEL_WARPS warps by weight count.
 struct MelQuad {
-    uint16_t lo[4];          // first bin read for each of the four filters (padded reads stay below PB_ROWS)
+    uint16_t lo[4];          // first bin read for each of the four filters: a multiple of 4, lo + 4 c4 <= PB_COLS
     uint16_t c4;             // number of weight quadruples per filter
     uint16_t off16;          // offset of the quad's weights in w, in units of 16 floats
     uint16_t pad_[2];
@@ -92,8 +101,7 @@ struct MelTables {
     uint16_t n_w;
     uint16_t n_mels;
     uint16_t quad_begin[MEL_WARPS + 1];   // mel warp j owns filter quads [quad_begin[j], quad_begin[j + 1])
-    uint16_t pad_[1];
-    float w[1280];
+    alignas(16) float w[1536];
 };
 static_assert(sizeof(MelQuad) == 16, "MelQuad is read with one LDS.128");
 static_assert(offsetof(MelTables, w) % 16 == 0, "mel weights must be 16-byte aligned");

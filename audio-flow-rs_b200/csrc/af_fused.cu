@@ -2,15 +2,15 @@
 // roles that run concurrently on different steps (32 frames) of the CTA's tiles and hand buffers to
 // each other through mbarriers -- there is no CTA-wide barrier after start-up:
 //
-//   warp 20      "V"  issues the TMA bulk copies (cp.async.bulk + mbarrier complete_tx) that stage the raw
+//   warp 23      "V"  issues the TMA bulk copies (cp.async.bulk + mbarrier complete_tx) that stage the raw
 //                     interleaved input of each half step in shared memory, two fills ahead; then K4's
 //                     energy part: one bit-exact 400-term sequential mean-square chain per lane (= frame)
-//   warps 21-27  "R"  K1: downmix + cubic (rubato FastFixedIn) resample from the stage into the padded
+//   warps 24-27  "R"  K1: downmix + cubic (rubato FastFixedIn) resample from the stage into the padded
 //                     16 kHz step buffer (double buffered), PCM written to HBM straight from registers
 //   warps 0-15   "F"  K2: Hann window + 512-point real FFT (packed 256-point complex, 16 x 16 in registers,
 //                     one half-warp per frame, transposed through shared memory, Hermitian split by
 //                     shuffles), power into pbuf[bin][frame]
-//   warps 16-19  "M"  K3: sparse banded mel projection + log, lane = frame, warp-uniform weight quads
+//   warps 16-22  "M"  K3: sparse banded mel projection + log, lane = frame, warp-uniform weight quads
 //
 // Replaces capture.rs:30-42, resampler.rs:71-93/132-166 (+ rubato) and the O(len) part of
 // vad.rs:157-168; the STFT/mel stages are spec-defined.  The sequential EMA/state
@@ -23,8 +23,8 @@ namespace af {
 struct __align__(128) FusedSmem {
     unsigned char stage[2][STAGE_BYTES];             // raw interleaved input of the two halves of a step (bulk-copy targets)
     float ybuf[2][YBUF_FLOATS];                      // padded 16 kHz samples of two consecutive steps
-    float scr[SF * SCR_FLOATS_PER_FRAME];            // per half-warp transpose scratch
-    float pbuf[PBUF_FLOATS];                         // 4*|X[k]|^2, [bin][frame]
+    float scr[FFT_WARPS * SCR_FLOATS_PER_WARP];      // per FFT warp transpose scratch
+    float pbuf[2][PBUF_FLOATS];                      // 4*|X[k]|^2, [pb_row(frame)][bin], two consecutive steps
     float2 tw1[16 * 16];                             // exp(-2 pi i l k1 / 256)
     float2 tw2[128];                                 // exp(-2 pi i k / 512)
     float window[416];                               // periodic Hann, zero beyond 400
@@ -32,7 +32,7 @@ struct __align__(128) FusedSmem {
     // pipeline barriers (mbarriers): full = data ready for the consumer, empty = buffer may be overwritten
     unsigned long long stage_full[2], stage_empty[2];
     unsigned long long y_full[2], y_empty[2];
-    unsigned long long p_full, p_empty;
+    unsigned long long p_full[2], p_empty[2];
     // metadata of the fill held by stage[h], written by the issuing thread before its arrive
     unsigned long long st_lo[2], st_hi[2];           // interleaved element range [lo, hi) held by the stage
     uint32_t st_interior[2];                         // 1: every tap of the half step is inside the stage and the stream;
@@ -63,18 +63,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, u
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
 {
-    // try_wait suspends for a short hardware-defined time; back off between polls so that waiting warps do not
-    // take issue slots from the working ones
+    // try_wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint
+    // expires), so waiting warps do not take issue slots from the working ones
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
         "WAIT_%=:\n\t"
-        "nanosleep.u32 40;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@!p bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(1000000u)
         : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
@@ -509,39 +506,48 @@ __device__ __forceinline__ void fft_load(const float *__restrict__ ybuf, const f
     for (int n1 = 13; n1 < 16; ++n1) { xr[n1] = 0.0f; xi[n1] = 0.0f; }
 }
 
-// the two 16-point passes of the packed 256-point transform; leaves Z[l + 16 k2] in slot(k2)
+// the two 16-point passes of the packed 256-point transform; leaves Z[l + 16 k2] in slot(k2).  The 16 x 16
+// transpose between them goes through the half-warp's scratch twice, real parts first, then imaginary parts.
 __device__ __forceinline__ void fft_passes(const float2 *__restrict__ tw1, float *__restrict__ scr, int l, float (&xr)[16],
                                            float (&xi)[16])
 {
-    // pass 1: 16-point FFT over n1 (this lane is n2 = l), twiddle W256^(l k1), transposed store
+    // pass 1: 16-point FFT over n1 (this lane is n2 = l), twiddle W256^(l k1)
     fft16<true>(xr, xi);
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) {
-        float ar = xr[fft16_slot(k1)], ai = xi[fft16_slot(k1)];
-        if (k1 > 0) {
-            const float2 w = tw1[k1 * 16 + l];
-            AF_CMUL(ar, ai, w.x, w.y);
-        }
-        *reinterpret_cast<float2 *>(scr + (k1 * SCR_ROW + l) * 2) = make_float2(ar, ai);
+    for (int k1 = 1; k1 < 16; ++k1) {
+        const float2 w = tw1[k1 * 16 + l];
+        AF_CMUL(xr[fft16_slot(k1)], xi[fft16_slot(k1)], w.x, w.y);
     }
-    __syncwarp();
-    // pass 2: this lane is k1 = l; read its row (all n2), 16-point FFT over n2
+    // transposed store / load: this lane becomes k1 = l and reads its row (all n2)
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const float4 v = *reinterpret_cast<const float4 *>(scr + (l * SCR_ROW + 2 * u) * 2);
-        xr[2 * u] = v.x; xi[2 * u] = v.y; xr[2 * u + 1] = v.z; xi[2 * u + 1] = v.w;
+    for (int k1 = 0; k1 < 16; ++k1) scr[k1 * SCR_ROW + l] = xr[fft16_slot(k1)];
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float4 v = *reinterpret_cast<const float4 *>(scr + l * SCR_ROW + 4 * u);
+        xr[4 * u] = v.x; xr[4 * u + 1] = v.y; xr[4 * u + 2] = v.z; xr[4 * u + 3] = v.w;
     }
     __syncwarp();
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) scr[k1 * SCR_ROW + l] = xi[fft16_slot(k1)];
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float4 v = *reinterpret_cast<const float4 *>(scr + l * SCR_ROW + 4 * u);
+        xi[4 * u] = v.x; xi[4 * u + 1] = v.y; xi[4 * u + 2] = v.z; xi[4 * u + 3] = v.w;
+    }
+    __syncwarp();
+    // pass 2: 16-point FFT over n2
     fft16<false>(xr, xi);
 }
 
-// Hermitian split + power -> pbuf[bin][q].  Pair k = l + 16 r with 256 - k, which lives in lane (16 - l) & 15 at
+// Hermitian split + power -> row pb_row(q) of pbuf.  Pair k = l + 16 r with 256 - k, which lives in lane (16 - l) & 15 at
 // k2 = 15 - r (lane 0 pairs with itself at k2 = (16 - r) & 15).
 __device__ __forceinline__ void fft_power(float *__restrict__ pbuf, const float2 *__restrict__ tw2, int q, int l, int lane,
                                           const float (&xr)[16], const float (&xi)[16])
 {
     const int src = ((16 - l) & 15) | (lane & 16);
-    float *pb = pbuf + q;
+    float *pb = pbuf + pb_row(q) * PB_ROW;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const float zr = xr[fft16_slot(r)], zi = xi[fft16_slot(r)];
@@ -556,12 +562,12 @@ __device__ __forceinline__ void fft_power(float *__restrict__ pbuf, const float2
         const float ti = w.x * o2i + w.y * o2r;
         const float ar = e2r + tr, ai = e2i + ti;      // 2 X[k]
         const float br = e2r - tr, bi = e2i - ti;      // 2 conj(X[256-k])
-        pb[k * PB_ROW] = ar * ar + ai * ai;
-        pb[(256 - k) * PB_ROW] = br * br + bi * bi;
+        pb[k] = ar * ar + ai * ai;
+        pb[256 - k] = br * br + bi * bi;
     }
     if (l == 0) {                                       // k = 128 pairs with itself
         const float zr = xr[fft16_slot(8)], zi = xi[fft16_slot(8)];
-        pb[128 * PB_ROW] = 4.0f * (zr * zr + zi * zi);
+        pb[128] = 4.0f * (zr * zr + zi * zi);
     }
 }
 
@@ -599,7 +605,7 @@ __device__ __forceinline__ void role_fft(FusedSmem &sm, const FusedParams &P, in
 {
     const int l = lane & 15, half = lane >> 4;
     const int q = warp * 2 + half;                      // this half-warp's frame inside the step
-    float *scr = sm.scr + q * SCR_FLOATS_PER_FRAME;
+    float *scr = sm.scr + warp * SCR_FLOATS_PER_WARP + 16 * half;
     const bool on = P.n_mels != 0;
     uint32_t it = 0;
     AF_STATS_DECL
@@ -616,9 +622,9 @@ __device__ __forceinline__ void role_fft(FusedSmem &sm, const FusedParams &P, in
             if (work) fft_load(sm.ybuf[b], sm.window, q, l, xr, xi);
             warp_arrive(&sm.y_empty[b], lane);                  // the step buffer is no longer needed by this warp
             if (work) fft_passes(sm.tw1, scr, l, xr, xi);
-            AF_WAIT(&sm.p_empty, (it & 1u) ^ 1u, 1);             // the mel warps are done with the previous step's power
-            if (work) fft_power(sm.pbuf, sm.tw2, q, l, lane, xr, xi);
-            warp_arrive(&sm.p_full, lane);
+            AF_WAIT(&sm.p_empty[b], ((it >> 1) & 1u) ^ 1u, 1);   // the mel warps are done with this power buffer
+            if (work) fft_power(sm.pbuf[b], sm.tw2, q, l, lane, xr, xi);
+            warp_arrive(&sm.p_full[b], lane);
         }
     }
     AF_STATS_FLUSH(0, lane);
@@ -639,31 +645,36 @@ __device__ __forceinline__ void role_mel(FusedSmem &sm, const FusedParams &P, in
         for (uint32_t g = 0; g < t.n_steps; ++g, ++it) {
             const uint32_t f0 = t.f_tile0 + g * SF;
             const int n_valid = f0 < n_frames ? (int)min((uint32_t)SF, n_frames - f0) : 0;
-            AF_WAIT(&sm.p_full, it & 1u, 0);
+            const int b = (int)(it & 1u);
+            AF_WAIT(&sm.p_full[b], (it >> 1) & 1u, 0);
             if (M && lm_row && n_valid > 0) {
-                const bool valid = lane < n_valid;
-                float *dst = lm_row + (uint64_t)(f0 + lane) * M;
-                const float *pcol = sm.pbuf + lane;
+                const int fr = pb_frame(lane);                          // frame held by power row `lane`
+                const bool valid = fr < n_valid;
+                float *dst = lm_row + (uint64_t)(f0 + fr) * M;
+                const float *prow = sm.pbuf[b] + lane * PB_ROW;
                 for (int qd = q0; qd < q1; ++qd) {
                     // four adjacent filters at a time: eight independent FMA chains, weights by warp-uniform LDS.128
                     const uint4 dq = *reinterpret_cast<const uint4 *>(&sm.mel.quad[qd]);
                     const int c4 = (int)(dq.z & 0xffffu);
                     const float4 *w4 = reinterpret_cast<const float4 *>(sm.mel.w) + 4 * (dq.z >> 16);
-                    const float *pa = pcol + (dq.x & 0xffffu) * PB_ROW, *pb = pcol + (dq.x >> 16) * PB_ROW;
-                    const float *pc = pcol + (dq.y & 0xffffu) * PB_ROW, *pd = pcol + (dq.y >> 16) * PB_ROW;
+                    const float4 *pa = reinterpret_cast<const float4 *>(prow + (dq.x & 0xffffu));
+                    const float4 *pb = reinterpret_cast<const float4 *>(prow + (dq.x >> 16));
+                    const float4 *pc = reinterpret_cast<const float4 *>(prow + (dq.y & 0xffffu));
+                    const float4 *pd = reinterpret_cast<const float4 *>(prow + (dq.y >> 16));
                     float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f, c0 = 0.0f, c1 = 0.0f, d0 = 0.0f, d1 = 0.0f;
 #pragma unroll 1
                     for (int j = 0; j < c4; ++j) {
                         const float4 wa = w4[0], wb = w4[1], wc = w4[2], wd = w4[3];
-                        a0 = fmaf(wa.x, pa[0], a0); a1 = fmaf(wa.y, pa[PB_ROW], a1);
-                        b0 = fmaf(wb.x, pb[0], b0); b1 = fmaf(wb.y, pb[PB_ROW], b1);
-                        c0 = fmaf(wc.x, pc[0], c0); c1 = fmaf(wc.y, pc[PB_ROW], c1);
-                        d0 = fmaf(wd.x, pd[0], d0); d1 = fmaf(wd.y, pd[PB_ROW], d1);
-                        a0 = fmaf(wa.z, pa[2 * PB_ROW], a0); a1 = fmaf(wa.w, pa[3 * PB_ROW], a1);
-                        b0 = fmaf(wb.z, pb[2 * PB_ROW], b0); b1 = fmaf(wb.w, pb[3 * PB_ROW], b1);
-                        c0 = fmaf(wc.z, pc[2 * PB_ROW], c0); c1 = fmaf(wc.w, pc[3 * PB_ROW], c1);
-                        d0 = fmaf(wd.z, pd[2 * PB_ROW], d0); d1 = fmaf(wd.w, pd[3 * PB_ROW], d1);
-                        w4 += 4; pa += 4 * PB_ROW; pb += 4 * PB_ROW; pc += 4 * PB_ROW; pd += 4 * PB_ROW;
+                        const float4 xa = pa[j], xb = pb[j], xc = pc[j], xd = pd[j];
+                        a0 = fmaf(wa.x, xa.x, a0); a1 = fmaf(wa.y, xa.y, a1);
+                        b0 = fmaf(wb.x, xb.x, b0); b1 = fmaf(wb.y, xb.y, b1);
+                        c0 = fmaf(wc.x, xc.x, c0); c1 = fmaf(wc.y, xc.y, c1);
+                        d0 = fmaf(wd.x, xd.x, d0); d1 = fmaf(wd.y, xd.y, d1);
+                        a0 = fmaf(wa.z, xa.z, a0); a1 = fmaf(wa.w, xa.w, a1);
+                        b0 = fmaf(wb.z, xb.z, b0); b1 = fmaf(wb.w, xb.w, b1);
+                        c0 = fmaf(wc.z, xc.z, c0); c1 = fmaf(wc.w, xc.w, c1);
+                        d0 = fmaf(wd.z, xd.z, d0); d1 = fmaf(wd.w, xd.w, d1);
+                        w4 += 4;
                     }
                     float o[4];
                     o[0] = __log2f(fmaxf(a0 + a1, log_floor)) * log_mul;
@@ -680,7 +691,7 @@ __device__ __forceinline__ void role_mel(FusedSmem &sm, const FusedParams &P, in
                     }
                 }
             }
-            warp_arrive(&sm.p_empty, lane);
+            warp_arrive(&sm.p_empty[b], lane);
         }
     }
     AF_STATS_FLUSH(1, lane);
@@ -837,7 +848,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
             uint32_t *md = reinterpret_cast<uint32_t *>(&sm.mel);
             for (int i = tid; i < (int)(sizeof(MelTables) / 4); i += FUSED_THREADS) md[i] = ms[i];
         }
-        for (int i = tid; i < PBUF_FLOATS; i += FUSED_THREADS) sm.pbuf[i] = 0.0f;   // incl. the zero rows behind bin 256
+        for (int i = tid; i < 2 * PBUF_FLOATS; i += FUSED_THREADS) sm.pbuf[0][i] = 0.0f;
     }
     if (tid == 0) {
         for (int h = 0; h < 2; ++h) {
@@ -846,8 +857,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
             mbar_init(&sm.y_full[h], RS_WARPS);
             mbar_init(&sm.y_empty[h], FFT_WARPS + 1);
         }
-        mbar_init(&sm.p_full, FFT_WARPS);
-        mbar_init(&sm.p_empty, MEL_WARPS);
+        for (int h = 0; h < 2; ++h) {
+            mbar_init(&sm.p_full[h], FFT_WARPS);
+            mbar_init(&sm.p_empty[h], MEL_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();

@@ -94,6 +94,11 @@ bool build_mel_tables(uint32_t n_mels, float f_min, float f_max, MelTables *t)
         los[m] = lo;
         for (int k = lo; k < hi; ++k) wts[m].push_back(w[k] * 0.25f);    // pbuf holds 4 |X|^2
     }
+    // every filter starts on a multiple of four bins (the mel warps read the power rows with LDS.128): zeros in front
+    for (uint32_t m = 0; m < n_mels; ++m) {
+        const int shift = los[m] & 3;
+        if (shift) { wts[m].insert(wts[m].begin(), (size_t)shift, 0.0f); los[m] -= shift; }
+    }
     // quads of adjacent filters share a trip count; weights interleaved per step: [a0..a3][b0..b3][c0..c3][d0..d3]
     const uint32_t cap16 = sizeof(t->w) / sizeof(float) / 16;
     const uint32_t n_quads = (n_mels + 3) / 4;
@@ -111,9 +116,10 @@ bool build_mel_tables(uint32_t n_mels, float f_min, float f_max, MelTables *t)
         for (uint32_t u = 0; u < 4; ++u) {
             const uint32_t m = 4 * qd + u;
             if (m >= n_mels) { Q.lo[u] = 0; continue; }                   // all-zero weights
-            // the padded reads must stay inside the power buffer (PB_ROWS rows): start earlier with zero weights in front
-            const int excess = los[m] + 4 * (int)c4 - PB_ROWS;
+            // the padded reads must stay inside the power row (PB_COLS floats): start earlier with zero weights in front
+            int excess = los[m] + 4 * (int)c4 - PB_COLS;
             if (excess > 0) {
+                excess = (excess + 3) & ~3;
                 if (excess > los[m]) return false;
                 wts[m].insert(wts[m].begin(), (size_t)excess, 0.0f);
                 los[m] -= excess;
@@ -123,7 +129,7 @@ bool build_mel_tables(uint32_t n_mels, float f_min, float f_max, MelTables *t)
             for (size_t k = 0; k < wts[m].size(); ++k) t->w[16 * (off16 + k / 4) + 4 * u + (k & 3)] = wts[m][k];
         }
         off16 += c4;
-        cost[qd] = 40u * c4 + 30u;
+        cost[qd] = 31u * c4 + 30u;
         total += cost[qd];
     }
     t->n_w = (uint16_t)(16 * off16); t->n_mels = (uint16_t)n_mels;
