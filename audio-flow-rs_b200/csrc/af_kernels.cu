@@ -4,6 +4,8 @@
 #include "af_device.cuh"
 #include "af_launch.h"
 
+#include <cmath>
+
 namespace af {
 
 // ---- AudioFrame::to_mono (capture.rs:30-42) on a device buffer ----
@@ -233,9 +235,230 @@ __global__ void af_vad_scan_kernel(const ScanJob J)
     if (J.final_out) J.final_out[s] = v;
 }
 
+// ---- the same scan, parallel inside a stream: one CTA per stream -------------------------------------------
+// The EMA is the only floating-point recurrence.  It is cut into chunks of SCAN_CHUNK frames; every chunk but the
+// first of a block starts `warm` frames early from 0 and must arrive at its first frame with EXACTLY (bit for bit)
+// the value the previous chunk ended with -- the influence of the unknown start decays as (1 - alpha)^warm, far
+// below one ulp for the warm-up lengths chosen by the host.  Each boundary is verified; a block with a mismatch
+// is recomputed sequentially by one thread, so the result never depends on the speculation.  The decisions
+// (one bit per frame) then drive the state machine: one thread walks the bit words run by run and records
+// the machine state at every word boundary, after which every thread expands its own words into state bytes.
+constexpr uint32_t SCAN_CHUNK = 128;                 // frames per EMA chunk (4 bit words)
+constexpr uint32_t SCAN_BLOCK = 8192;                // frames per block of a long stream (64 chunks, 256 words)
+constexpr uint32_t SCAN_THREADS = 128;
+
+struct EmitMask {          // collects the states of one word as two bit masks (Speech, Ending)
+    uint32_t speech = 0, ending = 0;
+    __device__ __forceinline__ void run(uint32_t j, uint32_t count, uint32_t v)
+    {
+        if (count == 0 || v == 0u) return;
+        const uint32_t m = (count >= 32u ? 0xffffffffu : ((1u << count) - 1u)) << j;
+        if (v == 1u) speech |= m; else ending |= m;
+    }
+};
+struct EmitNone {
+    __device__ __forceinline__ void run(uint32_t, uint32_t, uint32_t) {}
+};
+
+// vad_machine_word with a pluggable sink; j counts from the start of the word
+template <class Emit>
+__device__ __forceinline__ void vad_machine_word_t(VadMachine &m, uint32_t bits, uint32_t n, Emit &em, uint32_t timeout,
+                                                   uint32_t min_speech)
+{
+    uint32_t j = 0;
+    while (j < n) {
+        const uint32_t rem = bits >> j;
+        if (m.st == 0u) {
+            if (rem == 0u) { em.run(j, n - j, 0u); j = n; break; }
+            const uint32_t z = (uint32_t)__ffs((int)rem) - 1u;
+            em.run(j, z, 0u);
+            m.st = 1u; m.spk = 1u; m.sil = 0u;
+            em.run(j + z, 1u, 1u);
+            j += z + 1u;
+        } else if (m.st == 1u) {
+            if (rem & 1u) {
+                uint32_t r = (~rem == 0u) ? 32u : (uint32_t)__ffs((int)~rem) - 1u;
+                r = min(r, n - j);
+                m.spk += r; m.sil = 0u;
+                em.run(j, r, 1u);
+                j += r;
+            } else {
+                uint32_t r = rem ? (uint32_t)__ffs((int)rem) - 1u : 32u;
+                r = min(r, n - j);
+                const uint32_t need = timeout > m.sil ? timeout - m.sil : 1u;
+                if (r < need) {
+                    m.sil += r;
+                    em.run(j, r, 1u);
+                    j += r;
+                } else {
+                    em.run(j, need - 1u, 1u);
+                    m.sil += need;
+                    m.st = m.spk >= min_speech ? 2u : 0u;
+                    m.spk = 0u;
+                    em.run(j + need - 1u, 1u, m.st);
+                    j += need;
+                }
+            }
+        } else {
+            m.st = 0u; m.sil = 0u;
+            em.run(j, 1u, 0u);
+            j += 1u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const ScanJob J, uint32_t warm)
+{
+    __shared__ uint32_t s_bits[SCAN_BLOCK / 32];
+    __shared__ uint32_t s_entry[SCAN_BLOCK / 32][3];
+    __shared__ float s_spec[SCAN_BLOCK / SCAN_CHUNK], s_end[SCAN_BLOCK / SCAN_CHUNK];
+    __shared__ int s_bad;
+    const uint32_t s = blockIdx.x, tid = threadIdx.x;
+    const uint32_t T = J.n_frames ? J.n_frames[s] : J.n_frames_all;
+    const float *e = J.energy + (uint64_t)s * J.energy_stride;
+    uint8_t *out = J.states ? J.states + (uint64_t)s * J.states_stride : nullptr;
+    VadState v;
+    if (J.state_io) v = J.state_io[s];
+    else { v.smoothed = 0.0f; v.state = 0; v.silence_frames = 0; v.speech_frames = 0; }
+    const VadParams prm = J.prm;
+    const float alpha = prm.alpha, beta = __fsub_rn(1.0f, prm.alpha), e_min = prm.e_min;
+    const bool use_smoothed = alpha > 0.0f;
+    const uint32_t timeout = (uint32_t)prm.silence_timeout, minsp = (uint32_t)prm.min_speech;
+    // (the host only launches this kernel when every counter fits 32 bits with room to spare)
+    float carry_s = v.smoothed;
+    VadMachine carry_m{(uint32_t)v.state, (uint32_t)v.silence_frames, (uint32_t)v.speech_frames};
+    const bool aligned_out = out && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+
+    for (uint32_t b0 = 0; b0 < T; b0 += SCAN_BLOCK) {
+        const uint32_t n = min(SCAN_BLOCK, T - b0);
+        const uint32_t n_chunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK, n_words = (n + 31) / 32;
+        if (tid == 0) s_bad = 0;
+        // ---- phase 1: EMA chunks (speculative start) -> decision bits ----
+        for (uint32_t c = tid; c < n_chunks; c += SCAN_THREADS) {
+            const uint32_t f_begin = b0 + c * SCAN_CHUNK, f_end = min(f_begin + SCAN_CHUNK, b0 + n);
+            float sm;
+            if (c == 0) sm = carry_s;
+            else {
+                // warm-up: from 0 (or, reaching the start of the stream, from the true initial value)
+                uint32_t w0;
+                if (f_begin >= warm) { w0 = f_begin - warm; sm = 0.0f; }
+                else { w0 = 0; sm = v.smoothed; }
+                for (uint32_t f = w0; f < f_begin; ++f) sm = __fadd_rn(__fmul_rn(alpha, e[f]), __fmul_rn(beta, sm));
+                s_spec[c] = sm;
+            }
+            for (uint32_t f = f_begin; f < f_end; f += 32) {
+                const uint32_t m = min(32u, f_end - f);
+                uint32_t bits = 0;
+                for (uint32_t j = 0; j < m; ++j) {
+                    const float ev = e[f + j];
+                    sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
+                    bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
+                }
+                s_bits[(f - b0) >> 5] = bits;
+            }
+            s_end[c] = sm;
+        }
+        __syncthreads();
+        // ---- verify every boundary bit for bit ----
+        for (uint32_t c = 1 + tid; c < n_chunks; c += SCAN_THREADS)
+            if (__float_as_uint(s_spec[c]) != __float_as_uint(s_end[c - 1])) s_bad = 1;
+        __syncthreads();
+        if (s_bad) {                                      // (rare) redo the block strictly sequentially
+            if (tid == 0) {
+                float sm = carry_s;
+                for (uint32_t w = 0; w < n_words; ++w) {
+                    const uint32_t m = min(32u, n - w * 32);
+                    uint32_t bits = 0;
+                    for (uint32_t j = 0; j < m; ++j) {
+                        const float ev = e[b0 + w * 32 + j];
+                        sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
+                        bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
+                    }
+                    s_bits[w] = bits;
+                }
+                s_end[n_chunks - 1] = sm;
+            }
+            __syncthreads();
+        }
+        // ---- phase 2: one thread walks the words, recording the machine state at every word boundary ----
+        if (tid == 0) {
+            VadMachine m = carry_m;
+            EmitNone none;
+            for (uint32_t w = 0; w < n_words; ++w) {
+                s_entry[w][0] = m.st; s_entry[w][1] = m.sil; s_entry[w][2] = m.spk;
+                vad_machine_word_t(m, s_bits[w], min(32u, n - w * 32), none, timeout, minsp);
+            }
+            carry_m = m;
+        }
+        __syncthreads();
+        // ---- phase 3: every thread expands its words into state bytes ----
+        if (out) {
+            for (uint32_t w = tid; w < n_words; w += SCAN_THREADS) {
+                VadMachine m{s_entry[w][0], s_entry[w][1], s_entry[w][2]};
+                EmitMask em;
+                const uint32_t m_n = min(32u, n - w * 32);
+                vad_machine_word_t(m, s_bits[w], m_n, em, timeout, minsp);
+                uint32_t by[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t sp = ((em.speech >> (4 * k)) & 0xfu) * 0x00204081u & 0x01010101u;
+                    const uint32_t en = ((em.ending >> (4 * k)) & 0xfu) * 0x00204081u & 0x01010101u;
+                    by[k] = sp + 2u * en;
+                }
+                uint8_t *dst = out + b0 + w * 32;
+                if (m_n == 32u && aligned_out) {
+                    reinterpret_cast<uint4 *>(dst)[0] = make_uint4(by[0], by[1], by[2], by[3]);
+                    reinterpret_cast<uint4 *>(dst)[1] = make_uint4(by[4], by[5], by[6], by[7]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        for (uint32_t i = 0; i < 4; ++i)
+                            if (4u * k + i < m_n) dst[4 * k + i] = (uint8_t)(by[k] >> (8 * i));
+                }
+            }
+        }
+        // carries of the next block: the exact EMA value and the machine after the last word
+        const float next_s = s_end[n_chunks - 1];
+        VadMachine next_m = carry_m;
+        if (tid != 0) {
+            // recompute the end-of-block machine from the last word's entry (cheap, avoids another broadcast)
+            next_m = VadMachine{s_entry[n_words - 1][0], s_entry[n_words - 1][1], s_entry[n_words - 1][2]};
+            EmitNone none;
+            vad_machine_word_t(next_m, s_bits[n_words - 1], min(32u, n - (n_words - 1) * 32), none, timeout, minsp);
+        }
+        __syncthreads();                                  // everyone has read s_bits / s_entry / s_end
+        carry_s = next_s; carry_m = next_m;
+    }
+    if (tid == 0) {
+        v.smoothed = carry_s; v.state = (int)carry_m.st; v.silence_frames = carry_m.sil; v.speech_frames = carry_m.spk;
+        if (J.state_io) J.state_io[s] = v;
+        if (J.final_out) J.final_out[s] = v;
+    }
+}
+
+// warm-up length (frames) after which an EMA started from 0 agrees bit for bit with the true one in practice:
+// (1 - alpha)^warm < 2^-56 (24 bits of mantissa + 32 bits of dynamic range); 0 = no parallel scan for this alpha
+static uint32_t scan_warmup(float alpha)
+{
+    if (!(alpha >= 0.0f) || alpha > 1.0f) return 0;       // outside the EMA's sensible range: sequential kernel
+    if (alpha == 0.0f || alpha == 1.0f) return 32;        // no memory at all (alpha = 0 never uses the smoothed value)
+    const double w = 56.0 / -std::log2(1.0 - (double)alpha);
+    if (!(w <= 512.0)) return 0;
+    return ((uint32_t)std::ceil(w) + 31u) & ~31u;
+}
+
 cudaError_t launch_vad_scan(const ScanJob &job, cudaStream_t st)
 {
     if (job.n_streams == 0) return cudaSuccess;
+    const uint32_t warm = scan_warmup(job.prm.alpha);
+    // the parallel kernel keeps its counters in 32 bits and starts every stream from a fresh detector or from a
+    // state the caller vouches for; streams resumed from a saved state may hold 64-bit counters -> sequential kernel
+    const bool small = job.prm.silence_timeout < 0x40000000ull && job.prm.min_speech < 0x40000000ull &&
+                       job.n_frames_all < 0x40000000u;
+    if (warm != 0 && small && job.state_io == nullptr) {
+        af_vad_scan_par_kernel<<<job.n_streams, SCAN_THREADS, 0, st>>>(job, warm);
+        return cudaGetLastError();
+    }
     const int threads = 32;                       // one warp per CTA: spread the chains over the SMs
     af_vad_scan_kernel<<<(job.n_streams + threads - 1) / threads, threads, 0, st>>>(job);
     return cudaGetLastError();

@@ -420,3 +420,29 @@ def test_linearity_of_resampler(af):
     p = af.Pipeline(af.pipeline_config(n_mels=0, vad_enable=False))
     a, b = p.run_host([(x, 44100, 1), (x * np.float32(0.25), 44100, 1)])
     assert_bit_equal(a["pcm"] * np.float32(0.25), b["pcm"], "linearity")
+
+
+@pytest.mark.parametrize("alpha", [0.0, 0.05, 0.3, 0.9, 1.0])
+def test_parallel_vad_scan_long_streams(af, orc, alpha):
+    """The chunk-parallel EMA / state-machine scan (af_vad_scan_par_kernel) against the sequential oracle
+    (vad.rs:97-154): streams longer than one scan block (8192 frames), every smoothing regime (alpha = 0 uses the
+    raw energy, 0.05 falls back to the sequential kernel, 1 has no memory), plus a loud-then-nearly-silent stream
+    whose EMA takes longer than the speculative warm-up to forget its past -- the verified fallback must give
+    the same bits."""
+    rng = np.random.default_rng(7)
+    n1 = 16000 * 100                                                        # 100 s @ 16 kHz -> 9998 frames, two blocks
+    seg = rng.integers(0, 4, n1 // 4000 + 1).repeat(4000)[:n1]
+    amp = np.choose(seg, [1e-3, 0.02, 0.08, 0.3]).astype(np.float32)
+    x1 = (amp * rng.standard_normal(n1).astype(np.float32)).clip(-1, 1)
+    x2 = np.concatenate([0.9 * np.ones(16000 * 3, np.float32),              # loud, then 1e-6: the EMA decays for > 100 frames
+                         1e-6 * rng.standard_normal(16000 * 60).astype(np.float32)])
+    x3 = x1[:16000 * 7 + 123]
+    vc = af.VadConfig(threshold_db=-50.0, smoothing_factor=alpha, silence_timeout_frames=15, min_speech_frames=3)
+    oc = orc.default_vad_config()
+    oc.threshold_db, oc.smoothing_factor, oc.silence_timeout_frames, oc.min_speech_frames = -50.0, alpha, 15, 3
+    streams = [(x1, 16000, 1), (x2, 16000, 1), (x3, 16000, 1)]
+    got = af.Pipeline(af.pipeline_config(n_mels=0, vad=vc)).run_host(streams)
+    for i, ((x, rate, ch), g) in enumerate(zip(streams, got)):
+        ref = orc.pipeline_stream(x, ch, rate, None, oc, 400, 160, "f32")
+        assert len(ref["vad"]) == 1 + (len(x) - 400) // 160
+        _check_stream(g, ref, f"alpha {alpha} stream {i}")
