@@ -379,40 +379,61 @@ __device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, int h, c
         }
         return;
     }
-    uint32_t dk = a / q, rem = a - dk * q;
-    int k = sm.tile_k + (int)dk - 1 - f_lo;
-    const uint32_t inc_k = sm.inc_k, inc_rem = sm.inc_rem;
-    const float inv_q = 1.0f / (float)q;
-    const float *__restrict__ frac_tab = s.frac + out.base;
-    // batches of four outputs: the table fractions (L2) and the 16 taps are loaded before the first cubic
-    while (i < i_hi) {
-        int o[4], ii[4];
-        float frac[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            ii[u] = i + u * RS_THREADS;
-            o[u] = k;
-            frac[u] = (float)rem * inv_q;                                 // RS_EXACT: q is a power of two, exact
-            if (mode == RS_TABLE && ii[u] < i_hi) {
-                const float ft = __ldg(frac_tab + ii[u]);
-                o[u] += __float2int_rn(frac[u] - ft);                     // -1 when the f64 recurrence sits just below an integer
-                frac[u] = ft;
+    // general rational step (44.1 kHz -> 16 kHz: 441/160 with table fractions; 8 / 24 / 32 kHz: exact fractions):
+    // four CONSECUTIVE outputs per thread -- one 16-byte load of the table fractions, exact integer positions
+    // advanced by p/q per output, 16 taps, four cubics, one 16-byte store to the step buffer and to HBM
+    {
+        constexpr int QS = 4 * RS_THREADS;
+        int i4 = (i_lo & ~31) + 4 * rtid;
+        if (i4 < i_lo) i4 += QS;
+        const uint32_t p = s.p;
+        const uint32_t a0 = sm.tile_rem + (tile_off + (uint32_t)i4) * p;
+        uint32_t dk = a0 / q, rem = a0 - dk * q;
+        int k = sm.tile_k + (int)dk - 1 - f_lo;                  // tap y0 of output i4, relative to the staged frames
+        const uint32_t pk = p / q, pr = p - pk * q;              // per output
+        const uint32_t sweep = (uint32_t)(QS - 3) * p;           // from the quad's last output to the next sweep's first
+        const uint32_t sk = sweep / q, sr = sweep - sk * q;
+        const float inv_q = 1.0f / (float)q;
+        const float4 *__restrict__ frac4 = reinterpret_cast<const float4 *>(s.frac + out.base + i4);
+        const int lim4 = out.pcm ? (int)min((uint32_t)YLEN, out.wr_end - min(out.wr_end, out.base)) - 4 : -(1 << 30);
+        float *yq = out.yb + ypad(i4);
+        float *pq = out.pcm + out.base + i4;
+        for (; i4 < i_hi; i4 += QS) {
+            float ft[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (mode == RS_TABLE) {
+                const float4 t = __ldg(frac4);
+                ft[0] = t.x; ft[1] = t.y; ft[2] = t.z; ft[3] = t.w;
             }
-            k += (int)inc_k;
-            rem += inc_rem;
+            float y[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int o = k;
+                float frac = (float)rem * inv_q;                 // RS_EXACT: q is a power of two, exact
+                if (mode == RS_TABLE) {
+                    o += __float2int_rn(frac - ft[u]);           // -1 when the f64 recurrence sits just below an integer
+                    frac = ft[u];
+                }
+                const float y0 = tap_fast<KIND>(srcp, o), y1 = tap_fast<KIND>(srcp, o + 1);
+                const float y2 = tap_fast<KIND>(srcp, o + 2), y3 = tap_fast<KIND>(srcp, o + 3);
+                y[u] = interp_cubic(frac, y0, y1, y2, y3);
+                if (u < 3) {
+                    k += (int)pk; rem += pr;
+                    if (rem >= q) { rem -= q; k += 1; }
+                }
+            }
+            const float4 yv = make_float4(y[0], y[1], y[2], y[3]);
+            *reinterpret_cast<float4 *>(yq) = yv;
+            if (i4 <= lim4) __stcs(reinterpret_cast<float4 *>(pq), yv);
+            else {
+                const int left = lim4 + 4 - i4;
+                if (left > 0) __stcs(pq, yv.x);
+                if (left > 1) __stcs(pq + 1, yv.y);
+                if (left > 2) __stcs(pq + 2, yv.z);
+            }
+            k += (int)sk; rem += sr;
             if (rem >= q) { rem -= q; k += 1; }
+            frac4 += QS / 4; yq += ypad(QS); pq += QS;
         }
-        float y[4][4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int ou = ii[u] < i_hi ? o[u] : o[0];                    // keep the unused lanes of a partial batch in range
-#pragma unroll
-            for (int t = 0; t < 4; ++t) y[u][t] = tap_fast<KIND>(srcp, ou + t);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (ii[u] < i_hi) out.put(ii[u], interp_cubic(frac[u], y[u][0], y[u][1], y[u][2], y[u][3]));
-        i += 4 * RS_THREADS;
     }
 }
 

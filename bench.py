@@ -95,6 +95,26 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+
+def pipe_stats_clear():
+    import audioflow as af
+    buf = (C.c_uint64 * 32)()
+    af._check(af.load_library().af_debug_pipe_stats(buf))
+
+
+def pipe_stats_print():
+    """Per-role wait / work cycles of the fused kernel since the last clear (library built with `make STATS=1`)."""
+    import audioflow as af
+    buf = (C.c_uint64 * 32)()
+    af._check(af.load_library().af_debug_pipe_stats(buf))
+    names = {"fft": ("wait y_full", "wait p_empty"), "mel": ("wait p_full",),
+             "vad": ("wait stage_empty", "wait y_full", "issue_fill"),
+             "resample": ("wait y_empty", "wait stage_full", "tile setup", "carry+sync", "resample loops")}
+    for r, (role, waits) in enumerate(names.items()):
+        tot = max(int(buf[8 * r]), 1)
+        print(f"[pipe-stats] {role:9s} warp-cycles {tot:.3e}  " +
+              "  ".join(f"{w}: {100.0 * int(buf[8 * r + 1 + i]) / tot:5.1f}%" for i, w in enumerate(waits)), file=sys.stderr)
+
 # ---------------------------------------------------------------------------------------------
 # CPU legs (the oracle port of the reference path, all host threads)
 # ---------------------------------------------------------------------------------------------
@@ -240,7 +260,11 @@ def run_other_workload(args, af, synth, torch, dist, dev, rank, world, local_ran
             if world > 1:
                 shard.gather_vad(vad, nfr)           # VAD states + frame counts of every stream to every rank (NCCL)
 
+        if args.pipe_stats:
+            pipe_stats_clear()
         ms0 = time_steps(step_nogather, args.steps, args.warmup)
+        if args.pipe_stats:
+            pipe_stats_print()
         ms1 = time_steps(step_gather, args.steps, args.warmup)
         audio_s = S_total * SECONDS
         alg = sum((r * 4 + 16000 * 4 + 100 * N_MELS * 4 + 100) * SECONDS for r in rates)
@@ -409,20 +433,11 @@ def main():
         return ms, launches, sampler.summary()
 
     if args.pipe_stats:
-        buf = (C.c_uint64 * 32)()
-        af._check(af.load_library().af_debug_pipe_stats(buf))          # clear what the warm-up accumulated
+        pipe_stats_clear()
     ms, launches, clocks = timed(batch, outs, args.steps)
     ms_per_step = ms / args.steps
     if args.pipe_stats:
-        af._check(af.load_library().af_debug_pipe_stats(buf))
-        names = {"fft": ("wait y_full", "wait p_empty"), "mel": ("wait p_full",),
-                 "vad": ("wait stage_empty", "wait y_full", "issue_fill"),
-                 "resample": ("wait y_empty", "wait stage_full", "tile setup", "carry+sync", "resample loops")}
-        for r, (role, waits) in enumerate(names.items()):
-            tot = max(int(buf[8 * r]), 1)
-            print(f"[pipe-stats] {role:9s} warp-cycles {tot:.3e}  " +
-                  "  ".join(f"{w}: {100.0 * int(buf[8 * r + 1 + i]) / tot:5.1f}%" for i, w in enumerate(waits) if w != "-"),
-                  file=sys.stderr)
+        pipe_stats_print()
     value = world * audio_s_per_step_rank / (ms_per_step * 1e-3)
 
     # the same step with the VAD on (energies fused into the kernel + sequential scan kernel)
