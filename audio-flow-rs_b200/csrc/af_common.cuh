@@ -109,8 +109,12 @@ static_assert(offsetof(MelTables, w) % 16 == 0, "mel weights must be 16-byte ali
 // constant tables of the FFT, filled by the host in f64 and rounded once
 struct FftTables {
     float window[416];       // periodic Hann, zero beyond 400
-    float2 tw1[16 * 16];     // tw1[k1 * 16 + l] = exp(-2 pi i l k1 / 256)
-    float2 tw2[128];         // tw2[k] = exp(-2 pi i k / 512)
+    // twiddles in the layout of the packed (f32x2) FFT: one float4 = (re_a, re_b, im_a, im_b) for the two points a
+    // pack holds.  tw1p[p * 16 + l]: exp(-2 pi i l k1 / 256) for the points in slots 2p, 2p+1 of the 16-point
+    // transform (slot s holds k1 = (s >> 2) + 4 (s & 3)); tw2p[r * 16 + l]: exp(-2 pi i k / 512), k = l + 16 r and
+    // k = l + 16 (r + 4).
+    float4 tw1p[8 * 16];
+    float4 tw2p[4 * 16];
 };
 
 struct VadParams {

@@ -185,6 +185,110 @@ __device__ __forceinline__ void fft16(float (&xr)[16], float (&xi)[16])
     fft4(xr[8], xi[8], xr[9], xi[9], xr[10], xi[10], xr[11], xi[11]);
     fft4(xr[12], xi[12], xr[13], xi[13], xr[14], xi[14], xr[15], xi[15]);
 }
+
+// ------------------------------------------------------------------------------------------
+// Packed variant: sm_100a executes add / mul / fma on register PAIRS (PTX .f32x2, SASS FADD2 / FMUL2 /
+// FFMA2): one issue slot for two independent fp32 operations.  A "pack" holds the same component (real or
+// imaginary) of two different points, so the +-i rotations of the butterflies stay plain adds between the real
+// and the imaginary packs -- no data movement.  Points 2k and 2k+1 of the 16-point transform share pack k.
+// ------------------------------------------------------------------------------------------
+struct f2 { float x, y; };
+__device__ __forceinline__ f2 mk2(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b)
+{
+    f2 r;
+    asm("{.reg .b64 a, b, c; mov.b64 a, {%2, %3}; mov.b64 b, {%4, %5}; add.rn.f32x2 c, a, b; mov.b64 {%0, %1}, c;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b)
+{
+    f2 r;
+    asm("{.reg .b64 a, b, c; mov.b64 a, {%2, %3}; mov.b64 b, {%4, %5}; sub.rn.f32x2 c, a, b; mov.b64 {%0, %1}, c;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b)
+{
+    f2 r;
+    asm("{.reg .b64 a, b, c; mov.b64 a, {%2, %3}; mov.b64 b, {%4, %5}; mul.rn.f32x2 c, a, b; mov.b64 {%0, %1}, c;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c)
+{
+    f2 r;
+    asm("{.reg .b64 a, b, c, d; mov.b64 a, {%2, %3}; mov.b64 b, {%4, %5}; mov.b64 c, {%6, %7}; fma.rn.f32x2 d, a, b, c; "
+        "mov.b64 {%0, %1}, d;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+// (r + i i) (c + i s) on both halves
+__device__ __forceinline__ void cmul2(f2 &r, f2 &i, f2 c, f2 s)
+{
+    const f2 tr = fma2(mk2(-i.x, -i.y), s, mul2(r, c));
+    const f2 ti = fma2(r, s, mul2(i, c));
+    r = tr; i = ti;
+}
+// radix-4 butterfly on two transforms at once (the halves of the packs), in place; output c lands where input c was
+__device__ __forceinline__ void fft4p(f2 &r0, f2 &i0, f2 &r1, f2 &i1, f2 &r2, f2 &i2, f2 &r3, f2 &i3)
+{
+    const f2 t0r = add2(r0, r2), t0i = add2(i0, i2), t1r = sub2(r0, r2), t1i = sub2(i0, i2);
+    const f2 t2r = add2(r1, r3), t2i = add2(i1, i3), t3r = sub2(r1, r3), t3i = sub2(i1, i3);
+    r0 = add2(t0r, t2r); i0 = add2(t0i, t2i);
+    r2 = sub2(t0r, t2r); i2 = sub2(t0i, t2i);
+    r1 = add2(t1r, t3i); i1 = sub2(t1i, t3r);     // t1 - i t3
+    r3 = sub2(t1r, t3i); i3 = add2(t1i, t3r);     // t1 + i t3
+}
+// the same with input 3 known to be zero in both halves
+__device__ __forceinline__ void fft4p_z3(f2 &r0, f2 &i0, f2 &r1, f2 &i1, f2 &r2, f2 &i2, f2 &r3, f2 &i3)
+{
+    const f2 t0r = add2(r0, r2), t0i = add2(i0, i2), t1r = sub2(r0, r2), t1i = sub2(i0, i2);
+    const f2 ur = r1, ui = i1;
+    r0 = add2(t0r, ur); i0 = add2(t0i, ui);
+    r2 = sub2(t0r, ur); i2 = sub2(t0i, ui);
+    r1 = add2(t1r, ui); i1 = sub2(t1i, ur);
+    r3 = sub2(t1r, ui); i3 = add2(t1i, ur);
+}
+// radix-4 butterfly over the four slots held by two packs A = (s0, s1), B = (s2, s3): first level packed, second scalar
+__device__ __forceinline__ void fft4h(f2 &Ar, f2 &Ai, f2 &Br, f2 &Bi)
+{
+    const f2 Tr = add2(Ar, Br), Ti = add2(Ai, Bi);     // (t0, t2)
+    const f2 Ur = sub2(Ar, Br), Ui = sub2(Ai, Bi);     // (t1, t3)
+    Ar.x = Tr.x + Tr.y; Ai.x = Ti.x + Ti.y;            // z0
+    Br.x = Tr.x - Tr.y; Bi.x = Ti.x - Ti.y;            // z2
+    Ar.y = Ur.x + Ui.y; Ai.y = Ui.x - Ur.y;            // z1 = t1 - i t3
+    Br.y = Ur.x - Ui.y; Bi.y = Ui.x + Ur.y;            // z3 = t1 + i t3
+}
+// W16^(b c) for the packs 2c + j (b = 2j, 2j+1), c = 1..3: {cos pair, sin pair} per pack.  In constant memory so
+// that the packed multiplies take them as uniform-register operands instead of rebuilding them in registers.
+static __constant__ float2 c_fft16_tw[12] = {
+    {1.0f, 0.92387953251128674f},                 {0.0f, -0.38268343236508977f},                  // c = 1, b = 0, 1
+    {0.70710678118654752f, 0.38268343236508977f}, {-0.70710678118654752f, -0.92387953251128674f}, // c = 1, b = 2, 3
+    {1.0f, 0.70710678118654752f},                 {0.0f, -0.70710678118654752f},                  // c = 2, b = 0, 1
+    {0.0f, -0.70710678118654752f},                {-1.0f, -0.70710678118654752f},                 // c = 2, b = 2, 3
+    {1.0f, 0.38268343236508977f},                 {0.0f, -0.92387953251128674f},                  // c = 3, b = 0, 1
+    {-0.70710678118654752f, -0.92387953251128674f}, {-0.70710678118654752f, 0.38268343236508977f} // c = 3, b = 2, 3
+};
+__device__ __forceinline__ f2 fft16_tw(int i) { return mk2(c_fft16_tw[i].x, c_fft16_tw[i].y); }
+
+// In-register 16-point FFT on packs: point n in pack n >> 1, half n & 1 (same 4 x 4 decomposition and the same
+// output placement as fft16: X[k] in slot 4 (k & 3) + (k >> 2), slot s = pack s >> 1, half s & 1).
+// PRUNED: points 13, 14, 15 are known zeros.
+template <bool PRUNED>
+__device__ __forceinline__ void fft16p(f2 (&R)[8], f2 (&I)[8])
+{
+    // stage A: transforms b = (0, 1) live in packs 0, 2, 4, 6; b = (2, 3) in packs 1, 3, 5, 7
+    fft4p(R[0], I[0], R[2], I[2], R[4], I[4], R[6], I[6]);
+    if (PRUNED) fft4p_z3(R[1], I[1], R[3], I[3], R[5], I[5], R[7], I[7]);
+    else fft4p(R[1], I[1], R[3], I[3], R[5], I[5], R[7], I[7]);
+    // slot 4c + b (pack 2c + (b >> 1)) times W16^(b c)
+#pragma unroll
+    for (int p = 2; p < 8; ++p) cmul2(R[p], I[p], fft16_tw(2 * p - 4), fft16_tw(2 * p - 3));
+    // stage B: the four slots of each c
+#pragma unroll
+    for (int c = 0; c < 4; ++c) fft4h(R[2 * c], I[2 * c], R[2 * c + 1], I[2 * c + 1]);
+}
 __host__ __device__ constexpr int fft16_slot(int k) { return 4 * (k & 3) + (k >> 2); }
 
 }  // namespace af

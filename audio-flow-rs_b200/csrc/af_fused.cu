@@ -25,9 +25,8 @@ struct __align__(128) FusedSmem {
     float ybuf[2][YBUF_FLOATS];                      // padded 16 kHz samples of two consecutive steps
     float scr[FFT_WARPS * SCR_FLOATS_PER_WARP];      // per FFT warp transpose scratch
     float pbuf[2][PBUF_FLOATS];                      // 4*|X[k]|^2, [pb_row(frame)][bin], two consecutive steps
-    float2 tw1[16 * 16];                             // exp(-2 pi i l k1 / 256)
-    float2 tw2[128];                                 // exp(-2 pi i k / 512)
-    float window[416];                               // periodic Hann, zero beyond 400
+    uint32_t tmem_base;                              // TMEM allocation holding the FFT constants (see tmem_* above)
+    uint32_t pad_[3];
     MelTables mel;
     // pipeline barriers (mbarriers): full = data ready for the consumer, empty = buffer may be overwritten
     unsigned long long stage_full[2], stage_empty[2];
@@ -119,6 +118,69 @@ __device__ unsigned long long g_pipe_stats[32];
 
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// ---- tensor memory (TMEM) as a per-lane constant store -------------------------------------------------------
+// The FFT warps need 74 per-lane constants per frame pair (window samples, pass-1 and Hermitian-split twiddles).
+// They do not fit the register budget, and as shared-memory loads they were 37 of ~236 LSU wavefronts per frame
+// on an LSU-bound kernel.  TMEM is lane-addressed (thread t of a warp reads lane 32 (warp % 4) + t), has its own
+// datapath (tcgen05.ld, no LSU / shared-memory bandwidth) and is otherwise idle here: the constants are written
+// once per CTA into 74 columns of each lane quarter and fetched from there just before use.
+constexpr uint32_t TMEM_COLS = 128;          // allocation granularity: power of two >= 74
+constexpr uint32_t TM_TW1 = 0;               // 32 columns: tw1p[p] = columns 4p .. 4p+3  (re_a, re_b, im_a, im_b)
+constexpr uint32_t TM_TW2 = 32;              // 16 columns: tw2p[r] = columns 4r .. 4r+3
+constexpr uint32_t TM_WIN = 48;              // 26 columns: window[32 n1 + 2 l + e] at 2 n1 + e
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(TMEM_COLS) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float4 v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float4 tmem_ld4(uint32_t taddr)
+{
+    float4 v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(taddr));
+    return v;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ float2 tmem_ld2(uint32_t taddr)
+{
+    float2 v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(taddr));
+    return v;
+}
+// the loaded registers may be used only after the wait: passing them through the statement as in/out operands
+// keeps the compiler from scheduling a use above it
+__device__ __forceinline__ void tmem_wait_ld(float4 &a)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w)::"memory");
+}
+__device__ __forceinline__ void tmem_wait_ld(float4 &a, float4 &b)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w), "+f"(b.x), "+f"(b.y), "+f"(b.z), "+f"(b.w)::"memory");
+}
+__device__ __forceinline__ void tmem_wait_ld(float (&v)[8])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])::"memory");
+}
+__device__ __forceinline__ void tmem_wait_ld(float2 &a) { asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(a.x), "+f"(a.y)::"memory"); }
 
 // ---- geometry of a tile, recomputed by every role from the same tables ----
 struct TileGeo {
@@ -502,92 +564,111 @@ __device__ __forceinline__ void resample_dispatch(const FusedSmem &sm, int h, co
     else resample_half<KIND>(sm, h, s, out, tile_off, i_lo, i_hi, rtid);
 }
 
-// ---- F role: one frame per half-warp ----
-// window + pack: this lane holds z[16 n1 + l] = x[32 n1 + 2 l] + i x[32 n1 + 2 l + 1] of frame q
-__device__ __forceinline__ void fft_load(const float *__restrict__ ybuf, const float *__restrict__ window, int q, int l,
-                                         float (&xr)[16], float (&xi)[16])
+// ---- F role: one frame per half-warp, packed (f32x2) arithmetic: pack k = points 2k, 2k+1 of the lane ----
+// window + pack: this lane holds z[16 n1 + l] = x[32 n1 + 2 l] + i x[32 n1 + 2 l + 1] of frame q as point n1
+__device__ __forceinline__ void fft_load(const float *__restrict__ ybuf, uint32_t tm, int q, int l, f2 (&R)[8], f2 (&I)[8])
 {
     const float *yb = ybuf + 180 * q + 2 * l;      // ypad(160 q + 32 n1 + 2 l) = 180 q + 36 n1 + 2 l
-    const float *wp = window + 2 * l;              // both half-warps read the same window words: one wavefront
+    // window samples of this lane from TMEM, in three batches so that few registers are held at a time
+    float w[8];
 #pragma unroll
-    for (int n1 = 0; n1 < 12; ++n1) {
-        const float2 v = *reinterpret_cast<const float2 *>(yb + 36 * n1);
-        const float2 w = *reinterpret_cast<const float2 *>(wp + 32 * n1);
-        xr[n1] = __fmul_rn(v.x, w.x);
-        xi[n1] = __fmul_rn(v.y, w.y);
+    for (int g = 0; g < 3; ++g) {
+        tmem_ld8(tm + TM_WIN + 8 * g, w);
+        float2 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float2 *>(yb + 36 * (4 * g + j));
+        tmem_wait_ld(w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n1 = 4 * g + j;
+            const float re = __fmul_rn(v[j].x, w[2 * j]), im = __fmul_rn(v[j].y, w[2 * j + 1]);
+            if (n1 & 1) { R[n1 >> 1].y = re; I[n1 >> 1].y = im; }
+            else { R[n1 >> 1].x = re; I[n1 >> 1].x = im; }
+        }
     }
     {
+        float2 wl = tmem_ld2(tm + TM_WIN + 24);
         float2 v = make_float2(0.0f, 0.0f);
         if (l < 8) v = *reinterpret_cast<const float2 *>(yb + 36 * 12);   // samples 384 + 2l (+1) < 400; the window is 0 beyond
-        const float2 w = *reinterpret_cast<const float2 *>(wp + 32 * 12);
-        xr[12] = __fmul_rn(v.x, w.x);
-        xi[12] = __fmul_rn(v.y, w.y);
+        tmem_wait_ld(wl);
+        R[6] = mk2(__fmul_rn(v.x, wl.x), 0.0f);
+        I[6] = mk2(__fmul_rn(v.y, wl.y), 0.0f);
     }
-#pragma unroll
-    for (int n1 = 13; n1 < 16; ++n1) { xr[n1] = 0.0f; xi[n1] = 0.0f; }
+    R[7] = mk2(0.0f, 0.0f); I[7] = mk2(0.0f, 0.0f);
 }
 
 // the two 16-point passes of the packed 256-point transform; leaves Z[l + 16 k2] in slot(k2).  The 16 x 16
-// transpose between them goes through the half-warp's scratch twice, real parts first, then imaginary parts.
-__device__ __forceinline__ void fft_passes(const float2 *__restrict__ tw1, float *__restrict__ scr, int l, float (&xr)[16],
-                                           float (&xi)[16])
+// transpose between them goes through the warp's scratch twice, real parts first, then imaginary parts.
+__device__ __forceinline__ float &slot_of(f2 (&A)[8], int s) { return (s & 1) ? A[s >> 1].y : A[s >> 1].x; }
+__device__ __forceinline__ void fft_passes(uint32_t tm, float *__restrict__ scr, int l, f2 (&R)[8], f2 (&I)[8])
 {
-    // pass 1: 16-point FFT over n1 (this lane is n2 = l), twiddle W256^(l k1)
-    fft16<true>(xr, xi);
+    // pass 1: 16-point FFT over n1 (this lane is n2 = l), twiddle W256^(l k1) on the packs
+    fft16p<true>(R, I);
 #pragma unroll
-    for (int k1 = 1; k1 < 16; ++k1) {
-        const float2 w = tw1[k1 * 16 + l];
-        AF_CMUL(xr[fft16_slot(k1)], xi[fft16_slot(k1)], w.x, w.y);
+    for (int g = 0; g < 4; ++g) {                   // two packs per TMEM round trip
+        float4 wa = tmem_ld4(tm + TM_TW1 + 8 * g), wb = tmem_ld4(tm + TM_TW1 + 8 * g + 4);
+        tmem_wait_ld(wa, wb);
+        cmul2(R[2 * g], I[2 * g], mk2(wa.x, wa.y), mk2(wa.z, wa.w));
+        cmul2(R[2 * g + 1], I[2 * g + 1], mk2(wb.x, wb.y), mk2(wb.z, wb.w));
     }
     // transposed store / load: this lane becomes k1 = l and reads its row (all n2)
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) scr[k1 * SCR_ROW + l] = xr[fft16_slot(k1)];
+    for (int k1 = 0; k1 < 16; ++k1) scr[k1 * SCR_ROW + l] = slot_of(R, fft16_slot(k1));
     __syncwarp();
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const float4 v = *reinterpret_cast<const float4 *>(scr + l * SCR_ROW + 4 * u);
-        xr[4 * u] = v.x; xr[4 * u + 1] = v.y; xr[4 * u + 2] = v.z; xr[4 * u + 3] = v.w;
+        R[2 * u] = mk2(v.x, v.y); R[2 * u + 1] = mk2(v.z, v.w);
     }
     __syncwarp();
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) scr[k1 * SCR_ROW + l] = xi[fft16_slot(k1)];
+    for (int k1 = 0; k1 < 16; ++k1) scr[k1 * SCR_ROW + l] = slot_of(I, fft16_slot(k1));
     __syncwarp();
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const float4 v = *reinterpret_cast<const float4 *>(scr + l * SCR_ROW + 4 * u);
-        xi[4 * u] = v.x; xi[4 * u + 1] = v.y; xi[4 * u + 2] = v.z; xi[4 * u + 3] = v.w;
+        I[2 * u] = mk2(v.x, v.y); I[2 * u + 1] = mk2(v.z, v.w);
     }
     __syncwarp();
     // pass 2: 16-point FFT over n2
-    fft16<false>(xr, xi);
+    fft16p<false>(R, I);
 }
 
-// Hermitian split + power -> row pb_row(q) of pbuf.  Pair k = l + 16 r with 256 - k, which lives in lane (16 - l) & 15 at
-// k2 = 15 - r (lane 0 pairs with itself at k2 = (16 - r) & 15).
-__device__ __forceinline__ void fft_power(float *__restrict__ pbuf, const float2 *__restrict__ tw2, int q, int l, int lane,
-                                          const float (&xr)[16], const float (&xi)[16])
+// Hermitian split + power -> row pb_row(q) of pbuf, two bins r and r + 4 per pack.  Z[l + 16 k2] is in slot(k2) =
+// 4 (k2 & 3) + (k2 >> 2): k2 = r and r + 4 are the two halves of pack 2 r.  Bin k = l + 16 k2 pairs with 256 - k,
+// which lives in lane (16 - l) & 15 at k2' = 15 - k2 (lane 0 pairs with itself at k2' = (16 - k2) & 15).
+__device__ __forceinline__ void fft_power(float *__restrict__ pbuf, uint32_t tm, int q, int l, int lane,
+                                          f2 (&R)[8], f2 (&I)[8])
 {
     const int src = ((16 - l) & 15) | (lane & 16);
     float *pb = pbuf + pb_row(q) * PB_ROW;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const float zr = xr[fft16_slot(r)], zi = xi[fft16_slot(r)];
-        float pr = __shfl_sync(0xffffffffu, xr[fft16_slot(15 - r)], src);
-        float pi = __shfl_sync(0xffffffffu, xi[fft16_slot(15 - r)], src);
-        if (l == 0) { pr = xr[fft16_slot((16 - r) & 15)]; pi = xi[fft16_slot((16 - r) & 15)]; }
+    for (int r = 0; r < 4; ++r) {
+        const f2 zr = R[2 * r], zi = I[2 * r];                           // k2 = r (x), r + 4 (y)
+        // partners k2' = 15 - r -> slot 4 (3 - r) + 3 = pack 7 - 2 r half y;  k2' = 11 - r -> slot 4 (3 - r) + 2 = same pack half x
+        f2 pr, pi;
+        pr.x = __shfl_sync(0xffffffffu, R[7 - 2 * r].y, src); pi.x = __shfl_sync(0xffffffffu, I[7 - 2 * r].y, src);
+        pr.y = __shfl_sync(0xffffffffu, R[7 - 2 * r].x, src); pi.y = __shfl_sync(0xffffffffu, I[7 - 2 * r].x, src);
+        if (l == 0) {                                                    // own values at k2' = (16 - k2) & 15
+            pr.x = slot_of(R, fft16_slot((16 - r) & 15)); pi.x = slot_of(I, fft16_slot((16 - r) & 15));
+            pr.y = slot_of(R, fft16_slot(12 - r));        pi.y = slot_of(I, fft16_slot(12 - r));
+        }
+        float4 w = tmem_ld4(tm + TM_TW2 + 4 * r);
+        tmem_wait_ld(w);
+        const f2 wx = mk2(w.x, w.y), wy = mk2(w.z, w.w);
+        const f2 e2r = add2(zr, pr), e2i = sub2(zi, pi);                 // 2E = Z[k] + conj(Z[256-k])
+        const f2 o2r = add2(zi, pi), o2i = sub2(pr, zr);                 // 2O = -i (Z[k] - conj(Z[256-k]))
+        const f2 tr = fma2(mk2(-wy.x, -wy.y), o2i, mul2(wx, o2r));
+        const f2 ti = fma2(wy, o2r, mul2(wx, o2i));
+        const f2 ar = add2(e2r, tr), ai = add2(e2i, ti);                 // 2 X[k]
+        const f2 br = sub2(e2r, tr), bi = sub2(e2i, ti);                 // 2 conj(X[256-k])
+        const f2 pa = fma2(ai, ai, mul2(ar, ar)), pbv = fma2(bi, bi, mul2(br, br));
         const int k = l + 16 * r;
-        const float2 w = tw2[l + 16 * r];
-        const float e2r = zr + pr, e2i = zi - pi;      // 2E = Z[k] + conj(Z[256-k])
-        const float o2r = zi + pi, o2i = pr - zr;      // 2O = -i (Z[k] - conj(Z[256-k]))
-        const float tr = w.x * o2r - w.y * o2i;
-        const float ti = w.x * o2i + w.y * o2r;
-        const float ar = e2r + tr, ai = e2i + ti;      // 2 X[k]
-        const float br = e2r - tr, bi = e2i - ti;      // 2 conj(X[256-k])
-        pb[k] = ar * ar + ai * ai;
-        pb[256 - k] = br * br + bi * bi;
+        pb[k] = pa.x; pb[k + 64] = pa.y;
+        pb[256 - k] = pbv.x; pb[192 - k] = pbv.y;
     }
-    if (l == 0) {                                       // k = 128 pairs with itself
-        const float zr = xr[fft16_slot(8)], zi = xi[fft16_slot(8)];
+    if (l == 0) {                                       // k = 128 (k2 = 8) pairs with itself
+        const float zr = slot_of(R, fft16_slot(8)), zi = slot_of(I, fft16_slot(8));
         pb[128] = 4.0f * (zr * zr + zi * zi);
     }
 }
@@ -627,6 +708,7 @@ __device__ __forceinline__ void role_fft(FusedSmem &sm, const FusedParams &P, in
     const int l = lane & 15, half = lane >> 4;
     const int q = warp * 2 + half;                      // this half-warp's frame inside the step
     float *scr = sm.scr + warp * SCR_FLOATS_PER_WARP + 16 * half;
+    const uint32_t tm = sm.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);   // this warp's lane quarter
     const bool on = P.n_mels != 0;
     uint32_t it = 0;
     AF_STATS_DECL
@@ -638,13 +720,13 @@ __device__ __forceinline__ void role_fft(FusedSmem &sm, const FusedParams &P, in
             const int n_valid = f0 < n_frames ? (int)min((uint32_t)SF, n_frames - f0) : 0;
             const bool work = on && warp * 2 < n_valid;         // warp-uniform: skip fully invalid pairs
             const int b = (int)(it & 1u);
-            float xr[16], xi[16];
+            f2 R[8], I[8];
             AF_WAIT(&sm.y_full[b], (it >> 1) & 1u, 0);
-            if (work) fft_load(sm.ybuf[b], sm.window, q, l, xr, xi);
+            if (work) fft_load(sm.ybuf[b], tm, q, l, R, I);
             warp_arrive(&sm.y_empty[b], lane);                  // the step buffer is no longer needed by this warp
-            if (work) fft_passes(sm.tw1, scr, l, xr, xi);
+            if (work) fft_passes(tm, scr, l, R, I);
             AF_WAIT(&sm.p_empty[b], ((it >> 1) & 1u) ^ 1u, 1);   // the mel warps are done with this power buffer
-            if (work) fft_power(sm.pbuf[b], sm.tw2, q, l, lane, xr, xi);
+            if (work) fft_power(sm.pbuf[b], tm, q, l, lane, R, I);
             warp_arrive(&sm.p_full[b], lane);
         }
     }
@@ -859,11 +941,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
 
     // constant tables -> shared memory, barriers (once per CTA)
     {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(P.fft->tw1);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(sm.tw1);
-        for (int i = tid; i < (int)(sizeof(sm.tw1) / 4); i += FUSED_THREADS) dst[i] = src[i];
-        for (int i = tid; i < 256; i += FUSED_THREADS) reinterpret_cast<float *>(sm.tw2)[i] = reinterpret_cast<const float *>(P.fft->tw2)[i];
-        for (int i = tid; i < 416; i += FUSED_THREADS) sm.window[i] = P.fft->window[i];
         if (P.n_mels) {
             const uint32_t *ms = reinterpret_cast<const uint32_t *>(P.mel);
             uint32_t *md = reinterpret_cast<uint32_t *>(&sm.mel);
@@ -884,13 +961,36 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (warp == 0) tmem_alloc(&sm.tmem_base);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp < 4) {
+        // warps 0..3 own the four TMEM lane quarters: thread t writes the constants of FFT lane l = t & 15 into its lane
+        const uint32_t tm = sm.tmem_base + ((uint32_t)(32 * warp) << 16);
+        const int l = lane & 15;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) tmem_st4(tm + TM_TW1 + 4 * p, P.fft->tw1p[p * 16 + l]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) tmem_st4(tm + TM_TW2 + 4 * r, P.fft->tw2p[r * 16 + l]);
+#pragma unroll
+        for (int n1 = 0; n1 < 13; ++n1) tmem_st2(tm + TM_WIN + 2 * n1, P.fft->window[32 * n1 + 2 * l], P.fft->window[32 * n1 + 2 * l + 1]);
+        tmem_wait_st();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // 896 threads x 72 registers: every role fits (or nearly fits) that budget, so no setmaxnreg rebalancing
     if (warp < FFT_WARPS) role_fft(sm, P, warp, lane);
     else if (warp < VAD_WARP) role_mel(sm, P, warp - MEL_WARP0, lane);
     else if (warp == VAD_WARP) role_vad(sm, P, lane);
     else role_resample(sm, P, tid - RS_WARP0 * 32, lane);
+
+    // every role has drained its pipeline: release the tensor memory
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(sm.tmem_base);
 }
 
 size_t fused_smem_bytes() { return sizeof(FusedSmem); }

@@ -53,15 +53,18 @@ void build_fft_tables(FftTables *t)
 {
     std::memset(t, 0, sizeof(*t));
     for (int n = 0; n < WIN; ++n) t->window[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / (double)WIN));
-    for (int k1 = 0; k1 < 16; ++k1)
+    for (int p = 0; p < 8; ++p)
         for (int l = 0; l < 16; ++l) {
-            const double a = -2.0 * M_PI * (double)(l * k1) / 256.0;
-            t->tw1[k1 * 16 + l] = make_float2((float)std::cos(a), (float)std::sin(a));
+            const int sa = 2 * p, sb = 2 * p + 1;
+            const int ka = (sa >> 2) + 4 * (sa & 3), kb = (sb >> 2) + 4 * (sb & 3);
+            const double aa = -2.0 * M_PI * (double)(l * ka) / 256.0, ab = -2.0 * M_PI * (double)(l * kb) / 256.0;
+            t->tw1p[p * 16 + l] = make_float4((float)std::cos(aa), (float)std::cos(ab), (float)std::sin(aa), (float)std::sin(ab));
         }
-    for (int k = 0; k < 128; ++k) {
-        const double a = -2.0 * M_PI * (double)k / 512.0;
-        t->tw2[k] = make_float2((float)std::cos(a), (float)std::sin(a));
-    }
+    for (int r = 0; r < 4; ++r)
+        for (int l = 0; l < 16; ++l) {
+            const double aa = -2.0 * M_PI * (double)(l + 16 * r) / 512.0, ab = -2.0 * M_PI * (double)(l + 16 * (r + 4)) / 512.0;
+            t->tw2p[r * 16 + l] = make_float4((float)std::cos(aa), (float)std::cos(ab), (float)std::sin(aa), (float)std::sin(ab));
+        }
 }
 
 static double hz_to_mel_htk(double f) { return 2595.0 * std::log10(1.0 + f / 700.0); }
