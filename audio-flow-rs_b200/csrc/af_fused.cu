@@ -20,13 +20,25 @@
 
 namespace af {
 
+// one staged half step: what the V warp needs to issue its bulk copy and what the resampler warps need to read it
+struct FillDesc {
+    const char *src;         // first staged byte in global memory
+    uint32_t bytes;          // 0: nothing staged (taps come from global memory)
+    uint32_t lo, hi;         // interleaved element range [lo, hi) held by the stage (fits 32 bits: n_in < 2^31, <= 2 channels staged)
+    uint32_t interior;       // see st_interior
+    uint32_t pad_[2];
+};
+
 struct __align__(128) FusedSmem {
     unsigned char stage[2][STAGE_BYTES];             // raw interleaved input of the two halves of a step (bulk-copy targets)
     float ybuf[2][YBUF_FLOATS];                      // padded 16 kHz samples of two consecutive steps
     float scr[FFT_WARPS * SCR_FLOATS_PER_WARP];      // per FFT warp transpose scratch
     float pbuf[2][PBUF_FLOATS];                      // 4*|X[k]|^2, [pb_row(frame)][bin], two consecutive steps
     uint32_t tmem_base;                              // TMEM allocation holding the FFT constants (see tmem_* above)
-    uint32_t pad_[3];
+    uint32_t fdesc_steps[2];                         // steps of the tiles whose fill descriptors sit in fdesc[0 / 1]
+    uint32_t pad_[1];
+    FillDesc fdesc[2][2 * (TILE_FRAMES / SF)];       // fill descriptors of the current and the next tile (resampler warps -> V warp)
+    unsigned long long desc_ready;                   // first descriptors written
     MelTables mel;
     // pipeline barriers (mbarriers): full = data ready for the consumer, empty = buffer may be overwritten
     unsigned long long stage_full[2], stage_empty[2];
@@ -72,6 +84,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         "}" ::"r"(smem_u32(bar)),
         "r"(parity), "r"(1000000u)
         : "memory");
+}
+// non-blocking phase test
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0u;
 }
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
 {
@@ -212,6 +237,7 @@ struct FillTile {
     uint32_t p, q, mode, ch, bps, staged;
     long long k0;            // floor(position) of the tile's first output
     uint32_t rem0;           // and its remainder
+    uint32_t n_steps;
 };
 __device__ __forceinline__ FillTile fill_tile(const FusedParams &P, uint32_t tile)
 {
@@ -225,6 +251,7 @@ __device__ __forceinline__ FillTile fill_tile(const FusedParams &P, uint32_t til
     f.staged = sp->staged;
     f.k0 = 0; f.rem0 = 0;
     if (f.mode != RS_PASSTHROUGH) resample_pos(f.n_tile0, f.p, f.q, &f.k0, &f.rem0);
+    f.n_steps = (min(f.n_tile0 + (uint32_t)TILE_SAMPLES, f.n_out) - f.n_tile0 + STEP_SAMPLES - 1) / STEP_SAMPLES;
     return f;
 }
 // floor(position) of output n_tile0 + d (the host guarantees (TILE_SAMPLES + YLEN) * p + q < 2^32)
@@ -234,7 +261,7 @@ __device__ __forceinline__ long long fill_pos(const FillTile &f, uint32_t d)
     const uint32_t a = f.rem0 + d * f.p;
     return f.k0 + (long long)(f.q == 1 ? a : a / f.q);
 }
-__device__ __forceinline__ void issue_fill(FusedSmem &sm, const FusedParams &P, const FillTile &f, uint32_t g, int h)
+__device__ __forceinline__ FillDesc make_fill_desc(const FusedParams &P, const FillTile &f, uint32_t g, int h)
 {
     const uint32_t ch = f.ch, bps = f.bps;
     unsigned long long lo = 0, hi = 0;
@@ -270,10 +297,17 @@ __device__ __forceinline__ void issue_fill(FusedSmem &sm, const FusedParams &P, 
             }
         }
     }
-    sm.st_lo[h] = lo; sm.st_hi[h] = hi; sm.st_interior[h] = interior;
-    if (bytes) {
-        mbar_arrive_expect_tx(&sm.stage_full[h], bytes);
-        bulk_g2s(sm.stage[h], src, bytes, &sm.stage_full[h]);
+    FillDesc d;
+    d.src = src; d.bytes = bytes; d.lo = (uint32_t)lo; d.hi = (uint32_t)hi; d.interior = interior; d.pad_[0] = d.pad_[1] = 0;
+    return d;
+}
+// issued by ONE thread; always completes one phase of stage_full[h]
+__device__ __forceinline__ void issue_fill(FusedSmem &sm, const FillDesc &d, int h)
+{
+    sm.st_lo[h] = d.lo; sm.st_hi[h] = d.hi; sm.st_interior[h] = d.interior;
+    if (d.bytes) {
+        mbar_arrive_expect_tx(&sm.stage_full[h], d.bytes);
+        bulk_g2s(sm.stage[h], d.src, d.bytes, &sm.stage_full[h]);
     } else {
         mbar_arrive(&sm.stage_full[h]);
     }
@@ -674,29 +708,31 @@ __device__ __forceinline__ void fft_power(float *__restrict__ pbuf, uint32_t tm,
 }
 
 // ---- V role, lane = frame: calculate_energy (vad.rs:157-168), strictly sequential ----
-__device__ __forceinline__ float frame_energy_smem(const float *__restrict__ ybuf, int q)
+// The squares are independent (packed multiplies, two per instruction); the additions are one dependent chain in
+// the reference's order.  `between()` runs after every 128 samples: the V warp's opportunistic fill service.
+__device__ __forceinline__ float energy_acc4(float sum, float4 v)
+{
+    const f2 a = mul2(mk2(v.x, v.y), mk2(v.x, v.y)), b = mul2(mk2(v.z, v.w), mk2(v.z, v.w));
+    sum = __fadd_rn(sum, a.x); sum = __fadd_rn(sum, a.y);
+    sum = __fadd_rn(sum, b.x); sum = __fadd_rn(sum, b.y);
+    return sum;
+}
+template <class F>
+__device__ __forceinline__ float frame_energy_smem(const float *__restrict__ ybuf, int q, F between)
 {
     const float4 *yp = reinterpret_cast<const float4 *>(ybuf) + 45 * q;   // ypad(160 q) / 4
     float sum = 0.0f;
+#pragma unroll 1
+    for (int seg = 0; seg < 3; ++seg) {
 #pragma unroll 2
-    for (int s8 = 0; s8 < 12; ++s8) {
+        for (int s8 = 4 * seg; s8 < 4 * seg + 4; ++s8) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 v = yp[9 * s8 + j];            // 8 float4 of data + 1 of padding per 32 samples
-            sum = __fadd_rn(sum, __fmul_rn(v.x, v.x));
-            sum = __fadd_rn(sum, __fmul_rn(v.y, v.y));
-            sum = __fadd_rn(sum, __fmul_rn(v.z, v.z));
-            sum = __fadd_rn(sum, __fmul_rn(v.w, v.w));
+            for (int j = 0; j < 8; ++j) sum = energy_acc4(sum, yp[9 * s8 + j]);   // 8 float4 of data + 1 of padding per 32 samples
         }
+        between();
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {                       // samples 384..399
-        const float4 v = yp[9 * 12 + j];
-        sum = __fadd_rn(sum, __fmul_rn(v.x, v.x));
-        sum = __fadd_rn(sum, __fmul_rn(v.y, v.y));
-        sum = __fadd_rn(sum, __fmul_rn(v.z, v.z));
-        sum = __fadd_rn(sum, __fmul_rn(v.w, v.w));
-    }
+    for (int j = 0; j < 4; ++j) sum = energy_acc4(sum, yp[9 * 12 + j]);           // samples 384..399
     return __fdiv_rn(sum, (float)WIN);
 }
 
@@ -802,33 +838,50 @@ __device__ __forceinline__ void role_mel(FusedSmem &sm, const FusedParams &P, in
 
 __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, int lane)
 {
-    // fills run one step ahead of the resamplers; the energies of a step are computed once its buffer is full
+    // Two cursors.  FILLS (lane 0): the bulk copy of a half step is issued as soon as the resampler warps have
+    // released its stage buffer -- blocking for the step the resamplers need next, and opportunistically (one
+    // non-blocking test between the 128-sample segments of the energy chains) for the steps after it, so that a
+    // long chain never delays a fill.  ENERGIES: the 32 frames of the previous step once its buffer is full.
     const bool chains = P.do_energy && P.energy;
+    AF_STATS_DECL
+    // fill cursor (lane 0): tile ordinal, step, half.  The descriptors (source pointer, byte count, staged range) are
+    // worked out by eight resampler threads a tile ahead, so that issuing a fill is a handful of instructions here.
+    uint32_t tile_f = blockIdx.x, ord_f = 0, g_f = 0, it_f = 0;
+    int h_f = 0;
+    bool fill_live = tile_f < P.n_tiles;
+    mbar_wait(&sm.desc_ready, 0);
+    auto issue_next = [&](bool blocking) {                  // lane 0 only
+        if (!fill_live) return;
+        if (blocking) { AF_WAIT(&sm.stage_empty[h_f], (it_f & 1u) ^ 1u, 0); }
+        else if (!mbar_test(&sm.stage_empty[h_f], (it_f & 1u) ^ 1u)) return;
+        AF_TIC
+        const FillDesc d = sm.fdesc[ord_f & 1u][2 * g_f + h_f];
+        issue_fill(sm, d, h_f);
+        if (++h_f == 2) {
+            h_f = 0; ++it_f;
+            if (++g_f == sm.fdesc_steps[ord_f & 1u]) {
+                g_f = 0; ++ord_f; tile_f += gridDim.x;
+                fill_live = tile_f < P.n_tiles;
+            }
+        }
+        AF_TOC(2)
+    };
+    auto service = [&]() {
+        if (lane == 0) issue_next(false);
+        __syncwarp();
+    };
     uint32_t it = 0;
     bool have_prev = false;
     uint32_t prev_f0 = 0, prev_nf = 0, prev_stream = 0, prev_it = 0;
-    AF_STATS_DECL
     for (uint32_t tile = blockIdx.x;; tile += gridDim.x) {
         const bool live = tile < P.n_tiles;
         TileGeo t{};
         uint32_t n_frames = 0;
-        FillTile ft{};
-        if (live) {
-            t = tile_geo(P, tile, &n_frames);
-            if (lane == 0) ft = fill_tile(P, tile);
-        }
+        if (live) t = tile_geo(P, tile, &n_frames);
         const uint32_t n_steps = live ? t.n_steps : 1u;        // one drain iteration after the last tile
         for (uint32_t g = 0; g < n_steps; ++g) {
             if (live) {
-                if (lane == 0) {
-#pragma unroll 1
-                    for (int h = 0; h < 2; ++h) {
-                        AF_WAIT(&sm.stage_empty[h], (it & 1u) ^ 1u, 0);
-                        AF_TIC
-                        issue_fill(sm, P, ft, g, h);
-                        AF_TOC(2)
-                    }
-                }
+                if (lane == 0) while (fill_live && it_f <= it) issue_next(true);   // the fills of step `it` are out
                 __syncwarp();
             }
             if (have_prev) {
@@ -836,8 +889,8 @@ __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, in
                 AF_WAIT(&sm.y_full[b], (prev_it >> 1) & 1u, 1);
                 if (chains) {
                     const int n_valid = prev_f0 < prev_nf ? (int)min((uint32_t)SF, prev_nf - prev_f0) : 0;
-                    if (lane < n_valid)
-                        P.energy[(uint64_t)prev_stream * P.energy_stride + prev_f0 + lane] = frame_energy_smem(sm.ybuf[b], lane);
+                    const float en = frame_energy_smem(sm.ybuf[b], lane, service);
+                    if (lane < n_valid) P.energy[(uint64_t)prev_stream * P.energy_stride + prev_f0 + lane] = en;
                 }
                 warp_arrive(&sm.y_empty[b], lane);
             }
@@ -860,7 +913,7 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
     AF_STATS_DECL
     // the descriptor of a tile's stream is fetched one tile ahead into registers: threads 0..15 hold one word of
     // the StreamDev each, thread 32 the exact position of the tile's first output
-    uint32_t nx_word = 0, nx_rem = 0, nx_inck = 0, nx_incr = 0;
+    uint32_t nx_word = 0, nx_rem = 0, nx_inck = 0, nx_incr = 0, nx_ord = 0;
     int nx_k = 0;
     TileGeo nx_t{};
     auto prefetch = [&](uint32_t tile) {
@@ -882,6 +935,15 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
                 nx_inck = inc / q; nx_incr = inc % q;
             }
         }
+        // eight threads work out the eight fill descriptors of that tile for the V warp (slot = tile ordinal & 1)
+        constexpr int NF = 2 * (TILE_FRAMES / SF);
+        if (rtid >= 64 && rtid < 64 + NF) {
+            const int j = rtid - 64;
+            const FillTile ft = fill_tile(P, tile);
+            sm.fdesc[nx_ord & 1u][j] = make_fill_desc(P, ft, (uint32_t)(j >> 1), j & 1);
+            if (j == 0) sm.fdesc_steps[nx_ord & 1u] = ft.n_steps;
+        }
+        ++nx_ord;
     };
     prefetch(blockIdx.x);
     for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
@@ -891,6 +953,7 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
         if (rtid < (int)(sizeof(StreamDev) / 4)) reinterpret_cast<uint32_t *>(&sm.stream)[rtid] = nx_word;
         if (rtid == 32) { sm.tile_k = nx_k; sm.tile_rem = nx_rem; sm.inc_k = nx_inck; sm.inc_rem = nx_incr; }
         named_bar_sync(1, RS_THREADS);
+        if (tile == blockIdx.x && rtid == 0) mbar_arrive(&sm.desc_ready);   // the first tile's fill descriptors are written
         prefetch(tile + gridDim.x);
         AF_TOC(2)
         const StreamDev &s = sm.stream;
@@ -898,6 +961,9 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
         if (s.channels == 1) kind = s.format == FMT_F32 ? K_F32_1 : K_I16_1;
         else if (s.channels == 2) kind = s.format == FMT_F32 ? K_F32_2 : K_I16_2;
         float *pcm_row = P.pcm ? P.pcm + (uint64_t)t.stream * P.pcm_stride : nullptr;
+        // does this tile's fast path hand out output quads to fixed owner threads (see resample_half_fast)?
+        const bool quad_tile = s.mode != RS_PASSTHROUGH && ((kind == K_F32_1 && s.q == 1 && s.p == 3) || (kind != K_GENERIC && s.q > 1));
+        bool prev_quads = false;
 
         for (uint32_t g = 0; g < t.n_steps; ++g, ++it) {
             const int b = (int)(it & 1u);
@@ -906,10 +972,20 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
             AF_WAIT(&sm.y_empty[b], ((it >> 1) & 1u) ^ 1u, 0);   // FFT and VAD warps are done with this buffer
             AF_TIC2
             if (g > 0) {
-                // the 240-sample overlap with the previous step (written by all resampler threads: sync first)
-                named_bar_sync(1, RS_THREADS);
+                // the 240-sample overlap with the previous step
                 const float *prev = sm.ybuf[b ^ 1];
-                for (int i = rtid; i < CARRY; i += RS_THREADS) out.yb[ypad(i)] = prev[ypad(STEP_SAMPLES + i)];
+                if (prev_quads) {
+                    // the quad paths give every output quad a fixed owner thread: each thread carries the quad it wrote
+                    // itself in the previous step -- no synchronisation among the resampler warps
+                    constexpr int QS = 4 * RS_THREADS;
+                    int c4 = HALF_SPLIT + 4 * rtid;
+                    c4 += ((STEP_SAMPLES - c4 + QS - 1) / QS) * QS;           // first own quad at or after STEP_SAMPLES
+                    if (c4 < YLEN)
+                        *reinterpret_cast<float4 *>(out.yb + ypad(c4 - STEP_SAMPLES)) = *reinterpret_cast<const float4 *>(prev + ypad(c4));
+                } else {
+                    named_bar_sync(1, RS_THREADS);                            // written by all resampler threads: sync first
+                    for (int i = rtid; i < CARRY; i += RS_THREADS) out.yb[ypad(i)] = prev[ypad(STEP_SAMPLES + i)];
+                }
             }
             AF_TOC(3)
 #pragma unroll 1
@@ -925,6 +1001,7 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
                 default: resample_dispatch<K_GENERIC>(sm, h, s, out, toff, i_lo, i_hi, rtid); break;
                 }
                 AF_TOC(4)
+                if (h == 1) prev_quads = quad_tile && sm.st_interior[1] != 0u;   // (read before the stage is released)
                 warp_arrive(&sm.stage_empty[h], lane);          // this warp no longer reads stage[h] or its metadata
             }
             warp_arrive(&sm.y_full[b], lane);
@@ -959,6 +1036,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
             mbar_init(&sm.p_full[h], FFT_WARPS);
             mbar_init(&sm.p_empty[h], MEL_WARPS);
         }
+        mbar_init(&sm.desc_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&sm.tmem_base);

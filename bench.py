@@ -442,7 +442,13 @@ def main():
 
     # the same step with the VAD on (energies fused into the kernel + sequential scan kernel)
     pipe_v, batch_v, outs_v, bufs_v = make(True)
+    if args.pipe_stats:
+        timed(batch_v, outs_v, 2)
+        pipe_stats_clear()
     ms_v, launches_v, _ = timed(batch_v, outs_v, max(args.steps // 2, 3))
+    if args.pipe_stats:
+        print("[pipe-stats] --- with the VAD on ---", file=sys.stderr)
+        pipe_stats_print()
     ms_v_per_step = ms_v / max(args.steps // 2, 3)
 
     # ---- roofline of the dominant kernel: with the VAD off a step IS one launch of af_fused_kernel ----
