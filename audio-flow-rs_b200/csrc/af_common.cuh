@@ -80,10 +80,33 @@ struct StreamDev {
 };
 enum : uint32_t { RS_PASSTHROUGH = 0, RS_EXACT = 1, RS_TABLE = 2 };
 
-struct TileDev {
+// one staged half step: what the V warp needs to issue its bulk copy and what the resampler warps need to read it
+struct FillDesc {
+    const char *src;         // first staged byte in global memory
+    uint32_t bytes;          // 0: nothing staged (taps come from global memory)
+    uint32_t lo, hi;         // interleaved element range [lo, hi) held by the stage (fits 32 bits: n_in < 2^31, <= 2 channels staged)
+    uint32_t interior;       // 1: every tap of the half step is inside the stage and the stream; 2: inside the stream but not
+                             // staged (unchecked global loads); 0: checked path
+    uint32_t pad_[2];
+};
+constexpr int TILE_FILLS = 2 * (TILE_FRAMES / SF);   // half steps per tile
+
+// one tile (128 frames of one stream) with everything the kernel would otherwise have to derive with 64-bit
+// divisions: planned once per batch on the host (plan_tile, af_device.cuh), or per tick by the session set-up kernel
+struct alignas(16) TileDev {
     uint32_t stream;
     uint32_t tile;           // tile index inside the stream
+    int32_t k0;              // floor(position) of the tile's first output, in input frames
+    uint32_t rem0;           // and its remainder (numerator units)
+    uint32_t n_steps;        // steps of 32 frames
+    uint32_t tile_end;       // the tile owns stream samples [tile * TILE_SAMPLES, tile_end)
+    uint32_t n_frames;       // STFT frames of the stream (copy)
+    uint32_t pad_;
+    FillDesc fill[TILE_FILLS];
+    StreamDev sdesc;         // copy of the stream's descriptor: one level of loads per tile instead of two
 };
+static_assert(sizeof(FillDesc) == 32, "a fill descriptor is fetched with two 16-byte loads");
+static_assert(sizeof(TileDev) % 16 == 0 && offsetof(TileDev, fill) % 16 == 0, "fill descriptors must be 16-byte aligned");
 
 // mel filterbank in compact form (weights already carry the 1/4 of the unscaled power).  The mel warps work
 // lane = frame and walk FOUR adjacent filters (a "quad": one 16-byte store per frame) at a time, eight

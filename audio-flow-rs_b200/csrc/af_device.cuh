@@ -67,6 +67,65 @@ __host__ __device__ __forceinline__ void resample_pos(uint64_t n, uint32_t p, ui
     *rem = (uint32_t)(num % q);
 }
 
+// Plans one tile: the exact position of its first output and the eight stage fills (two per step of 32 frames).
+// A fill covers the taps of the outputs [lo_i, hi_i) of its half step: bytes rounded out to 16, never past the
+// stream's last full 16 bytes, and only when it fits the stage; `interior` says which resampling path may run.
+__host__ __device__ inline void plan_tile(const StreamDev &s, uint32_t stream, uint32_t tile, TileDev *t)
+{
+    const uint32_t n_tile0 = tile * (uint32_t)TILE_SAMPLES;
+    const uint32_t tile_end = s.n_out - n_tile0 < (uint32_t)TILE_SAMPLES ? s.n_out : n_tile0 + (uint32_t)TILE_SAMPLES;
+    t->stream = stream; t->tile = tile;
+    long long k0 = 0; uint32_t rem0 = 0;
+    if (s.mode != RS_PASSTHROUGH) resample_pos(n_tile0, s.p, s.q, &k0, &rem0);
+    t->k0 = (int32_t)k0; t->rem0 = rem0;
+    t->n_steps = (tile_end - n_tile0 + STEP_SAMPLES - 1) / STEP_SAMPLES;
+    t->tile_end = tile_end;
+    t->n_frames = s.n_frames; t->pad_ = 0;
+    t->sdesc = s;
+    const uint32_t ch = s.channels, bps = s.format == FMT_I16 ? 2u : 4u;
+    const uint32_t left = s.n_out - n_tile0;                       // outputs from the tile start to the stream end
+    for (int j = 0; j < TILE_FILLS; ++j) {
+        const uint32_t g = (uint32_t)j >> 1;
+        const int h = j & 1;
+        FillDesc d;
+        d.src = reinterpret_cast<const char *>(s.data); d.bytes = 0; d.lo = 0; d.hi = 0; d.interior = 0; d.pad_[0] = d.pad_[1] = 0;
+        const uint32_t d_first = g * STEP_SAMPLES + (uint32_t)(h == 0 ? (g == 0 ? 0 : CARRY) : HALF_SPLIT);
+        const uint32_t d_full = g * STEP_SAMPLES + (uint32_t)(h == 0 ? HALF_SPLIT : YLEN);
+        const uint32_t d_last = d_full < left ? d_full : left;
+        if (g < t->n_steps && d_first < d_last) {
+            // floor(position) of output n_tile0 + d (the host guarantees (TILE_SAMPLES + YLEN) * p + q < 2^32)
+            long long ka, kb;
+            if (s.mode == RS_PASSTHROUGH) { ka = (long long)n_tile0 + d_first; kb = (long long)n_tile0 + d_last - 1; }
+            else {
+                ka = k0 + (long long)((rem0 + d_first * s.p) / s.q);
+                kb = k0 + (long long)((rem0 + (d_last - 1) * s.p) / s.q);
+            }
+            // interior half step: no tap (k-2 .. k+2) leaves the stream, no output beyond n_out, whole channel frames
+            const bool geom = (ka - 2 >= 0) && (kb + 3 <= (long long)s.n_in) &&
+                              ((unsigned long long)(kb + 3) * ch <= s.n_samples) && (d_last == d_full) && ch <= 2;
+            if (geom) d.interior = 2;                            // unchecked taps straight from global memory
+            long long i_lo = ka - 2, i_hi = kb + 3;
+            if (i_lo < 0) i_lo = 0;
+            if (i_hi > (long long)s.n_in) i_hi = (long long)s.n_in;
+            if (s.staged && i_lo < i_hi) {
+                unsigned long long b_lo = ((unsigned long long)i_lo * ch * bps) & ~15ull;
+                unsigned long long e_hi = (unsigned long long)i_hi * ch;
+                if (e_hi > s.n_samples) e_hi = s.n_samples;
+                unsigned long long b_hi = (e_hi * bps + 15ull) & ~15ull;
+                const unsigned long long b_end = (s.n_samples * bps) & ~15ull;   // never read past the stream's last full 16 bytes
+                if (b_hi > b_end) b_hi = b_end;
+                if (b_hi > b_lo && b_hi - b_lo <= (unsigned long long)STAGE_BYTES) {
+                    d.bytes = (uint32_t)(b_hi - b_lo);
+                    d.lo = (uint32_t)(b_lo / bps); d.hi = (uint32_t)(b_hi / bps);
+                    d.src += b_lo;
+                    if (geom && (unsigned long long)(kb + 3) * ch <= d.hi) d.interior = 1;   // ... and from the stage
+                }
+            }
+        }
+        t->fill[j] = d;
+    }
+}
+
 // One resampled sample, given the exact integer position (k, rem) and the stream tables.
 //   RS_EXACT: q is a power of two (or 1) -> the f64 recurrence of the reference is exact and
 //             frac = rem / q.

@@ -20,13 +20,11 @@
 
 namespace af {
 
-// one staged half step: what the V warp needs to issue its bulk copy and what the resampler warps need to read it
-struct FillDesc {
-    const char *src;         // first staged byte in global memory
-    uint32_t bytes;          // 0: nothing staged (taps come from global memory)
-    uint32_t lo, hi;         // interleaved element range [lo, hi) held by the stage (fits 32 bits: n_in < 2^31, <= 2 channels staged)
-    uint32_t interior;       // see st_interior
-    uint32_t pad_[2];
+struct RsTile {
+    StreamDev stream;
+    int tile_k;                                      // floor(position) of the tile's first output
+    uint32_t tile_rem;                               // and its remainder (numerator units)
+    uint32_t inc_k, inc_rem;                         // position increment for RS_THREADS outputs
 };
 
 struct __align__(128) FusedSmem {
@@ -35,10 +33,7 @@ struct __align__(128) FusedSmem {
     float scr[FFT_WARPS * SCR_FLOATS_PER_WARP];      // per FFT warp transpose scratch
     float pbuf[2][PBUF_FLOATS];                      // 4*|X[k]|^2, [pb_row(frame)][bin], two consecutive steps
     uint32_t tmem_base;                              // TMEM allocation holding the FFT constants (see tmem_* above)
-    uint32_t fdesc_steps[2];                         // steps of the tiles whose fill descriptors sit in fdesc[0 / 1]
-    uint32_t pad_[1];
-    FillDesc fdesc[2][2 * (TILE_FRAMES / SF)];       // fill descriptors of the current and the next tile (resampler warps -> V warp)
-    unsigned long long desc_ready;                   // first descriptors written
+    uint32_t pad_[3];
     MelTables mel;
     // pipeline barriers (mbarriers): full = data ready for the consumer, empty = buffer may be overwritten
     unsigned long long stage_full[2], stage_empty[2];
@@ -48,11 +43,9 @@ struct __align__(128) FusedSmem {
     unsigned long long st_lo[2], st_hi[2];           // interleaved element range [lo, hi) held by the stage
     uint32_t st_interior[2];                         // 1: every tap of the half step is inside the stage and the stream;
                                                      // 2: inside the stream but not staged (unchecked global loads)
-    // resampler role: descriptor of the tile's stream and the exact position of the tile's first output
-    StreamDev stream;
-    int tile_k;                                      // floor(position) of the tile's first output
-    uint32_t tile_rem;                               // and its remainder (numerator units)
-    uint32_t inc_k, inc_rem;                         // position increment for RS_THREADS outputs
+    // resampler role: every warp keeps its own copy of the tile's stream descriptor and first-output position, so that
+    // a new tile needs no synchronisation among the resampler warps
+    RsTile rs[RS_WARPS];
 };
 static_assert(sizeof(FusedSmem) <= 232448, "FusedSmem exceeds the 227 KB a CTA may use");
 
@@ -213,97 +206,27 @@ struct TileGeo {
 };
 __device__ __forceinline__ TileGeo tile_geo(const FusedParams &P, uint32_t tile, uint32_t *n_frames)
 {
-    const TileDev td = P.tiles[tile];
-    const StreamDev *sp = P.streams + td.stream;
-    const uint32_t n_out = sp->n_out;
-    if (n_frames) *n_frames = sp->n_frames;
+    const TileDev *td = P.tiles + tile;
     TileGeo t;
-    t.stream = td.stream;
-    t.n_tile0 = td.tile * TILE_SAMPLES;
-    t.tile_end = min(t.n_tile0 + (uint32_t)TILE_SAMPLES, n_out);
-    t.f_tile0 = td.tile * TILE_FRAMES;
-    t.n_steps = (t.tile_end - t.n_tile0 + STEP_SAMPLES - 1) / STEP_SAMPLES;
+    t.stream = td->stream;
+    t.n_tile0 = td->tile * TILE_SAMPLES;
+    t.tile_end = td->tile_end;
+    t.f_tile0 = td->tile * TILE_FRAMES;
+    t.n_steps = td->n_steps;
+    if (n_frames) *n_frames = td->n_frames;
     return t;
 }
 __device__ __forceinline__ int half_lo(uint32_t g, int h) { return h == 0 ? (g == 0 ? 0 : CARRY) : HALF_SPLIT; }
 __device__ __forceinline__ int half_hi(int h) { return h == 0 ? HALF_SPLIT : YLEN; }
 
-// ---- stage fill: issued by ONE thread for the half step (tile, g, h); always completes one mbarrier phase ----
-// what the issuing thread keeps about the current tile (one 64-bit division per tile, 32-bit arithmetic per fill)
-struct FillTile {
-    const char *data;
-    unsigned long long n_samples;
-    uint32_t n_in, n_out, n_tile0;
-    uint32_t p, q, mode, ch, bps, staged;
-    long long k0;            // floor(position) of the tile's first output
-    uint32_t rem0;           // and its remainder
-    uint32_t n_steps;
-};
-__device__ __forceinline__ FillTile fill_tile(const FusedParams &P, uint32_t tile)
-{
-    const TileDev td = P.tiles[tile];
-    const StreamDev *sp = P.streams + td.stream;
-    FillTile f;
-    f.data = reinterpret_cast<const char *>(sp->data);
-    f.n_samples = sp->n_samples; f.n_in = sp->n_in; f.n_out = sp->n_out;
-    f.n_tile0 = td.tile * TILE_SAMPLES;
-    f.p = sp->p; f.q = sp->q; f.mode = sp->mode; f.ch = sp->channels; f.bps = sp->format == FMT_I16 ? 2u : 4u;
-    f.staged = sp->staged;
-    f.k0 = 0; f.rem0 = 0;
-    if (f.mode != RS_PASSTHROUGH) resample_pos(f.n_tile0, f.p, f.q, &f.k0, &f.rem0);
-    f.n_steps = (min(f.n_tile0 + (uint32_t)TILE_SAMPLES, f.n_out) - f.n_tile0 + STEP_SAMPLES - 1) / STEP_SAMPLES;
-    return f;
-}
-// floor(position) of output n_tile0 + d (the host guarantees (TILE_SAMPLES + YLEN) * p + q < 2^32)
-__device__ __forceinline__ long long fill_pos(const FillTile &f, uint32_t d)
-{
-    if (f.mode == RS_PASSTHROUGH) return (long long)f.n_tile0 + d;
-    const uint32_t a = f.rem0 + d * f.p;
-    return f.k0 + (long long)(f.q == 1 ? a : a / f.q);
-}
-__device__ __forceinline__ FillDesc make_fill_desc(const FusedParams &P, const FillTile &f, uint32_t g, int h)
-{
-    const uint32_t ch = f.ch, bps = f.bps;
-    unsigned long long lo = 0, hi = 0;
-    uint32_t bytes = 0, interior = 0;
-    const char *src = f.data;
-    {
-        const uint32_t d_first = g * STEP_SAMPLES + (uint32_t)half_lo(g, h);
-        const uint32_t d_full = g * STEP_SAMPLES + (uint32_t)half_hi(h);
-        const uint32_t left = f.n_out - f.n_tile0;                 // outputs from the tile start to the stream end
-        const uint32_t d_last = min(d_full, left);
-        if (d_first < d_last) {
-            const long long k0 = fill_pos(f, d_first), k1 = fill_pos(f, d_last - 1);
-            // interior half step: no tap (k-2 .. k+2) leaves the stream, no output beyond n_out, whole channel frames
-            const bool geom = (k0 - 2 >= 0) && (k1 + 3 <= (long long)f.n_in) &&
-                              ((unsigned long long)(k1 + 3) * ch <= f.n_samples) && (d_last == d_full) && ch <= 2;
-            if (geom) interior = 2;                              // unchecked taps straight from global memory
-            long long i_lo = k0 - 2, i_hi = k1 + 3;
-            if (i_lo < 0) i_lo = 0;
-            if (i_hi > (long long)f.n_in) i_hi = (long long)f.n_in;
-            if (P.use_stage && f.staged && i_lo < i_hi) {
-                unsigned long long b_lo = ((unsigned long long)i_lo * ch * bps) & ~15ull;
-                unsigned long long e_hi = (unsigned long long)i_hi * ch;
-                if (e_hi > f.n_samples) e_hi = f.n_samples;
-                unsigned long long b_hi = (e_hi * bps + 15ull) & ~15ull;
-                const unsigned long long b_end = (f.n_samples * bps) & ~15ull;   // never read past the stream's last full 16 bytes
-                if (b_hi > b_end) b_hi = b_end;
-                if (b_hi > b_lo && b_hi - b_lo <= (unsigned long long)STAGE_BYTES) {
-                    bytes = (uint32_t)(b_hi - b_lo);
-                    lo = bps == 2 ? b_lo >> 1 : b_lo >> 2; hi = bps == 2 ? b_hi >> 1 : b_hi >> 2;
-                    src += b_lo;
-                    if (geom && (unsigned long long)(k1 + 3) * ch <= hi) interior = 1;   // ... and from the stage
-                }
-            }
-        }
-    }
-    FillDesc d;
-    d.src = src; d.bytes = bytes; d.lo = (uint32_t)lo; d.hi = (uint32_t)hi; d.interior = interior; d.pad_[0] = d.pad_[1] = 0;
-    return d;
-}
+// ---- stage fill (descriptors planned per tile by plan_tile, af_device.cuh) ----
 // issued by ONE thread; always completes one phase of stage_full[h]
-__device__ __forceinline__ void issue_fill(FusedSmem &sm, const FillDesc &d, int h)
+__device__ __forceinline__ void issue_fill(FusedSmem &sm, const FusedParams &P, FillDesc d, int h)
 {
+    if (!P.use_stage) {                                  // "sync" variant: nothing staged
+        d.bytes = 0; d.lo = 0; d.hi = 0;
+        if (d.interior == 1u) d.interior = 2u;
+    }
     sm.st_lo[h] = d.lo; sm.st_hi[h] = d.hi; sm.st_interior[h] = d.interior;
     if (d.bytes) {
         mbar_arrive_expect_tx(&sm.stage_full[h], d.bytes);
@@ -395,7 +318,7 @@ struct YSink {
 
 // ---- resampling, interior half steps: every tap comes unchecked from the stage (or the stream) ----
 template <int KIND, bool STAGED>
-__device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, int h, const StreamDev &s, const YSink &out,
+__device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, const RsTile &rt, int h, const StreamDev &s, const YSink &out,
                                                    uint32_t tile_off, int i_lo, int i_hi, int rtid)
 {
     // taps come from the shared-memory stage (first staged mono frame f_lo) or, when the half step does not fit the
@@ -418,7 +341,7 @@ __device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, int h, c
         static_assert(QS % 32 == 0, "a sweep must keep the 32-sample padding phase");
         int i4 = (i_lo & ~31) + 4 * rtid;
         if (i4 < i_lo) i4 += QS;
-        const float *px = reinterpret_cast<const float *>(srcp) + (sm.tile_k + 3 * (int)tile_off - 1 - f_lo) + 3 * i4;
+        const float *px = reinterpret_cast<const float *>(srcp) + (rt.tile_k + 3 * (int)tile_off - 1 - f_lo) + 3 * i4;
         float *yq = out.yb + ypad(i4);
         float *pq = out.pcm + out.base + i4;
         // a quad at i is stored whole when i + 4 <= (samples of this step the tile owns); never without a PCM output
@@ -458,12 +381,12 @@ __device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, int h, c
         if (i4 < i_hi) quad(px, yq, pq, i4);
         return;
     }
-    const uint32_t a = sm.tile_rem + (tile_off + (uint32_t)i) * s.p;
+    const uint32_t a = rt.tile_rem + (tile_off + (uint32_t)i) * s.p;
     if (q == 1) {
         // integer step (48 kHz -> 16 kHz): frac == 0 exactly; the cubic returns y1 bit for bit whenever y1 != 0 and
         // the taps are finite with |x| < 2 -- checked per sample, everything else takes the polynomial
-        int o = sm.tile_k + (int)a - 1 - f_lo;
-        const int inc = (int)sm.inc_k;
+        int o = rt.tile_k + (int)a - 1 - f_lo;
+        const int inc = (int)rt.inc_k;
 #pragma unroll 2
         for (; i < i_hi; i += RS_THREADS, o += inc) {
             const float y0 = tap_fast<KIND>(srcp, o), y1 = tap_fast<KIND>(srcp, o + 1);
@@ -483,9 +406,9 @@ __device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, int h, c
         int i4 = (i_lo & ~31) + 4 * rtid;
         if (i4 < i_lo) i4 += QS;
         const uint32_t p = s.p;
-        const uint32_t a0 = sm.tile_rem + (tile_off + (uint32_t)i4) * p;
+        const uint32_t a0 = rt.tile_rem + (tile_off + (uint32_t)i4) * p;
         uint32_t dk = a0 / q, rem = a0 - dk * q;
-        int k = sm.tile_k + (int)dk - 1 - f_lo;                  // tap y0 of output i4, relative to the staged frames
+        int k = rt.tile_k + (int)dk - 1 - f_lo;                  // tap y0 of output i4, relative to the staged frames
         const uint32_t pk = p / q, pr = p - pk * q;              // per output
         const uint32_t sweep = (uint32_t)(QS - 3) * p;           // from the quad's last output to the next sweep's first
         const uint32_t sk = sweep / q, sr = sweep - sk * q;
@@ -535,7 +458,7 @@ __device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, int h, c
 
 // ---- resampling, checked: samples [base + i_lo, base + i_hi) of the stream, zero beyond n_out ----
 template <int KIND>
-__device__ __noinline__ void resample_half(const FusedSmem &sm, int h, const StreamDev &s, const YSink out,
+__device__ __noinline__ void resample_half(const FusedSmem &sm, const RsTile &rt, int h, const StreamDev &s, const YSink out,
                                            uint32_t tile_off, int i_lo, int i_hi, int rtid)
 {
     const unsigned char *__restrict__ stage = sm.stage[h];
@@ -551,12 +474,12 @@ __device__ __noinline__ void resample_half(const FusedSmem &sm, int h, const Str
     }
     // exact integer position of this thread's first output, relative to the tile start
     const uint32_t q = s.q;
-    const uint32_t a = sm.tile_rem + (tile_off + (uint32_t)i) * s.p;
+    const uint32_t a = rt.tile_rem + (tile_off + (uint32_t)i) * s.p;
     uint32_t dk, rem;
     if (q == 1) { dk = a; rem = 0; }
     else { dk = a / q; rem = a - dk * q; }
-    int k = sm.tile_k + (int)dk;
-    const uint32_t inc_k = sm.inc_k, inc_rem = sm.inc_rem;
+    int k = rt.tile_k + (int)dk;
+    const uint32_t inc_k = rt.inc_k, inc_rem = rt.inc_rem;
     const float inv_q = 1.0f / (float)q;
     const float *__restrict__ frac_tab = s.frac;
     for (; i < i_hi; i += RS_THREADS) {
@@ -589,13 +512,13 @@ __device__ __noinline__ void resample_half(const FusedSmem &sm, int h, const Str
 }
 
 template <int KIND>
-__device__ __forceinline__ void resample_dispatch(const FusedSmem &sm, int h, const StreamDev &s, const YSink &out,
+__device__ __forceinline__ void resample_dispatch(const FusedSmem &sm, const RsTile &rt, int h, const StreamDev &s, const YSink &out,
                                                   uint32_t tile_off, int i_lo, int i_hi, int rtid)
 {
     const uint32_t interior = sm.st_interior[h];
-    if (KIND != K_GENERIC && interior == 1) resample_half_fast<KIND, true>(sm, h, s, out, tile_off, i_lo, i_hi, rtid);
-    else if (KIND != K_GENERIC && interior == 2) resample_half_fast<KIND, false>(sm, h, s, out, tile_off, i_lo, i_hi, rtid);
-    else resample_half<KIND>(sm, h, s, out, tile_off, i_lo, i_hi, rtid);
+    if (KIND != K_GENERIC && interior == 1) resample_half_fast<KIND, true>(sm, rt, h, s, out, tile_off, i_lo, i_hi, rtid);
+    else if (KIND != K_GENERIC && interior == 2) resample_half_fast<KIND, false>(sm, rt, h, s, out, tile_off, i_lo, i_hi, rtid);
+    else resample_half<KIND>(sm, rt, h, s, out, tile_off, i_lo, i_hi, rtid);
 }
 
 // ---- F role: one frame per half-warp, packed (f32x2) arithmetic: pack k = points 2k, 2k+1 of the lane ----
@@ -844,26 +767,35 @@ __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, in
     // long chain never delays a fill.  ENERGIES: the 32 frames of the previous step once its buffer is full.
     const bool chains = P.do_energy && P.energy;
     AF_STATS_DECL
-    // fill cursor (lane 0): tile ordinal, step, half.  The descriptors (source pointer, byte count, staged range) are
-    // worked out by eight resampler threads a tile ahead, so that issuing a fill is a handful of instructions here.
-    uint32_t tile_f = blockIdx.x, ord_f = 0, g_f = 0, it_f = 0;
+    // fill cursor (lane 0): tile, step, half.  The descriptors (source pointer, byte count, staged range) were planned
+    // per tile on the host; the next one is fetched right after a fill is issued, so that issuing a fill is a
+    // handful of instructions once its stage buffer is released.
+    uint32_t tile_f = blockIdx.x, g_f = 0, it_f = 0, steps_f = 0;
     int h_f = 0;
     bool fill_live = tile_f < P.n_tiles;
-    mbar_wait(&sm.desc_ready, 0);
+    FillDesc d_next{};
+    auto fetch_desc = [&]() {
+        const uint4 *src = reinterpret_cast<const uint4 *>(&P.tiles[tile_f].fill[2 * g_f + h_f]);
+        const uint4 a = __ldg(src), b = __ldg(src + 1);
+        d_next.src = reinterpret_cast<const char *>(((unsigned long long)a.y << 32) | a.x);
+        d_next.bytes = a.z; d_next.lo = a.w; d_next.hi = b.x; d_next.interior = b.y;
+    };
+    if (lane == 0 && fill_live) { steps_f = P.tiles[tile_f].n_steps; fetch_desc(); }
     auto issue_next = [&](bool blocking) {                  // lane 0 only
         if (!fill_live) return;
         if (blocking) { AF_WAIT(&sm.stage_empty[h_f], (it_f & 1u) ^ 1u, 0); }
         else if (!mbar_test(&sm.stage_empty[h_f], (it_f & 1u) ^ 1u)) return;
         AF_TIC
-        const FillDesc d = sm.fdesc[ord_f & 1u][2 * g_f + h_f];
-        issue_fill(sm, d, h_f);
+        issue_fill(sm, P, d_next, h_f);
         if (++h_f == 2) {
             h_f = 0; ++it_f;
-            if (++g_f == sm.fdesc_steps[ord_f & 1u]) {
-                g_f = 0; ++ord_f; tile_f += gridDim.x;
+            if (++g_f == steps_f) {
+                g_f = 0; tile_f += gridDim.x;
                 fill_live = tile_f < P.n_tiles;
+                if (fill_live) steps_f = P.tiles[tile_f].n_steps;
             }
         }
+        if (fill_live) fetch_desc();
         AF_TOC(2)
     };
     auto service = [&]() {
@@ -911,52 +843,39 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
 {
     uint32_t it = 0;
     AF_STATS_DECL
-    // the descriptor of a tile's stream is fetched one tile ahead into registers: threads 0..15 hold one word of
-    // the StreamDev each, thread 32 the exact position of the tile's first output
-    uint32_t nx_word = 0, nx_rem = 0, nx_inck = 0, nx_incr = 0, nx_ord = 0;
+    // the descriptor of a tile's stream is fetched one tile ahead into registers: lanes 0..15 of every warp hold one
+    // word of the StreamDev each, lane 16 the planned position of the tile's first output
+    RsTile &rt = sm.rs[rtid >> 5];
+    uint32_t nx_word = 0, nx_rem = 0, nx_inck = 0, nx_incr = 0;
     int nx_k = 0;
     TileGeo nx_t{};
     auto prefetch = [&](uint32_t tile) {
         if (tile >= P.n_tiles) return;
-        const TileDev td = P.tiles[tile];
-        const StreamDev *sp = P.streams + td.stream;
-        nx_t.stream = td.stream;
-        nx_t.n_tile0 = td.tile * TILE_SAMPLES;
-        nx_t.tile_end = min(nx_t.n_tile0 + (uint32_t)TILE_SAMPLES, sp->n_out);
-        nx_t.n_steps = (nx_t.tile_end - nx_t.n_tile0 + STEP_SAMPLES - 1) / STEP_SAMPLES;
-        if (rtid < (int)(sizeof(StreamDev) / 4)) nx_word = reinterpret_cast<const uint32_t *>(sp)[rtid];
-        if (rtid == 32) {
+        const TileDev *td = P.tiles + tile;
+        const StreamDev *sp = &td->sdesc;
+        nx_t.stream = td->stream;
+        nx_t.n_tile0 = td->tile * TILE_SAMPLES;
+        nx_t.tile_end = td->tile_end;
+        nx_t.n_steps = td->n_steps;
+        if (lane < (int)(sizeof(StreamDev) / 4)) nx_word = reinterpret_cast<const uint32_t *>(sp)[lane];
+        if (lane == 16) {
+            nx_k = td->k0; nx_rem = td->rem0;
             const uint32_t p = sp->p, q = sp->q;
-            if (sp->mode != RS_PASSTHROUGH) {
-                long long k; uint32_t rem;
-                resample_pos((uint64_t)td.tile * TILE_SAMPLES, p, q, &k, &rem);
-                nx_k = (int)k; nx_rem = rem;
-                const uint32_t inc = (uint32_t)RS_THREADS * p;
-                nx_inck = inc / q; nx_incr = inc % q;
-            }
+            const uint32_t inc = (uint32_t)RS_THREADS * p;
+            nx_inck = q ? inc / q : 0; nx_incr = q ? inc % q : 0;
         }
-        // eight threads work out the eight fill descriptors of that tile for the V warp (slot = tile ordinal & 1)
-        constexpr int NF = 2 * (TILE_FRAMES / SF);
-        if (rtid >= 64 && rtid < 64 + NF) {
-            const int j = rtid - 64;
-            const FillTile ft = fill_tile(P, tile);
-            sm.fdesc[nx_ord & 1u][j] = make_fill_desc(P, ft, (uint32_t)(j >> 1), j & 1);
-            if (j == 0) sm.fdesc_steps[nx_ord & 1u] = ft.n_steps;
-        }
-        ++nx_ord;
     };
     prefetch(blockIdx.x);
     for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         AF_TIC
         const TileGeo t = nx_t;
-        named_bar_sync(1, RS_THREADS);                  // every resampler thread is done with the previous tile's descriptor
-        if (rtid < (int)(sizeof(StreamDev) / 4)) reinterpret_cast<uint32_t *>(&sm.stream)[rtid] = nx_word;
-        if (rtid == 32) { sm.tile_k = nx_k; sm.tile_rem = nx_rem; sm.inc_k = nx_inck; sm.inc_rem = nx_incr; }
-        named_bar_sync(1, RS_THREADS);
-        if (tile == blockIdx.x && rtid == 0) mbar_arrive(&sm.desc_ready);   // the first tile's fill descriptors are written
+        __syncwarp();                                   // this warp is done with the previous tile's descriptor
+        if (lane < (int)(sizeof(StreamDev) / 4)) reinterpret_cast<uint32_t *>(&rt.stream)[lane] = nx_word;
+        if (lane == 16) { rt.tile_k = nx_k; rt.tile_rem = nx_rem; rt.inc_k = nx_inck; rt.inc_rem = nx_incr; }
+        __syncwarp();
         prefetch(tile + gridDim.x);
         AF_TOC(2)
-        const StreamDev &s = sm.stream;
+        const StreamDev &s = rt.stream;
         int kind = K_GENERIC;
         if (s.channels == 1) kind = s.format == FMT_F32 ? K_F32_1 : K_I16_1;
         else if (s.channels == 2) kind = s.format == FMT_F32 ? K_F32_2 : K_I16_2;
@@ -994,11 +913,11 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
                 const int i_lo = half_lo(g, h), i_hi = half_hi(h);
                 AF_TIC2
                 switch (kind) {
-                case K_F32_1: resample_dispatch<K_F32_1>(sm, h, s, out, toff, i_lo, i_hi, rtid); break;
-                case K_I16_1: resample_dispatch<K_I16_1>(sm, h, s, out, toff, i_lo, i_hi, rtid); break;
-                case K_F32_2: resample_dispatch<K_F32_2>(sm, h, s, out, toff, i_lo, i_hi, rtid); break;
-                case K_I16_2: resample_dispatch<K_I16_2>(sm, h, s, out, toff, i_lo, i_hi, rtid); break;
-                default: resample_dispatch<K_GENERIC>(sm, h, s, out, toff, i_lo, i_hi, rtid); break;
+                case K_F32_1: resample_dispatch<K_F32_1>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                case K_I16_1: resample_dispatch<K_I16_1>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                case K_F32_2: resample_dispatch<K_F32_2>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                case K_I16_2: resample_dispatch<K_I16_2>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                default: resample_dispatch<K_GENERIC>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
                 }
                 AF_TOC(4)
                 if (h == 1) prev_quads = quad_tile && sm.st_interior[1] != 0u;   // (read before the stage is released)
@@ -1036,7 +955,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
             mbar_init(&sm.p_full[h], FFT_WARPS);
             mbar_init(&sm.p_empty[h], MEL_WARPS);
         }
-        mbar_init(&sm.desc_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&sm.tmem_base);

@@ -541,18 +541,20 @@ cudaError_t launch_session_resample(const SessionResample &J, uint32_t n_streams
 }
 
 // every stream of a session has the same lengths: refresh the fused kernel's stream table in place
-__global__ void af_session_setup_kernel(StreamDev *tab, uint32_t n_streams, uint32_t n, uint32_t n_frames, uint32_t n_vad)
+__global__ void af_session_setup_kernel(StreamDev *tab, TileDev *tiles, uint32_t n_streams, uint32_t n, uint32_t n_frames,
+                                        uint32_t n_vad)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_streams) return;
     tab[s].n_samples = n; tab[s].n_in = n; tab[s].n_out = n; tab[s].n_frames = n_frames; tab[s].n_vad_frames = n_vad;
+    plan_tile(tab[s], s, 0, &tiles[s]);               // the tick's single tile: positions and stage fills
 }
 
-cudaError_t launch_session_setup(StreamDev *tab, uint32_t n_streams, uint32_t n, uint32_t n_frames, uint32_t n_vad,
+cudaError_t launch_session_setup(StreamDev *tab, TileDev *tiles, uint32_t n_streams, uint32_t n, uint32_t n_frames, uint32_t n_vad,
                                  cudaStream_t st)
 {
     if (n_streams == 0) return cudaSuccess;
-    af_session_setup_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(tab, n_streams, n, n_frames, n_vad);
+    af_session_setup_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(tab, tiles, n_streams, n, n_frames, n_vad);
     return cudaGetLastError();
 }
 

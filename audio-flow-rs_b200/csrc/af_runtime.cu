@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/audioflow_gpu.h"
+#include "af_device.cuh"
 #include "af_launch.h"
 #include "af_plan.h"
 
@@ -698,7 +699,11 @@ int build_sub(af_batch *b, SubBatch &sb, const void *slot_in_base)
         }
         d.tile_begin = (uint32_t)sb.h_tiles.size();
         d.n_tiles = (hs.n_out + TILE_SAMPLES - 1) / TILE_SAMPLES;
-        for (uint32_t t = 0; t < d.n_tiles; ++t) sb.h_tiles.push_back(TileDev{(uint32_t)i, t});
+        for (uint32_t t = 0; t < d.n_tiles; ++t) {
+            TileDev td;
+            plan_tile(d, (uint32_t)i, t, &td);                  // positions and stage fills: no 64-bit divisions in the kernel
+            sb.h_tiles.push_back(td);
+        }
         nf[i] = hs.n_frames; nv[i] = hs.n_vad_frames;
     }
     if (!sb.d_streams) {
@@ -1159,10 +1164,8 @@ AF_API int af_session_create(af_pipeline *p, size_t n_streams, uint32_t sample_r
         AF_CUDA(cudaMemcpy(s->d_tab[i], tab.data(), n_streams * sizeof(StreamDev), cudaMemcpyHostToDevice));
     }
     if (s->y_stride > (uint64_t)TILE_SAMPLES) return fail(AF_ERR_INVALID, "max_tick_samples too large for a session (%u)", max_tick_samples);
-    std::vector<TileDev> tiles(n_streams);
-    for (size_t k = 0; k < n_streams; ++k) tiles[k] = TileDev{(uint32_t)k, 0};
-    AF_CUDA(cudaMalloc(&s->d_tiles, n_streams * sizeof(TileDev)));
-    AF_CUDA(cudaMemcpy(s->d_tiles, tiles.data(), n_streams * sizeof(TileDev), cudaMemcpyHostToDevice));
+    AF_CUDA(cudaMalloc(&s->d_tiles, n_streams * sizeof(TileDev)));    // planned per tick by the session set-up kernel
+    AF_CUDA(cudaMemset(s->d_tiles, 0, n_streams * sizeof(TileDev)));
     AF_CUDA(cudaMalloc(&s->d_vad, n_streams * sizeof(VadState)));
     AF_CUDA(cudaMalloc(&s->d_energy, n_streams * s->energy_stride * sizeof(float)));
     s->frac_cap = max_new_y + 64;
@@ -1274,7 +1277,7 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
             if (st_stride < T) return fail(AF_ERR_CAPACITY, "vad_stride too small for %u frames", T);
         }
         if (stft_frames) {
-            AF_CUDA(launch_session_setup(s->d_tab[s->y_cur], (uint32_t)S, y_total, T, cfg.vad_enable ? T : 0, st));
+            AF_CUDA(launch_session_setup(s->d_tab[s->y_cur], s->d_tiles, (uint32_t)S, y_total, T, cfg.vad_enable ? T : 0, st));
             FusedParams P{};
             P.streams = s->d_tab[s->y_cur]; P.tiles = s->d_tiles; P.n_tiles = (uint32_t)S;
             P.fft = g_ctx.d_fft; P.mel = s->pipe->d_mel;
