@@ -27,11 +27,11 @@ constexpr int HALF_SPLIT = 2688;             // a step's raw input is staged in 
 constexpr int TILE_FRAMES = 128;             // frames per tile (work unit of one CTA)
 constexpr int TILE_SAMPLES = TILE_FRAMES * HOP;   // 20480
 constexpr int FFT_WARPS = 16;                // warps 0..15: window + FFT + power, one frame per half-warp
-constexpr int MEL_WARPS = 5;                 // warps 16..22: mel projection + log, lane = frame
+constexpr int MEL_WARPS = 4;                 // warps 16..19: mel projection + log, lane = frame
 constexpr int MEL_WARP0 = FFT_WARPS;
-constexpr int VAD_WARP = MEL_WARP0 + MEL_WARPS;   // warp 23: stage fills (TMA bulk copies) + sequential frame energies
-constexpr int RS_WARP0 = VAD_WARP + 1;       // warps 24..27: downmix + resample + PCM write-out
-constexpr int RS_WARPS = 6;
+constexpr int VAD_WARP = MEL_WARP0 + MEL_WARPS;   // warp 20: stage fills (TMA bulk copies) + sequential frame energies
+constexpr int RS_WARP0 = VAD_WARP + 1;       // warps 21..27: downmix + resample + PCM write-out
+constexpr int RS_WARPS = 7;                  // 224 threads: a half step (2688 outputs) is exactly three quads per thread
 constexpr int RS_THREADS = RS_WARPS * 32;
 constexpr int FUSED_WARPS = RS_WARP0 + RS_WARPS;  // 28
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;   // 896
@@ -111,14 +111,19 @@ static_assert(sizeof(TileDev) % 16 == 0 && offsetof(TileDev, fill) % 16 == 0, "f
 // mel filterbank in compact form (weights already carry the 1/4 of the unscaled power).  The mel warps work
 // lane = frame and walk FOUR adjacent filters (a "quad": one 16-byte store per frame) at a time, eight
 // independent FMA chains: the quad's weights are zero padded to a common number of quadruples and interleaved
-// [a0..a3][b0..b3][c0..c3][d0..d3] per step so that four warp-uniform LDS.128 feed sixteen FMAs.  The quads are
-// split over the MEL_WARPS warps by weight count.
-struct MelQuad {
-    uint16_t lo[4];          // first bin read for each of the four filters: a multiple of 4, lo + 4 c4 <= PB_COLS
-    uint16_t c4;             // number of weight quadruples per filter
-    uint16_t off16;          // offset of the quad's weights in w, in units of 16 floats
-    uint16_t pad_[2];
+// [a0..a3][b0..b3][c0..c3][d0..d3] per step.  The quads are split over the MEL_WARPS warps by cost.  The weights of
+// a quad are warp-uniform: they are served from tensor memory (one tcgen05.ld of 16 columns per step, no
+// shared-memory bandwidth) when the quarter of TMEM its warp can address has room for them, else by LDS.128.
+struct alignas(16) MelQuad {
+    uint32_t off[4];         // byte offset, inside a power row, of the first bin each of the four filters reads (a multiple of 16)
+    uint32_t c4;             // number of weight quadruples per filter; off / 4 + 4 c4 <= PB_COLS
+    uint32_t woff;           // byte offset of the quad's weights inside MelTables::w (a multiple of 64)
+    uint32_t tcol;           // first TMEM column of the quad's weights (16 columns per step), MEL_NO_TMEM: not resident
+    uint32_t pad_;
 };
+constexpr uint32_t MEL_NO_TMEM = 0xffffffffu;
+constexpr uint32_t TMEM_COLS = 512;          // the whole tensor memory of the SM (one CTA per SM)
+constexpr uint32_t TM_MEL0 = 80;             // first column of the mel weights (the FFT constants use 0..73)
 struct MelTables {
     MelQuad quad[MAX_MELS / 4];
     uint16_t n_w;
@@ -126,8 +131,17 @@ struct MelTables {
     uint16_t quad_begin[MEL_WARPS + 1];   // mel warp j owns filter quads [quad_begin[j], quad_begin[j + 1])
     alignas(16) float w[1536];
 };
-static_assert(sizeof(MelQuad) == 16, "MelQuad is read with one LDS.128");
+static_assert(sizeof(MelQuad) == 32, "MelQuad is read with two LDS.128");
 static_assert(offsetof(MelTables, w) % 16 == 0, "mel weights must be 16-byte aligned");
+
+// what the roles downstream of the resampler need to know about a step (32 frames): published through shared
+// memory with the buffer hand-off, so that the FFT and mel warps keep no tile state of their own
+struct alignas(16) StepInfo {
+    float *lm_dst;           // log-mel row of the step's first frame (nullptr: no features)
+    int n_valid;             // low byte: frames of the step that exist in the stream (0..32); STEP_LAST: the CTA's last step
+    uint32_t pad_;
+};
+constexpr int STEP_LAST = 0x100;
 
 // constant tables of the FFT, filled by the host in f64 and rounded once
 struct FftTables {

@@ -34,6 +34,10 @@ struct __align__(128) FusedSmem {
     float pbuf[2][PBUF_FLOATS];                      // 4*|X[k]|^2, [pb_row(frame)][bin], two consecutive steps
     uint32_t tmem_base;                              // TMEM allocation holding the FFT constants (see tmem_* above)
     uint32_t pad_[3];
+    StepInfo yinfo[2];                               // what ybuf[b] holds: written by resampler thread 0 before its y_full arrive
+    StepInfo pinfo[4];                               // ring (step & 3) of what the power buffers hold: copied from yinfo by FFT
+                                                     // thread 0 as soon as it sees a step, four deep so that no FFT lane has to
+                                                     // carry the record across the transform (the mel warps lag < 3 steps)
     MelTables mel;
     // pipeline barriers (mbarriers): full = data ready for the consumer, empty = buffer may be overwritten
     unsigned long long stage_full[2], stage_empty[2];
@@ -143,7 +147,6 @@ template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setma
 // on an LSU-bound kernel.  TMEM is lane-addressed (thread t of a warp reads lane 32 (warp % 4) + t), has its own
 // datapath (tcgen05.ld, no LSU / shared-memory bandwidth) and is otherwise idle here: the constants are written
 // once per CTA into 74 columns of each lane quarter and fetched from there just before use.
-constexpr uint32_t TMEM_COLS = 128;          // allocation granularity: power of two >= 74
 constexpr uint32_t TM_TW1 = 0;               // 32 columns: tw1p[p] = columns 4p .. 4p+3  (re_a, re_b, im_a, im_b)
 constexpr uint32_t TM_TW2 = 32;              // 16 columns: tw2p[r] = columns 4r .. 4r+3
 constexpr uint32_t TM_WIN = 48;              // 26 columns: window[32 n1 + 2 l + e] at 2 n1 + e
@@ -182,6 +185,20 @@ __device__ __forceinline__ float2 tmem_ld2(uint32_t taddr)
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(taddr));
     return v;
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+                   "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float4 &a, const float4 &b, const float4 &c, const float4 &d)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+                 "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "f"(c.x), "f"(c.y), "f"(c.z), "f"(c.w),
+                 "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
+                 : "memory");
+}
 // the loaded registers may be used only after the wait: passing them through the statement as in/out operands
 // keeps the compiler from scheduling a use above it
 __device__ __forceinline__ void tmem_wait_ld(float4 &a)
@@ -198,11 +215,17 @@ __device__ __forceinline__ void tmem_wait_ld(float (&v)[8])
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])::"memory");
 }
+__device__ __forceinline__ void tmem_wait_ld(float (&v)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                   "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])::"memory");
+}
 __device__ __forceinline__ void tmem_wait_ld(float2 &a) { asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(a.x), "+f"(a.y)::"memory"); }
 
 // ---- geometry of a tile, recomputed by every role from the same tables ----
 struct TileGeo {
-    uint32_t stream, n_tile0, tile_end, f_tile0, n_steps;
+    uint32_t stream, n_tile0, tile_end, f_tile0, n_steps, n_frames;
 };
 __device__ __forceinline__ TileGeo tile_geo(const FusedParams &P, uint32_t tile, uint32_t *n_frames)
 {
@@ -213,6 +236,7 @@ __device__ __forceinline__ TileGeo tile_geo(const FusedParams &P, uint32_t tile,
     t.tile_end = td->tile_end;
     t.f_tile0 = td->tile * TILE_FRAMES;
     t.n_steps = td->n_steps;
+    t.n_frames = td->n_frames;
     if (n_frames) *n_frames = td->n_frames;
     return t;
 }
@@ -669,94 +693,153 @@ __device__ __forceinline__ void role_fft(FusedSmem &sm, const FusedParams &P, in
     float *scr = sm.scr + warp * SCR_FLOATS_PER_WARP + 16 * half;
     const uint32_t tm = sm.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);   // this warp's lane quarter
     const bool on = P.n_mels != 0;
-    uint32_t it = 0;
     AF_STATS_DECL
-    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        uint32_t n_frames;
-        const TileGeo t = tile_geo(P, tile, &n_frames);
-        for (uint32_t g = 0; g < t.n_steps; ++g, ++it) {
-            const uint32_t f0 = t.f_tile0 + g * SF;
-            const int n_valid = f0 < n_frames ? (int)min((uint32_t)SF, n_frames - f0) : 0;
-            const bool work = on && warp * 2 < n_valid;         // warp-uniform: skip fully invalid pairs
-            const int b = (int)(it & 1u);
-            f2 R[8], I[8];
-            AF_WAIT(&sm.y_full[b], (it >> 1) & 1u, 0);
-            if (work) fft_load(sm.ybuf[b], tm, q, l, R, I);
-            warp_arrive(&sm.y_empty[b], lane);                  // the step buffer is no longer needed by this warp
-            if (work) fft_passes(tm, scr, l, R, I);
-            AF_WAIT(&sm.p_empty[b], ((it >> 1) & 1u) ^ 1u, 1);   // the mel warps are done with this power buffer
-            if (work) fft_power(sm.pbuf[b], tm, q, l, lane, R, I);
-            warp_arrive(&sm.p_full[b], lane);
-        }
+    // no tile state here: the resampler publishes what each step buffer holds (StepInfo), including the end of the work
+    for (uint32_t it = 0;; ++it) {
+        const int b = (int)(it & 1u);
+        f2 R[8], I[8];
+        AF_WAIT(&sm.y_full[b], (it >> 1) & 1u, 0);
+        const int nv = sm.yinfo[b].n_valid;                 // frames that exist, STEP_LAST on the CTA's last step
+        const bool work = on && warp * 2 < (nv & 0xff);     // warp-uniform: skip fully invalid pairs
+        if (warp == 0 && lane == 0) sm.pinfo[it & 3u] = sm.yinfo[b];
+        if (work) fft_load(sm.ybuf[b], tm, q, l, R, I);
+        warp_arrive(&sm.y_empty[b], lane);                  // the step buffer (and its info) is no longer needed by this warp
+        if (work) fft_passes(tm, scr, l, R, I);
+        AF_WAIT(&sm.p_empty[b], ((it >> 1) & 1u) ^ 1u, 1);   // the mel warps are done with this power buffer
+        if (work) fft_power(sm.pbuf[b], tm, q, l, lane, R, I);
+        warp_arrive(&sm.p_full[b], lane);
+        if (nv & STEP_LAST) break;
     }
     AF_STATS_FLUSH(0, lane);
 }
 
-__device__ __forceinline__ void role_mel(FusedSmem &sm, const FusedParams &P, int mw, int lane)
+// log2 of a value that is never subnormal (it was clamped to a normal floor): no range fix-up around MUFU.LG2
+__device__ __forceinline__ float lg2_ftz(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// one step of a filter quad: four bins of each of the four filters against sixteen warp-uniform weights, all offsets
+// immediate.  The weights come from tensor memory (one tcgen05.ld, issued before the power loads so that the two
+// latencies overlap) or, for a quad that is not resident there, from shared memory.
+#define AF_MEL_FMA16()                                                                              \
+    a0 = fmaf(wa.x, xa.x, a0); a1 = fmaf(wa.y, xa.y, a1);                                         \
+    b0 = fmaf(wb.x, xb.x, b0); b1 = fmaf(wb.y, xb.y, b1);                                         \
+    c0 = fmaf(wc.x, xc.x, c0); c1 = fmaf(wc.y, xc.y, c1);                                         \
+    d0 = fmaf(wd.x, xd.x, d0); d1 = fmaf(wd.y, xd.y, d1);                                         \
+    a0 = fmaf(wa.z, xa.z, a0); a1 = fmaf(wa.w, xa.w, a1);                                         \
+    b0 = fmaf(wb.z, xb.z, b0); b1 = fmaf(wb.w, xb.w, b1);                                         \
+    c0 = fmaf(wc.z, xc.z, c0); c1 = fmaf(wc.w, xc.w, c1);                                         \
+    d0 = fmaf(wd.z, xd.z, d0); d1 = fmaf(wd.w, xd.w, d1);
+#define AF_MEL_STEP_S(i)                                                                            \
+    {                                                                                               \
+        const float4 wa = w4[4 * (i)], wb = w4[4 * (i) + 1], wc = w4[4 * (i) + 2], wd = w4[4 * (i) + 3]; \
+        const float4 xa = pa[i], xb = pb[i], xc = pc[i], xd = pd[i];                                \
+        AF_MEL_FMA16()                                                                              \
+    }
+#define AF_MEL_STEP_T(i)                                                                            \
+    {                                                                                               \
+        float w_[16];                                                                               \
+        tmem_ld16(tq + 16u * (i), w_);                                                              \
+        const float4 xa = pa[i], xb = pb[i], xc = pc[i], xd = pd[i];                                \
+        tmem_wait_ld(w_);                                                                           \
+        const float4 wa = make_float4(w_[0], w_[1], w_[2], w_[3]), wb = make_float4(w_[4], w_[5], w_[6], w_[7]);       \
+        const float4 wc = make_float4(w_[8], w_[9], w_[10], w_[11]), wd = make_float4(w_[12], w_[13], w_[14], w_[15]); \
+        AF_MEL_FMA16()                                                                              \
+    }
+// the steps run from the quad's last quadruple down to its first through an unrolled chain entered at `c4`
+#define AF_MEL_CHAIN(STEP)                                                                          \
+    switch (c4) {                                                                                   \
+    case 8: STEP(7)                                                                                 \
+    case 7: STEP(6)                                                                                 \
+    case 6: STEP(5)                                                                                 \
+    case 5: STEP(4)                                                                                 \
+    case 4: STEP(3)                                                                                 \
+    case 3: STEP(2)                                                                                 \
+    case 2: STEP(1)                                                                                 \
+    case 1: STEP(0)                                                                                 \
+    default: break;                                                                                 \
+    }
+
+template <bool FAST_LOG, bool VEC>
+__device__ __forceinline__ void role_mel_run(FusedSmem &sm, const FusedParams &P, int mw, int lane)
 {
     const uint32_t M = P.n_mels;
     const float log_mul = P.log_scale, log_floor = P.log_floor;
     const int q0 = sm.mel.quad_begin[mw], q1 = sm.mel.quad_begin[mw + 1];
-    const bool vec = (M & 3u) == 0 && (P.logmel_stride & 3ull) == 0 && ((reinterpret_cast<uintptr_t>(P.logmel) & 15) == 0);
-    uint32_t it = 0;
+    const int fr = pb_frame(lane);                              // frame held by power row `lane`
+    const uint32_t tm = sm.tmem_base + ((uint32_t)(32 * ((MEL_WARP0 + mw) & 3)) << 16);   // this warp's lane quarter
     AF_STATS_DECL
-    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        uint32_t n_frames;
-        const TileGeo t = tile_geo(P, tile, &n_frames);
-        float *lm_row = P.logmel ? P.logmel + (uint64_t)t.stream * P.logmel_stride : nullptr;
-        for (uint32_t g = 0; g < t.n_steps; ++g, ++it) {
-            const uint32_t f0 = t.f_tile0 + g * SF;
-            const int n_valid = f0 < n_frames ? (int)min((uint32_t)SF, n_frames - f0) : 0;
-            const int b = (int)(it & 1u);
-            AF_WAIT(&sm.p_full[b], (it >> 1) & 1u, 0);
-            if (M && lm_row && n_valid > 0) {
-                const int fr = pb_frame(lane);                          // frame held by power row `lane`
-                const bool valid = fr < n_valid;
-                float *dst = lm_row + (uint64_t)(f0 + fr) * M;
-                const float *prow = sm.pbuf[b] + lane * PB_ROW;
-                for (int qd = q0; qd < q1; ++qd) {
-                    // four adjacent filters at a time: eight independent FMA chains, weights by warp-uniform LDS.128
-                    const uint4 dq = *reinterpret_cast<const uint4 *>(&sm.mel.quad[qd]);
-                    const int c4 = (int)(dq.z & 0xffffu);
-                    const float4 *w4 = reinterpret_cast<const float4 *>(sm.mel.w) + 4 * (dq.z >> 16);
-                    const float4 *pa = reinterpret_cast<const float4 *>(prow + (dq.x & 0xffffu));
-                    const float4 *pb = reinterpret_cast<const float4 *>(prow + (dq.x >> 16));
-                    const float4 *pc = reinterpret_cast<const float4 *>(prow + (dq.y & 0xffffu));
-                    const float4 *pd = reinterpret_cast<const float4 *>(prow + (dq.y >> 16));
-                    float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f, c0 = 0.0f, c1 = 0.0f, d0 = 0.0f, d1 = 0.0f;
+    // no tile state here: the FFT warps forward what each power buffer holds (StepInfo), including the end of the work
+    for (uint32_t it = 0;; ++it) {
+        const int b = (int)(it & 1u);
+        AF_WAIT(&sm.p_full[b], (it >> 1) & 1u, 0);
+        const StepInfo info = sm.pinfo[it & 3u];
+        const int n_valid = info.n_valid & 0xff;
+        if (M && info.lm_dst && n_valid > 0) {
+            const bool valid = fr < n_valid;
+            float *dst = info.lm_dst + (uint32_t)fr * M + 4 * q0;
+            const char *prow = reinterpret_cast<const char *>(sm.pbuf[b] + lane * PB_ROW);
+            const uint4 *qtab = reinterpret_cast<const uint4 *>(&sm.mel.quad[q0]);
+            for (int qd = q0; qd < q1; ++qd, qtab += 2, dst += 4) {
+                const uint4 d0q = qtab[0], d1q = qtab[1];
+                const float4 *pa = reinterpret_cast<const float4 *>(prow + d0q.x);
+                const float4 *pb = reinterpret_cast<const float4 *>(prow + d0q.y);
+                const float4 *pc = reinterpret_cast<const float4 *>(prow + d0q.z);
+                const float4 *pd = reinterpret_cast<const float4 *>(prow + d0q.w);
+                int c4 = (int)d1q.x;
+                float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f, c0 = 0.0f, c1 = 0.0f, d0 = 0.0f, d1 = 0.0f;
+                if (d1q.z != MEL_NO_TMEM) {
+                    const uint32_t tq = tm + d1q.z;
+                    AF_MEL_CHAIN(AF_MEL_STEP_T)
+                } else {
+                    const float4 *w4 = reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(sm.mel.w) + d1q.y);
 #pragma unroll 1
-                    for (int j = 0; j < c4; ++j) {
-                        const float4 wa = w4[0], wb = w4[1], wc = w4[2], wd = w4[3];
-                        const float4 xa = pa[j], xb = pb[j], xc = pc[j], xd = pd[j];
-                        a0 = fmaf(wa.x, xa.x, a0); a1 = fmaf(wa.y, xa.y, a1);
-                        b0 = fmaf(wb.x, xb.x, b0); b1 = fmaf(wb.y, xb.y, b1);
-                        c0 = fmaf(wc.x, xc.x, c0); c1 = fmaf(wc.y, xc.y, c1);
-                        d0 = fmaf(wd.x, xd.x, d0); d1 = fmaf(wd.y, xd.y, d1);
-                        a0 = fmaf(wa.z, xa.z, a0); a1 = fmaf(wa.w, xa.w, a1);
-                        b0 = fmaf(wb.z, xb.z, b0); b1 = fmaf(wb.w, xb.w, b1);
-                        c0 = fmaf(wc.z, xc.z, c0); c1 = fmaf(wc.w, xc.w, c1);
-                        d0 = fmaf(wd.z, xd.z, d0); d1 = fmaf(wd.w, xd.w, d1);
-                        w4 += 4;
-                    }
-                    float o[4];
+                    for (; c4 > 8; --c4) AF_MEL_STEP_S(c4 - 1)      // wide filters (few mel bands): generic steps first
+                    AF_MEL_CHAIN(AF_MEL_STEP_S)
+                }
+                float o[4];
+                if (FAST_LOG) {
+                    o[0] = lg2_ftz(fmaxf(a0 + a1, log_floor)) * log_mul;
+                    o[1] = lg2_ftz(fmaxf(b0 + b1, log_floor)) * log_mul;
+                    o[2] = lg2_ftz(fmaxf(c0 + c1, log_floor)) * log_mul;
+                    o[3] = lg2_ftz(fmaxf(d0 + d1, log_floor)) * log_mul;
+                } else {
                     o[0] = __log2f(fmaxf(a0 + a1, log_floor)) * log_mul;
                     o[1] = __log2f(fmaxf(b0 + b1, log_floor)) * log_mul;
                     o[2] = __log2f(fmaxf(c0 + c1, log_floor)) * log_mul;
                     o[3] = __log2f(fmaxf(d0 + d1, log_floor)) * log_mul;
-                    if (valid) {
-                        if (vec) __stcs(reinterpret_cast<float4 *>(dst + 4 * qd), make_float4(o[0], o[1], o[2], o[3]));
-                        else {
+                }
+                if (valid) {
+                    if (VEC) __stcs(reinterpret_cast<float4 *>(dst), make_float4(o[0], o[1], o[2], o[3]));
+                    else {
 #pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (4 * qd + u < (int)M) dst[4 * qd + u] = o[u];
-                        }
+                        for (int u = 0; u < 4; ++u)
+                            if (4 * qd + u < (int)M) dst[u] = o[u];
                     }
                 }
             }
-            warp_arrive(&sm.p_empty[b], lane);
         }
+        warp_arrive(&sm.p_empty[b], lane);
+        if (info.n_valid & STEP_LAST) break;
     }
     AF_STATS_FLUSH(1, lane);
+}
+#undef AF_MEL_CHAIN
+#undef AF_MEL_STEP_T
+#undef AF_MEL_STEP_S
+#undef AF_MEL_FMA16
+
+__device__ __forceinline__ void role_mel(FusedSmem &sm, const FusedParams &P, int mw, int lane)
+{
+    // the clamped value is normal: lg2.approx.ftz needs no range fix-up; 16-byte stores when every row allows them
+    const bool fast_log = P.log_floor >= 1.17549435e-38f;
+    const bool vec = (P.n_mels & 3u) == 0 && (P.logmel_stride & 3ull) == 0 && ((reinterpret_cast<uintptr_t>(P.logmel) & 15) == 0);
+    if (fast_log && vec) role_mel_run<true, true>(sm, P, mw, lane);
+    else if (vec) role_mel_run<false, true>(sm, P, mw, lane);
+    else role_mel_run<false, false>(sm, P, mw, lane);
 }
 
 __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, int lane)
@@ -857,6 +940,7 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
         nx_t.n_tile0 = td->tile * TILE_SAMPLES;
         nx_t.tile_end = td->tile_end;
         nx_t.n_steps = td->n_steps;
+        nx_t.n_frames = td->n_frames;
         if (lane < (int)(sizeof(StreamDev) / 4)) nx_word = reinterpret_cast<const uint32_t *>(sp)[lane];
         if (lane == 16) {
             nx_k = td->k0; nx_rem = td->rem0;
@@ -923,6 +1007,16 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
                 if (h == 1) prev_quads = quad_tile && sm.st_interior[1] != 0u;   // (read before the stage is released)
                 warp_arrive(&sm.stage_empty[h], lane);          // this warp no longer reads stage[h] or its metadata
             }
+            if (rtid == 0) {
+                // what this step buffer holds, for the FFT and mel warps (they keep no tile state)
+                const uint32_t f0 = (t.n_tile0 / HOP) + g * SF, n_frames = t.n_frames;
+                StepInfo info;
+                info.lm_dst = (P.logmel && P.n_mels) ? P.logmel + (uint64_t)t.stream * P.logmel_stride + (uint64_t)f0 * P.n_mels : nullptr;
+                info.n_valid = f0 < n_frames ? (int)min((uint32_t)SF, n_frames - f0) : 0;
+                if (g + 1 == t.n_steps && tile + gridDim.x >= P.n_tiles) info.n_valid |= STEP_LAST;
+                info.pad_ = 0;
+                sm.yinfo[b] = info;
+            }
             warp_arrive(&sm.y_full[b], lane);
         }
     }
@@ -971,6 +1065,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
         for (int r = 0; r < 4; ++r) tmem_st4(tm + TM_TW2 + 4 * r, P.fft->tw2p[r * 16 + l]);
 #pragma unroll
         for (int n1 = 0; n1 < 13; ++n1) tmem_st2(tm + TM_WIN + 2 * n1, P.fft->window[32 * n1 + 2 * l], P.fft->window[32 * n1 + 2 * l + 1]);
+        tmem_wait_st();
+    } else if (warp >= MEL_WARP0 && warp < MEL_WARP0 + MEL_WARPS && P.n_mels) {
+        // every mel warp copies the weights of its resident quads into its own TMEM lane quarter: all 32 lanes (rows)
+        // hold the same sixteen values per step, so that a 32x32b load hands every lane the warp-uniform weights
+        const uint32_t tm = sm.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+        const int mw = warp - MEL_WARP0;
+        for (int qd = sm.mel.quad_begin[mw]; qd < sm.mel.quad_begin[mw + 1]; ++qd) {
+            const MelQuad &Q = sm.mel.quad[qd];
+            if (Q.tcol == MEL_NO_TMEM) continue;
+            const float4 *w4 = reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(sm.mel.w) + Q.woff);
+            for (uint32_t j = 0; j < Q.c4; ++j) tmem_st16(tm + Q.tcol + 16u * j, w4[4 * j], w4[4 * j + 1], w4[4 * j + 2], w4[4 * j + 3]);
+        }
         tmem_wait_st();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -115,10 +115,10 @@ bool build_mel_tables(uint32_t n_mels, float f_min, float f_max, MelTables *t)
         const uint32_t c4 = (uint32_t)((longest + 3) / 4);
         if (off16 + c4 > cap16) return false;
         MelQuad &Q = t->quad[qd];
-        Q.c4 = (uint16_t)c4; Q.off16 = (uint16_t)off16;
+        Q.c4 = c4; Q.woff = 64u * off16; Q.tcol = MEL_NO_TMEM;
         for (uint32_t u = 0; u < 4; ++u) {
             const uint32_t m = 4 * qd + u;
-            if (m >= n_mels) { Q.lo[u] = 0; continue; }                   // all-zero weights
+            if (m >= n_mels) { Q.off[u] = 0; continue; }                   // all-zero weights
             // the padded reads must stay inside the power row (PB_COLS floats): start earlier with zero weights in front
             int excess = los[m] + 4 * (int)c4 - PB_COLS;
             if (excess > 0) {
@@ -128,11 +128,11 @@ bool build_mel_tables(uint32_t n_mels, float f_min, float f_max, MelTables *t)
                 los[m] -= excess;
                 if (wts[m].size() > 4 * (size_t)c4) return false;
             }
-            Q.lo[u] = (uint16_t)los[m];
+            Q.off[u] = 4u * (uint32_t)los[m];
             for (size_t k = 0; k < wts[m].size(); ++k) t->w[16 * (off16 + k / 4) + 4 * u + (k & 3)] = wts[m][k];
         }
         off16 += c4;
-        cost[qd] = 31u * c4 + 30u;
+        cost[qd] = 24u * c4 + 40u;                     // warp instructions per quad in role_mel
         total += cost[qd];
     }
     t->n_w = (uint16_t)(16 * off16); t->n_mels = (uint16_t)n_mels;
@@ -145,6 +145,16 @@ bool build_mel_tables(uint32_t n_mels, float f_min, float f_max, MelTables *t)
         t->quad_begin[j] = (uint16_t)q;
     }
     t->quad_begin[MEL_WARPS] = (uint16_t)n_quads;
+    // tensor-memory residence of the weights: mel warp j is warp MEL_WARP0 + j of the CTA and can only address the
+    // TMEM lane quarter (MEL_WARP0 + j) % 4; a quad takes 16 columns per step after the FFT constants
+    uint32_t next_col[4] = {TM_MEL0, TM_MEL0, TM_MEL0, TM_MEL0};
+    for (int j = 0; j < MEL_WARPS; ++j) {
+        uint32_t &col = next_col[(MEL_WARP0 + j) & 3];
+        for (uint32_t qd = t->quad_begin[j]; qd < t->quad_begin[j + 1]; ++qd) {
+            const uint32_t need = 16u * t->quad[qd].c4;
+            if (t->quad[qd].c4 <= 8 && col + need <= TMEM_COLS) { t->quad[qd].tcol = col; col += need; }
+        }
+    }
     return true;
 }
 

@@ -1,9 +1,11 @@
 // af_runtime.cu -- the C ABI of libaudioflow_gpu.so (include/audioflow_gpu.h): library context,
 // compat objects mirroring the reference's Rust types, and the batched pipeline host runtime.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -1088,6 +1090,7 @@ struct af_session {
     uint64_t lm_stride = 0, st_stride = 0;
     std::vector<float> frac_host;
     uint64_t frames_emitted = 0;
+    float *ring_stage = nullptr; size_t ring_stage_cap = 0;   // pinned rows for af_session_push_rings
 };
 
 extern "C" {
@@ -1108,6 +1111,7 @@ AF_API void af_session_destroy(af_session *s)
     if (s->d_in_stage) cudaFree(s->d_in_stage);
     if (s->d_lm) cudaFree(s->d_lm);
     if (s->d_states) cudaFree(s->d_states);
+    if (s->ring_stage) cudaFreeHost(s->ring_stage);
     delete s;
 }
 
@@ -1362,6 +1366,133 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
         if (n_vad) n_vad[k] = cfg.vad_enable ? T : 0;
     }
     return AF_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// capture hand-off: RingBuffer (capture.rs:84-161) in pinned host memory, feeding sessions
+// ------------------------------------------------------------------------------------------
+struct af_ring {
+    float *buf = nullptr;
+    size_t capacity = 0;
+    bool pinned = false;
+    std::mutex mu;                                  // the reference locks its Vec for every call (capture.rs:103,124,159)
+    std::atomic<size_t> write_pos{0}, read_pos{0};
+};
+
+namespace {
+// (write_pos - read_pos + capacity) % capacity, as capture.rs:107-109,128,152
+inline size_t ring_used(const af_ring *r)
+{
+    const size_t w = r->write_pos.load(std::memory_order_seq_cst), rd = r->read_pos.load(std::memory_order_seq_cst);
+    return (w + r->capacity - rd) % r->capacity;
+}
+}  // namespace
+
+extern "C" {
+
+AF_API int af_ring_create(size_t capacity_samples, af_ring **out)
+{
+    if (!out) return fail(AF_ERR_INVALID, "null out pointer");
+    // RingBuffer::new(0) builds, then every call divides by zero (capture.rs:108): refuse it here
+    if (capacity_samples == 0) return fail(AF_ERR_INVALID, "ring capacity must be positive");
+    af_ring *r = new af_ring;
+    r->capacity = capacity_samples;
+    // pinned when a device is bound (the session copies straight out of it), plain memory otherwise: the ring is a
+    // host container, not a compute path
+    if (g_ctx.ready && cudaHostAlloc((void **)&r->buf, capacity_samples * sizeof(float), cudaHostAllocDefault) == cudaSuccess) r->pinned = true;
+    else {
+        cudaGetLastError();
+        r->buf = static_cast<float *>(malloc(capacity_samples * sizeof(float)));
+        if (!r->buf) { delete r; return fail(AF_ERR_INVALID, "out of memory for a ring of %zu samples", capacity_samples); }
+    }
+    memset(r->buf, 0, capacity_samples * sizeof(float));
+    *out = r;
+    return AF_OK;
+}
+
+AF_API void af_ring_destroy(af_ring *r)
+{
+    if (!r) return;
+    if (r->pinned) cudaFreeHost(r->buf); else free(r->buf);
+    delete r;
+}
+
+AF_API size_t af_ring_capacity(const af_ring *r) { return r ? r->capacity : 0; }
+
+// RingBuffer::write (capture.rs:101-121): keeps one slot free, drops what does not fit, returns the count written
+AF_API size_t af_ring_write(af_ring *r, const float *data, size_t n)
+{
+    if (!r || (!data && n)) return 0;
+    std::lock_guard<std::mutex> lk(r->mu);
+    const size_t w = r->write_pos.load(std::memory_order_seq_cst);
+    const size_t used = ring_used(r);
+    const size_t avail = r->capacity - used;                 // saturating_sub: used < capacity always
+    const size_t to_write = std::min(n, avail ? avail - 1 : 0);
+    const size_t first = std::min(to_write, r->capacity - w);
+    memcpy(r->buf + w, data, first * sizeof(float));
+    memcpy(r->buf, data + first, (to_write - first) * sizeof(float));
+    if (to_write) r->write_pos.store((w + to_write) % r->capacity, std::memory_order_seq_cst);
+    return to_write;
+}
+
+// RingBuffer::read (capture.rs:123-147): AF_RING_EMPTY (not an error) is the reference's None; otherwise
+// min(size, available) samples are copied out -- read(0) on a non-empty ring is Some(vec![])
+AF_API int af_ring_read(af_ring *r, float *out, size_t size, size_t *n_read)
+{
+    if (!r || !n_read || (!out && size)) return fail(AF_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(r->mu);
+    const size_t rd = r->read_pos.load(std::memory_order_seq_cst);
+    const size_t used = ring_used(r);
+    *n_read = 0;
+    if (used == 0) return AF_RING_EMPTY;
+    const size_t to_read = std::min(size, used);
+    const size_t first = std::min(to_read, r->capacity - rd);
+    memcpy(out, r->buf + rd, first * sizeof(float));
+    memcpy(out + first, r->buf, (to_read - first) * sizeof(float));
+    r->read_pos.store((rd + to_read) % r->capacity, std::memory_order_seq_cst);
+    *n_read = to_read;
+    return AF_OK;
+}
+
+AF_API size_t af_ring_available(const af_ring *r) { return r ? ring_used(r) : 0; }   // capture.rs:149-154
+
+AF_API void af_ring_clear(af_ring *r)                                                  // capture.rs:156-161
+{
+    if (!r) return;
+    std::lock_guard<std::mutex> lk(r->mu);
+    r->write_pos.store(0, std::memory_order_seq_cst);
+    r->read_pos.store(0, std::memory_order_seq_cst);
+    memset(r->buf, 0, r->capacity * sizeof(float));
+}
+
+// One session tick fed by the capture rings: takes exactly n_samples from each of the session's n_streams rings
+// (AudioCapturer::read_frame, capture.rs:310-319, for every stream at once) into the session's pinned staging rows
+// and pushes them.  Nothing is consumed unless every ring holds n_samples.
+AF_API int af_session_push_rings(af_session *s, af_ring *const *rings, uint32_t n_samples, const af_outputs *out,
+                                 uint32_t *n_pcm, uint32_t *n_feat, uint32_t *n_vad)
+{
+    if (!s || !rings) return fail(AF_ERR_INVALID, "null argument");
+    if (s->format != AF_FMT_F32) return fail(AF_ERR_INVALID, "capture rings hold f32 samples; the session was created for i16");
+    for (size_t k = 0; k < s->S; ++k) {
+        if (!rings[k]) return fail(AF_ERR_INVALID, "ring %zu is null", k);
+        const size_t have = af_ring_available(rings[k]);
+        if (have < n_samples) return fail(AF_ERR_INVALID, "ring %zu holds %zu samples, the tick needs %u", k, have, n_samples);
+    }
+    const uint64_t stride = round_up(std::max<uint32_t>(n_samples, 4), 4);
+    if (s->ring_stage_cap < stride * s->S) {
+        if (s->ring_stage) cudaFreeHost(s->ring_stage);
+        s->ring_stage = nullptr; s->ring_stage_cap = 0;
+        AF_CUDA(cudaHostAlloc((void **)&s->ring_stage, stride * s->S * sizeof(float), cudaHostAllocDefault));
+        s->ring_stage_cap = stride * s->S;
+    }
+    for (size_t k = 0; k < s->S; ++k) {
+        size_t got = 0;
+        const int rc = af_ring_read(rings[k], s->ring_stage + k * stride, n_samples, &got);
+        if (rc != AF_OK || got != n_samples) return fail(AF_ERR_INVALID, "ring %zu changed under the tick (another reader?)", k);
+    }
+    return af_session_push(s, s->ring_stage, stride, n_samples, AF_MEM_HOST, out, n_pcm, n_feat, n_vad);
 }
 
 }  // extern "C"

@@ -245,6 +245,26 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
                            const af_outputs *out, uint32_t *n_pcm, uint32_t *n_feat, uint32_t *n_vad);
 AF_API int af_session_reset(af_session *s);
 
+/* ---- RingBuffer  (src-tauri/src/modules/audio/capture.rs:84-161): capture hand-off ------ */
+/* The cpal callback writes captured f32 samples, the processing task reads them.  Same semantics as the
+ * reference: one slot stays free (capacity - 1 usable), a write drops what does not fit and returns the
+ * count written, a read returns min(size, available).  The storage is pinned host memory when a device is
+ * bound, so a session tick copies straight out of it.  Calls lock like the reference's Mutex<Vec<f32>>. */
+typedef struct af_ring af_ring;
+#define AF_RING_EMPTY (-1) /* af_ring_read: nothing available -- the reference's `None`, not an error */
+AF_API int af_ring_create(size_t capacity_samples, af_ring **out);       /* RingBuffer::new  capture.rs:91-99 */
+AF_API void af_ring_destroy(af_ring *r);
+AF_API size_t af_ring_capacity(const af_ring *r);
+AF_API size_t af_ring_write(af_ring *r, const float *data, size_t n);    /* RingBuffer::write capture.rs:101-121 */
+AF_API int af_ring_read(af_ring *r, float *out, size_t size, size_t *n_read);   /* RingBuffer::read capture.rs:123-147 */
+AF_API size_t af_ring_available(const af_ring *r);                       /* capture.rs:149-154 */
+AF_API void af_ring_clear(af_ring *r);                                   /* capture.rs:156-161 */
+/* AudioCapturer::read_frame (capture.rs:310-319) for every stream of a session at once: takes exactly
+ * n_samples from each of the n_streams rings and pushes them as one tick (af_session_push).  Nothing is
+ * consumed unless every ring holds n_samples. */
+AF_API int af_session_push_rings(af_session *s, af_ring *const *rings, uint32_t n_samples, const af_outputs *out,
+                                 uint32_t *n_pcm, uint32_t *n_feat, uint32_t *n_vad);
+
 #ifdef __cplusplus
 }
 #endif
