@@ -26,15 +26,66 @@ constexpr int YLEN = STEP_SAMPLES + CARRY;   // 5360 samples live per step
 constexpr int HALF_SPLIT = 2688;             // a step's raw input is staged in two fills: outputs [.., 2688) and [2688, YLEN)
 constexpr int TILE_FRAMES = 128;             // frames per tile (work unit of one CTA)
 constexpr int TILE_SAMPLES = TILE_FRAMES * HOP;   // 20480
-constexpr int FFT_WARPS = 16;                // warps 0..15: window + FFT + power, one frame per half-warp
-constexpr int MEL_WARPS = 4;                 // warps 16..19: mel projection + log, lane = frame
-constexpr int MEL_WARP0 = FFT_WARPS;
-constexpr int VAD_WARP = MEL_WARP0 + MEL_WARPS;   // warp 20: stage fills (TMA bulk copies) + sequential frame energies
-constexpr int RS_WARP0 = VAD_WARP + 1;       // warps 21..27: downmix + resample + PCM write-out
-constexpr int RS_WARPS = 7;                  // 224 threads: a half step (2688 outputs) is exactly three quads per thread
+constexpr int FFT_WARPS = 16;                // "F": window + FFT + power, one frame per half-warp
+constexpr int MEL_WARPS = 4;                 // "M": mel projection + log, lane = frame
+constexpr int RS_WARPS = 7;                  // "R": downmix + resample + PCM write-out.  224 threads: a half step (2688
+                                             // outputs) is exactly three quads per thread
 constexpr int RS_THREADS = RS_WARPS * 32;
-constexpr int FUSED_WARPS = RS_WARP0 + RS_WARPS;  // 28
+constexpr int FUSED_WARPS = FFT_WARPS + MEL_WARPS + 1 + RS_WARPS;   // 28 (one "V" warp: stage fills + sequential frame energies)
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;   // 896
+// Which role a hardware warp plays.  Warp w issues from scheduler (SM sub-partition) w % 4, seven warps each, and
+// addresses TMEM lane quarter w % 4.  Three layouts, chosen per launch (FusedParams::layout):
+//   0  balanced: four FFT warps per scheduler -- best with the VAD off (measured 0.580 vs 0.597 ms, cfg2)
+//   1  the V warp, whose 400-term dependent chains are the critical path with the VAD on, shares its scheduler with
+//      only two of the issue-hungry FFT warps (0.702 vs 0.750 ms)
+//   2  ... with only one
+//   3  ... with none (mel + five resampler warps)
+// In every layout mel warp j sits on scheduler j, so the TMEM columns of the mel weights do not depend on the layout.
+enum : int { ROLE_F = 0, ROLE_M = 1, ROLE_V = 2, ROLE_R = 3 };
+constexpr int N_LAYOUTS = 4;
+struct WarpRole { int role, index; };
+constexpr unsigned long long pack_layout(int layout)
+{
+    constexpr int F = ROLE_F, M = ROLE_M, V = ROLE_V, R = ROLE_R;
+    // rows = w / 4, columns = scheduler
+    constexpr int tab[N_LAYOUTS][FUSED_WARPS] = {
+        {F, F, F, F,  F, F, F, F,  F, F, F, F,  F, F, F, F,  M, M, M, M,  V, R, R, R,  R, R, R, R},
+        {V, F, F, F,  F, F, F, F,  F, F, F, F,  M, F, F, F,  R, M, M, M,  R, F, F, R,  R, R, R, R},
+        {V, F, F, F,  F, F, F, F,  M, F, F, F,  R, M, M, M,  R, F, F, F,  R, F, F, F,  R, R, R, R},
+        {V, F, F, F,  M, F, F, F,  R, F, F, F,  R, F, F, F,  R, F, F, F,  R, F, R, R,  R, M, M, M}};
+    unsigned long long m = 0;
+    for (int w = 0; w < FUSED_WARPS; ++w) m |= (unsigned long long)tab[layout][w] << (2 * w);
+    return m;
+}
+// two bits per warp, so that the kernel decodes its role from an immediate (no table in local memory)
+constexpr unsigned long long LAYOUT_BITS0 = pack_layout(0), LAYOUT_BITS1 = pack_layout(1), LAYOUT_BITS2 = pack_layout(2),
+                             LAYOUT_BITS3 = pack_layout(3);
+__host__ __device__ constexpr int warp_role_of(int layout, int w)
+{
+    const unsigned long long m = layout == 0 ? LAYOUT_BITS0 : (layout == 1 ? LAYOUT_BITS1 : (layout == 2 ? LAYOUT_BITS2 : LAYOUT_BITS3));
+    return (int)((m >> (2 * w)) & 3ull);
+}
+__host__ __device__ constexpr WarpRole warp_role(int layout, int w)
+{
+    const int r = warp_role_of(layout, w);
+    int idx = 0;
+    for (int i = 0; i < w; ++i) idx += warp_role_of(layout, i) == r ? 1 : 0;
+    return WarpRole{r, idx};
+}
+constexpr bool layouts_ok()
+{
+    for (int l = 0; l < N_LAYOUTS; ++l) {
+        int n[4] = {0, 0, 0, 0};
+        for (int w = 0; w < FUSED_WARPS; ++w) {
+            const WarpRole r = warp_role(l, w);
+            ++n[r.role];
+            if (r.role == ROLE_M && (w & 3) != r.index) return false;      // mel warp j on scheduler / TMEM quarter j
+        }
+        if (n[ROLE_F] != FFT_WARPS || n[ROLE_M] != MEL_WARPS || n[ROLE_V] != 1 || n[ROLE_R] != RS_WARPS) return false;
+    }
+    return true;
+}
+static_assert(layouts_ok(), "every layout needs 16 F, 4 M (mel warp j on scheduler j), 1 V and 7 R warps");
 
 // padded index of 16 kHz sample i inside the step buffer: 4 pad words after every 32 samples so
 // that the 32 VAD lanes (frame starts 160 apart) hit distinct bank quads with LDS.128
@@ -104,6 +155,7 @@ struct alignas(16) TileDev {
     uint32_t pad_;
     FillDesc fill[TILE_FILLS];
     StreamDev sdesc;         // copy of the stream's descriptor: one level of loads per tile instead of two
+    uint32_t inc_k, inc_rem; // position increment of RS_THREADS outputs: (RS_THREADS * p) / q and % q
 };
 static_assert(sizeof(FillDesc) == 32, "a fill descriptor is fetched with two 16-byte loads");
 static_assert(sizeof(TileDev) % 16 == 0 && offsetof(TileDev, fill) % 16 == 0, "fill descriptors must be 16-byte aligned");
@@ -182,6 +234,7 @@ struct FusedParams {
     float log_floor;
     float log_scale;         // ln(2) (natural log) or log10(2): multiplies log2(mel)
     uint32_t use_stage;      // 0: plain global loads everywhere ("sync" variant)
+    uint32_t layout;         // warp-to-role layout (warp_role)
 };
 
 }  // namespace af

@@ -82,6 +82,10 @@ __host__ __device__ inline void plan_tile(const StreamDev &s, uint32_t stream, u
     t->tile_end = tile_end;
     t->n_frames = s.n_frames; t->pad_ = 0;
     t->sdesc = s;
+    {
+        const uint32_t inc = (uint32_t)RS_THREADS * s.p;
+        t->inc_k = s.q ? inc / s.q : 0; t->inc_rem = s.q ? inc % s.q : 0;
+    }
     const uint32_t ch = s.channels, bps = s.format == FMT_I16 ? 2u : 4u;
     const uint32_t left = s.n_out - n_tile0;                       // outputs from the tile start to the stream end
     for (int j = 0; j < TILE_FILLS; ++j) {

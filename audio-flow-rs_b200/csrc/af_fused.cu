@@ -691,7 +691,7 @@ __device__ __forceinline__ void role_fft(FusedSmem &sm, const FusedParams &P, in
     const int l = lane & 15, half = lane >> 4;
     const int q = warp * 2 + half;                      // this half-warp's frame inside the step
     float *scr = sm.scr + warp * SCR_FLOATS_PER_WARP + 16 * half;
-    const uint32_t tm = sm.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);   // this warp's lane quarter
+    const uint32_t tm = sm.tmem_base + ((uint32_t)(32 * ((threadIdx.x >> 5) & 3)) << 16);   // this (hardware) warp's lane quarter
     const bool on = P.n_mels != 0;
     AF_STATS_DECL
     // no tile state here: the resampler publishes what each step buffer holds (StepInfo), including the end of the work
@@ -770,7 +770,7 @@ __device__ __forceinline__ void role_mel_run(FusedSmem &sm, const FusedParams &P
     const float log_mul = P.log_scale, log_floor = P.log_floor;
     const int q0 = sm.mel.quad_begin[mw], q1 = sm.mel.quad_begin[mw + 1];
     const int fr = pb_frame(lane);                              // frame held by power row `lane`
-    const uint32_t tm = sm.tmem_base + ((uint32_t)(32 * ((MEL_WARP0 + mw) & 3)) << 16);   // this warp's lane quarter
+    const uint32_t tm = sm.tmem_base + ((uint32_t)(32 * ((threadIdx.x >> 5) & 3)) << 16);   // this warp's lane quarter
     AF_STATS_DECL
     // no tile state here: the FFT warps forward what each power buffer holds (StepInfo), including the end of the work
     for (uint32_t it = 0;; ++it) {
@@ -942,12 +942,7 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
         nx_t.n_steps = td->n_steps;
         nx_t.n_frames = td->n_frames;
         if (lane < (int)(sizeof(StreamDev) / 4)) nx_word = reinterpret_cast<const uint32_t *>(sp)[lane];
-        if (lane == 16) {
-            nx_k = td->k0; nx_rem = td->rem0;
-            const uint32_t p = sp->p, q = sp->q;
-            const uint32_t inc = (uint32_t)RS_THREADS * p;
-            nx_inck = q ? inc / q : 0; nx_incr = q ? inc % q : 0;
-        }
+        if (lane == 16) { nx_k = td->k0; nx_rem = td->rem0; nx_inck = td->inc_k; nx_incr = td->inc_rem; }   // planned on the host
     };
     prefetch(blockIdx.x);
     for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
@@ -1066,11 +1061,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
 #pragma unroll
         for (int n1 = 0; n1 < 13; ++n1) tmem_st2(tm + TM_WIN + 2 * n1, P.fft->window[32 * n1 + 2 * l], P.fft->window[32 * n1 + 2 * l + 1]);
         tmem_wait_st();
-    } else if (warp >= MEL_WARP0 && warp < MEL_WARP0 + MEL_WARPS && P.n_mels) {
+    } else if (warp_role(P.layout, warp).role == ROLE_M && P.n_mels) {
         // every mel warp copies the weights of its resident quads into its own TMEM lane quarter: all 32 lanes (rows)
         // hold the same sixteen values per step, so that a 32x32b load hands every lane the warp-uniform weights
         const uint32_t tm = sm.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
-        const int mw = warp - MEL_WARP0;
+        const int mw = warp_role(P.layout, warp).index;
         for (int qd = sm.mel.quad_begin[mw]; qd < sm.mel.quad_begin[mw + 1]; ++qd) {
             const MelQuad &Q = sm.mel.quad[qd];
             if (Q.tcol == MEL_NO_TMEM) continue;
@@ -1084,10 +1079,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // 896 threads x 72 registers: every role fits (or nearly fits) that budget, so no setmaxnreg rebalancing
-    if (warp < FFT_WARPS) role_fft(sm, P, warp, lane);
-    else if (warp < VAD_WARP) role_mel(sm, P, warp - MEL_WARP0, lane);
-    else if (warp == VAD_WARP) role_vad(sm, P, lane);
-    else role_resample(sm, P, tid - RS_WARP0 * 32, lane);
+    const WarpRole wr = warp_role(P.layout, warp);
+    if (wr.role == ROLE_F) role_fft(sm, P, wr.index, lane);
+    else if (wr.role == ROLE_M) role_mel(sm, P, wr.index, lane);
+    else if (wr.role == ROLE_V) role_vad(sm, P, lane);
+    else role_resample(sm, P, wr.index * 32 + lane, lane);
 
     // every role has drained its pipeline: release the tensor memory
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

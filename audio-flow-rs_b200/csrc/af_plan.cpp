@@ -145,11 +145,11 @@ bool build_mel_tables(uint32_t n_mels, float f_min, float f_max, MelTables *t)
         t->quad_begin[j] = (uint16_t)q;
     }
     t->quad_begin[MEL_WARPS] = (uint16_t)n_quads;
-    // tensor-memory residence of the weights: mel warp j is warp MEL_WARP0 + j of the CTA and can only address the
-    // TMEM lane quarter (MEL_WARP0 + j) % 4; a quad takes 16 columns per step after the FFT constants
+    // tensor-memory residence of the weights: mel warp j sits on scheduler j in every layout (warp_role) and can only
+    // address the TMEM lane quarter j; a quad takes 16 columns per step after the FFT constants
     uint32_t next_col[4] = {TM_MEL0, TM_MEL0, TM_MEL0, TM_MEL0};
     for (int j = 0; j < MEL_WARPS; ++j) {
-        uint32_t &col = next_col[(MEL_WARP0 + j) & 3];
+        uint32_t &col = next_col[j & 3];
         for (uint32_t qd = t->quad_begin[j]; qd < t->quad_begin[j + 1]; ++qd) {
             const uint32_t need = 16u * t->quad[qd].c4;
             if (t->quad[qd].c4 <= 8 && col + need <= TMEM_COLS) { t->quad[qd].tcol = col; col += need; }

@@ -97,6 +97,15 @@ int require_ctx()
     return AF_OK;
 }
 
+// warp-to-role layout of the fused kernel (warp_role, af_common.cuh): the V warp gets a lighter scheduler when it
+// has energy chains to run.  AF_LAYOUT=<n> overrides (experiments).
+uint32_t fused_layout(bool energies)
+{
+    static const int forced = [] { const char *e = getenv("AF_LAYOUT"); return e ? atoi(e) : -1; }();
+    if (forced >= 0 && forced < N_LAYOUTS) return (uint32_t)forced;
+    return energies ? 2u : 0u;
+}
+
 inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // exact output length of BatchResampler::process(all) + flush() and (optionally) the frac table
@@ -742,6 +751,7 @@ int run_sub(af_batch *b, SubBatch &sb, float *pcm, uint64_t pcm_stride, float *l
         P.log_floor = cfg.log_floor;
         P.log_scale = cfg.log10 ? 0.30102999566398120f : 0.69314718055994531f;   // log10(2) : ln(2)
         P.use_stage = g_ctx.variant == "sync" ? 0u : 1u;
+        P.layout = fused_layout(stft_vad);
         const int n_ctas = (int)std::min<size_t>(sb.h_tiles.size(), (size_t)g_ctx.sm_count);   // one persistent CTA per SM
         AF_CUDA(launch_fused(P, n_ctas, st));
         count_launch();
@@ -1293,6 +1303,7 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
             P.log_floor = cfg.log_floor;
             P.log_scale = cfg.log10 ? 0.30102999566398120f : 0.69314718055994531f;
             P.use_stage = g_ctx.variant == "sync" ? 0u : 1u;
+            P.layout = fused_layout(P.do_energy != 0);
             if (P.n_mels || P.do_energy) {
                 AF_CUDA(launch_fused(P, (int)std::min<size_t>(S, (size_t)g_ctx.sm_count), st));
                 count_launch(2);
