@@ -126,6 +126,11 @@ def load_library():
         "af_session_push": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(OutputsC),
                                       C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "af_session_reset": (C.c_int, [vp]),
+        "af_ring_create": (C.c_int, [sz, C.POINTER(vp)]), "af_ring_destroy": (None, [vp]),
+        "af_ring_capacity": (sz, [vp]), "af_ring_write": (sz, [vp, fp, sz]),
+        "af_ring_read": (C.c_int, [vp, fp, sz, szp]), "af_ring_available": (sz, [vp]), "af_ring_clear": (None, [vp]),
+        "af_session_push_rings": (C.c_int, [vp, C.POINTER(vp), C.c_uint32, C.POINTER(OutputsC),
+                                            C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -510,11 +515,8 @@ class Session:
     def reset(self):
         _check(load_library().af_session_reset(self._h))
 
-    def push(self, x: np.ndarray) -> dict:
+    def _tick(self, call) -> dict:
         cfg = self.pipe.cfg
-        x = np.ascontiguousarray(x, dtype=np.int16 if self.fmt == AF_FMT_I16 else np.float32)
-        assert x.ndim == 2 and x.shape[0] == self.S
-        n = x.shape[1]
         M = max(cfg.n_mels, 1)
         pcm = np.zeros((self.S, (self.max_pcm + 3) // 4 * 4), np.float32)
         lm = np.zeros((self.S, (self.max_T * M + 3) // 4 * 4), np.float32)
@@ -525,10 +527,62 @@ class Session:
                      C.addressof(fin) if cfg.vad_enable else None)
         u32p = C.POINTER(C.c_uint32)
         npcm, nf, nv = (np.zeros(self.S, np.uint32) for _ in range(3))
-        _check(load_library().af_session_push(self._h, x.ctypes.data, n, n, AF_MEM_HOST, C.byref(o),
-                                              npcm.ctypes.data_as(u32p), nf.ctypes.data_as(u32p), nv.ctypes.data_as(u32p)))
+        _check(call(C.byref(o), npcm.ctypes.data_as(u32p), nf.ctypes.data_as(u32p), nv.ctypes.data_as(u32p)))
         T = int(max(nf[0], nv[0]))
         return {"pcm": pcm[:, :npcm[0]].copy(), "logmel": lm[:, :int(nf[0]) * M].reshape(self.S, int(nf[0]), M).copy(),
                 "vad": vad[:, :int(nv[0])].copy(), "n_frames": T,
                 "vad_final": [dict(state=int(f.state), smoothed=float(f.smoothed_energy), speech_frames=int(f.speech_frames))
                               for f in fin]}
+
+    def push(self, x: np.ndarray) -> dict:
+        x = np.ascontiguousarray(x, dtype=np.int16 if self.fmt == AF_FMT_I16 else np.float32)
+        assert x.ndim == 2 and x.shape[0] == self.S
+        n = x.shape[1]
+        L = load_library()
+        return self._tick(lambda o, a, b, c: L.af_session_push(self._h, x.ctypes.data, n, n, AF_MEM_HOST, o, a, b, c))
+
+    def push_rings(self, rings, n_samples: int) -> dict:
+        """One tick fed by the capture rings (AudioCapturer::read_frame for every stream, capture.rs:310-319)."""
+        assert len(rings) == self.S
+        arr = (C.c_void_p * self.S)(*[r._h for r in rings])
+        L = load_library()
+        return self._tick(lambda o, a, b, c: L.af_session_push_rings(self._h, arr, n_samples, o, a, b, c))
+
+
+# ---------------------------------------------------------------------------------------------
+# RingBuffer (capture.rs:84-161): the capture hand-off, same method names and semantics
+# ---------------------------------------------------------------------------------------------
+AF_RING_EMPTY = -1
+
+
+class RingBuffer:
+    def __init__(self, capacity_samples: int):
+        h = C.c_void_p()
+        _check(load_library().af_ring_create(capacity_samples, C.byref(h)))
+        self._h = h
+        self.capacity = int(load_library().af_ring_capacity(h))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.af_ring_destroy(self._h)
+            self._h = None
+
+    def write(self, data) -> int:
+        a = np.ascontiguousarray(data, dtype=np.float32)
+        return int(load_library().af_ring_write(self._h, a.ctypes.data_as(C.POINTER(C.c_float)), a.size))
+
+    def read(self, size: int):
+        """None when nothing is available, else an array of min(size, available) samples."""
+        out = np.empty(max(size, 1), np.float32)
+        n = C.c_size_t(0)
+        rc = load_library().af_ring_read(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), size, C.byref(n))
+        if rc == AF_RING_EMPTY:
+            return None
+        _check(rc)
+        return out[:n.value].copy()
+
+    def available(self) -> int:
+        return int(load_library().af_ring_available(self._h))
+
+    def clear(self):
+        load_library().af_ring_clear(self._h)

@@ -109,6 +109,33 @@ private:
     uint32_t in_, out_;
 };
 
+// capture.rs:84-161 -- the capture hand-off.  write() keeps one slot free and returns the count written; read() returns
+// nothing (the reference's None) on an empty ring, else min(size, available) samples.
+class RingBuffer {
+public:
+    explicit RingBuffer(size_t capacity_samples) { check(af_ring_create(capacity_samples, &h_)); capacity = af_ring_capacity(h_); }
+    RingBuffer(const RingBuffer &) = delete;
+    ~RingBuffer() { if (h_) af_ring_destroy(h_); }
+    size_t write(const std::vector<float> &data) { return af_ring_write(h_, data.data(), data.size()); }
+    bool read(size_t size, std::vector<float> *out)
+    {
+        out->assign(size, 0.0f);
+        size_t n = 0;
+        const int rc = af_ring_read(h_, out->data(), size, &n);
+        if (rc == AF_RING_EMPTY) { out->clear(); return false; }
+        check(rc);
+        out->resize(n);
+        return true;
+    }
+    size_t available() const { return af_ring_available(h_); }
+    void clear() { af_ring_clear(h_); }
+    af_ring *handle() { return h_; }
+    size_t capacity = 0;
+
+private:
+    af_ring *h_ = nullptr;
+};
+
 // vad.rs:8-54
 enum class VadLevel { Aggressive, Balanced, Relaxed };
 enum class VadState { Silence = 0, Speech = 1, Ending = 2 };

@@ -20,7 +20,17 @@ pub struct af_vad_config {
 
 pub const AF_OK: c_int = 0;
 
+#[repr(C)] pub struct af_ring { _private: [u8; 0] }
+pub const AF_RING_EMPTY: c_int = -1;
+
 extern "C" {
+    pub fn af_ring_create(capacity_samples: usize, out: *mut *mut af_ring) -> c_int;
+    pub fn af_ring_destroy(r: *mut af_ring);
+    pub fn af_ring_write(r: *mut af_ring, data: *const f32, n: usize) -> usize;
+    pub fn af_ring_read(r: *mut af_ring, out: *mut f32, size: usize, n_read: *mut usize) -> c_int;
+    pub fn af_ring_available(r: *const af_ring) -> usize;
+    pub fn af_ring_clear(r: *mut af_ring);
+
     pub fn af_init(device: c_int) -> c_int;
     pub fn af_last_error(buf: *mut c_char, cap: usize) -> usize;
 

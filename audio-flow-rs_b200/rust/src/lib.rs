@@ -135,6 +135,37 @@ impl Drop for BatchResampler {
     fn drop(&mut self) { unsafe { ffi::af_batch_resampler_destroy(self.h) } }
 }
 
+/// capture.rs:84-161 -- same `&self` methods as the reference (it locks internally); shared across threads with `Arc`.
+pub struct RingBuffer {
+    h: *mut ffi::af_ring,
+    pub capacity: usize,
+}
+unsafe impl Send for RingBuffer {}
+unsafe impl Sync for RingBuffer {}
+
+impl RingBuffer {
+    pub fn new(capacity_samples: usize) -> Self {
+        let mut h = ptr::null_mut();
+        let rc = unsafe { ffi::af_ring_create(capacity_samples, &mut h) };
+        assert!(rc == 0, "RingBuffer::new({capacity_samples})");
+        Self { h, capacity: capacity_samples }
+    }
+    pub fn write(&self, data: &[f32]) -> usize { unsafe { ffi::af_ring_write(self.h, data.as_ptr(), data.len()) } }
+    pub fn read(&self, size: usize) -> Option<Vec<f32>> {
+        let mut out = vec![0.0f32; size];
+        let mut n = 0usize;
+        let rc = unsafe { ffi::af_ring_read(self.h, out.as_mut_ptr(), size, &mut n) };
+        if rc == ffi::AF_RING_EMPTY { return None; }
+        out.truncate(n);
+        Some(out)
+    }
+    pub fn available(&self) -> usize { unsafe { ffi::af_ring_available(self.h) } }
+    pub fn clear(&self) { unsafe { ffi::af_ring_clear(self.h) } }
+}
+impl Drop for RingBuffer {
+    fn drop(&mut self) { unsafe { ffi::af_ring_destroy(self.h) } }
+}
+
 /// vad.rs:8-17
 #[derive(Debug, Clone, Copy, PartialEq, Eq, Default)]
 pub enum VadLevel { #[default] Aggressive, Balanced, Relaxed }

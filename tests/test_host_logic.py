@@ -111,3 +111,59 @@ def test_vad_threshold_edge_cases():
     assert np.isnan(L.af_debug_vad_energy_threshold(float("inf")))
     tiny = np.float32(L.af_debug_vad_energy_threshold(float("-inf")))
     assert tiny.view(np.uint32) == 1          # any positive energy is speech; 0 is not
+
+
+# ---- RingBuffer (capture.rs:84-161): the reference's own tests, capture.rs:425-515 and :547-560 ----
+def test_ring_buffer_reference_tests():
+    import threading
+    import audioflow as af
+    b = af.RingBuffer(1024)
+    assert b.capacity == 1024                                             # test_ring_buffer_new
+    assert b.write([1.0, 2.0, 3.0]) == 3                                  # test_ring_buffer_write_read
+    assert b.read(3).tolist() == [1.0, 2.0, 3.0]
+    b = af.RingBuffer(1024)                                               # test_ring_buffer_partial_read
+    b.write([1.0, 2.0, 3.0, 4.0, 5.0])
+    assert b.read(2).tolist() == [1.0, 2.0]
+    assert b.read(3).tolist() == [3.0, 4.0, 5.0]
+    b = af.RingBuffer(10)                                                 # test_ring_buffer_wrap_around
+    b.write([1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0])
+    b.read(5)
+    b.write([8.0, 9.0, 10.0])
+    assert b.read(5).tolist() == [6.0, 7.0, 8.0, 9.0, 10.0]
+    b = af.RingBuffer(10)                                                 # test_ring_buffer_overflow: one slot stays free
+    assert b.write([1.0] * 20) == 9
+    r = b.read(9)
+    assert len(r) == 9 and r.tolist() == [1.0] * 9
+    assert af.RingBuffer(1024).read(100) is None                          # test_ring_buffer_read_empty
+    b = af.RingBuffer(1024)                                               # test_ring_buffer_available
+    assert b.available() == 0
+    b.write([1.0] * 100)
+    assert b.available() == 100
+    b.read(50)
+    assert b.available() == 50
+    b.clear()                                                             # test_ring_buffer_clear
+    assert b.available() == 0
+    b = af.RingBuffer(1024)                                               # test_ring_buffer_thread_safe
+    t = threading.Thread(target=lambda: b.write([1.0, 2.0, 3.0]))
+    t.start(); t.join()
+    assert b.read(3).tolist() == [1.0, 2.0, 3.0]
+
+
+def test_ring_buffer_edges():
+    import audioflow as af
+    b = af.RingBuffer(4)
+    assert b.write([]) == 0 and b.read(0) is None                          # empty ring: None even for read(0)
+    assert b.write([1.0, 2.0, 3.0, 4.0]) == 3                              # capacity - 1 usable
+    assert b.write([9.0]) == 0                                             # full: dropped
+    assert len(b.read(0)) == 0                                             # Some(vec![]) on a non-empty ring
+    assert b.read(10).tolist() == [1.0, 2.0, 3.0]
+    # many wraps keep the order
+    b = af.RingBuffer(7)
+    nxt, got = 0.0, []
+    for _ in range(50):
+        w = b.write([nxt + i for i in range(5)])
+        nxt += w
+        got += b.read(3).tolist()
+    assert got == [float(i) for i in range(len(got))]
+    with pytest.raises(Exception):
+        af.RingBuffer(0)                                                  # the reference would divide by zero on first use

@@ -69,3 +69,36 @@ def test_session_reset_and_20ms_vad(af, orc):
             st, _ = orc.VoiceActivityDetector().stream(ref_pcm, 320, 320)
             assert_bit_equal(np.concatenate(vad[i]), st, f"rep {rep} stream {i}")
         ses.reset()
+
+
+def test_session_fed_by_capture_rings(af, orc):
+    """The capture hand-off (RingBuffer, capture.rs:84-161 -> AudioCapturer::read_frame, capture.rs:310-319): producer
+    chunks of uneven size go into one ring per stream, ticks of 960 samples come out; the session must produce exactly
+    what pushing the same samples directly produces, and a tick must consume nothing unless every ring can serve it."""
+    from audioflow import synth
+    S, tick, n_ticks, rate = 4, 960, 12, 48000
+    xs = [synth.stream(90 + i, tick * n_ticks / rate + 0.01, rate, 1)[: tick * n_ticks] for i in range(S)]
+    pipe = af.Pipeline(af.pipeline_config(n_mels=80))
+    direct = af.Session(pipe, S, rate, 1, af.AF_FMT_F32, max_tick_samples=tick)
+    ringed = af.Session(pipe, S, rate, 1, af.AF_FMT_F32, max_tick_samples=tick)
+    rings = [af.RingBuffer(4096) for _ in range(S)]
+    fed = [0] * S
+    rng = np.random.default_rng(5)
+    for t in range(n_ticks):
+        # cpal-style producer: irregular callback sizes until every ring holds a tick
+        while min(r.available() for r in rings) < tick:
+            for i in range(S):
+                n = int(rng.integers(100, 700))
+                n = min(n, len(xs[i]) - fed[i])
+                fed[i] += rings[i].write(xs[i][fed[i]:fed[i] + n])
+        a = direct.push(np.stack([xs[i][t * tick:(t + 1) * tick] for i in range(S)]))
+        b = ringed.push_rings(rings, tick)
+        for k in ("pcm", "logmel", "vad"):
+            assert_bit_equal(a[k], b[k], f"tick {t} {k}")
+    # a ring that cannot serve the tick: error, nothing consumed anywhere
+    before = [r.available() for r in rings]
+    rings[2].clear()
+    before[2] = 0
+    with pytest.raises(ValueError):                     # AF_ERR_INVALID
+        ringed.push_rings(rings, tick)
+    assert [r.available() for r in rings] == before
