@@ -897,9 +897,13 @@ AF_API int af_batch_create(af_pipeline *p, const af_stream_desc *streams, size_t
         b->subs[0].first = 0; b->subs[0].count = n_streams;
         if (n_streams) { rc = build_sub(b.get(), b->subs[0], nullptr); if (rc) return rc; }
     } else {
-        // host mode: groups of streams of ~96 MB input, cycled through 3 slots so that the H2D copy of
+        // host mode: groups of streams of ~32 MB input (measured: 96 MB 29.4 ms, 32 MB 28.3 ms per cfg2 batch against a
+        // PCIe ceiling of 28.1 ms on the box), cycled through 3 slots so that the H2D copy of
         // group g+1, the kernels of group g and the D2H copy of group g-1 overlap
-        const size_t target = 96ull << 20;
+        // (AF_HOST_SUB_MB / AF_HOST_SLOTS override the defaults: experiments)
+        static const size_t sub_mb = [] { const char *e = getenv("AF_HOST_SUB_MB"); return e ? (size_t)atoi(e) : (size_t)32; }();
+        static const size_t want_slots = [] { const char *e = getenv("AF_HOST_SLOTS"); return e ? (size_t)atoi(e) : (size_t)3; }();
+        const size_t target = std::max<size_t>(sub_mb, 1) << 20;
         size_t i = 0;
         while (i < n_streams) {
             SubBatch sb;
@@ -918,7 +922,7 @@ AF_API int af_batch_create(af_pipeline *p, const af_stream_desc *streams, size_t
         size_t max_rows = 0, max_in = 0;
         for (auto &sb : b->subs) { max_rows = std::max(max_rows, sb.count); max_in = std::max(max_in, sb.in_bytes); }
         b->slot_rows = max_rows;
-        const size_t n_slots = std::min<size_t>(3, std::max<size_t>(1, b->subs.size()));
+        const size_t n_slots = std::min<size_t>(std::max<size_t>(want_slots, 1), std::max<size_t>(1, b->subs.size()));
         b->slots.resize(n_slots);
         for (auto &s : b->slots) {
             AF_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
@@ -1012,10 +1016,19 @@ AF_API int af_batch_run_host(af_batch *b, const af_outputs *o)
         SubBatch &sb = b->subs[g];
         af_batch::Slot &sl = b->slots[g % n_slots];
         cudaStream_t st = sl.st;
-        for (size_t i = 0; i < sb.count; ++i) {
-            const af_stream_desc &d = b->streams[sb.first + i].desc;
-            const size_t sz = d.n_samples * (d.format == AF_FMT_I16 ? 2 : 4);
-            if (sz) AF_CUDA(cudaMemcpyAsync((char *)sl.d_in + sb.in_off[i], d.data, sz, cudaMemcpyHostToDevice, st));
+        // host -> device: one copy per run of streams that are contiguous on both sides (rows of one host array are)
+        for (size_t i = 0; i < sb.count;) {
+            const af_stream_desc &d0 = b->streams[sb.first + i].desc;
+            size_t bytes = d0.n_samples * (d0.format == AF_FMT_I16 ? 2 : 4);
+            size_t j = i + 1;
+            while (j < sb.count) {
+                const af_stream_desc &dj = b->streams[sb.first + j].desc;
+                if ((const char *)dj.data != (const char *)d0.data + bytes || sb.in_off[j] != sb.in_off[i] + bytes) break;
+                bytes += dj.n_samples * (dj.format == AF_FMT_I16 ? 2 : 4);
+                ++j;
+            }
+            if (bytes) AF_CUDA(cudaMemcpyAsync((char *)sl.d_in + sb.in_off[i], d0.data, bytes, cudaMemcpyHostToDevice, st));
+            i = j;
         }
         const bool need_pcm = (cfg.write_pcm && o->pcm) || (cfg.vad_enable && cfg.vad_frame_len != 0);
         rc = run_sub(b, sb, need_pcm ? sl.d_pcm : nullptr, b->pcm_stride, sl.d_logmel, b->logmel_stride, sl.d_vad,

@@ -492,7 +492,7 @@ def main():
         e2e = {"value": world * args.e2e_steps * audio_s_per_step_rank / dt, "unit": "audio-s/s",
                "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": d2h,
                "ms_per_step": 1e3 * dt / args.e2e_steps,
-               "note": "af_batch_run_host: pinned host PCM in, PCM + log-mel back on the host; 3-slot H2D/compute/D2H overlap"}
+               "note": "af_batch_run_host: pinned host PCM in, PCM + log-mel back on the host; 3-slot H2D/compute/D2H overlap over ~32 MB groups of streams, one H2D copy per contiguous run of host rows (PCIe ceiling of the box, tools/pcie_probe.py: 28.1 ms for these bytes)"}
         # spot-check of the e2e result against the device-resident run
         lm_host = np.ctypeslib.as_array(C.cast(pl, C.POINTER(C.c_float)), shape=(S, hb.logmel_stride))
         T = int(hb.n_feat[0])
