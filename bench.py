@@ -504,9 +504,9 @@ def main():
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, dt = cpu_pipeline_rate(64, SECONDS)
+        v, cores, dt = cpu_pipeline_rate(S, SECONDS, repeats=3)      # ~10-30 s of CPU work on a 16-thread box
         cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
-               "sample": f"64 of the {S} streams x {SECONDS:.0f} s (all {cores} host threads, {dt:.1f} s wall); " + PORT_NOTE}
+               "sample": f"all {S} streams x {SECONDS:.0f} s, best of 3 passes (all {cores} host threads, {dt:.1f} s wall per pass); " + PORT_NOTE}
 
     if rank == 0:
         line = {
