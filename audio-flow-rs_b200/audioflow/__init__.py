@@ -126,6 +126,8 @@ def load_library():
         "af_session_push": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(OutputsC),
                                       C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "af_session_reset": (C.c_int, [vp]),
+        "af_session_enable_levels": (C.c_int, [vp, C.c_int]),
+        "af_session_levels": (C.c_int, [vp, fp, fp, u8p]),
         "af_ring_create": (C.c_int, [sz, C.POINTER(vp)]), "af_ring_destroy": (None, [vp]),
         "af_ring_capacity": (sz, [vp]), "af_ring_write": (sz, [vp, fp, sz]),
         "af_ring_read": (C.c_int, [vp, fp, sz, szp]), "af_ring_available": (sz, [vp]), "af_ring_clear": (None, [vp]),
@@ -540,6 +542,16 @@ class Session:
         n = x.shape[1]
         L = load_library()
         return self._tick(lambda o, a, b, c: L.af_session_push(self._h, x.ctypes.data, n, n, AF_MEM_HOST, o, a, b, c))
+
+    def enable_levels(self, on: bool = True):
+        _check(load_library().af_session_enable_levels(self._h, 1 if on else 0))
+
+    def levels(self) -> dict:
+        """AudioLevel / VolumeLevel payloads of the last tick: level_db (energy_db()), peak (max |y|), is_speech."""
+        lv, pk, sp = np.zeros(self.S, np.float32), np.zeros(self.S, np.float32), np.zeros(self.S, np.uint8)
+        _check(load_library().af_session_levels(self._h, lv.ctypes.data_as(C.POINTER(C.c_float)),
+                                                pk.ctypes.data_as(C.POINTER(C.c_float)), sp.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return {"level_db": lv, "peak": pk, "is_speech": sp.astype(bool)}
 
     def push_rings(self, rings, n_samples: int) -> dict:
         """One tick fed by the capture rings (AudioCapturer::read_frame for every stream, capture.rs:310-319)."""

@@ -568,6 +568,27 @@ cudaError_t launch_session_setup(StreamDev *tab, TileDev *tiles, uint32_t n_stre
     return cudaGetLastError();
 }
 
+// ---- level metering (events/mod.rs:41 AudioLevel{level, peak}): peak = max |y| over the tick's new 16 kHz samples ----
+// One warp per stream; max is order-independent, so the result is bit-exact against any reference order.
+__global__ void af_peak_kernel(const float *__restrict__ y, uint64_t y_stride, uint32_t n, uint32_t n_streams, float *__restrict__ peak)
+{
+    const uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= n_streams) return;
+    const float *row = y + (uint64_t)s * y_stride;
+    float m = 0.0f;
+    for (uint32_t i = lane; i < n; i += 32) m = fmaxf(m, fabsf(row[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) peak[s] = m;
+}
+
+cudaError_t launch_peak(const float *y, uint64_t y_stride, uint32_t n, uint32_t n_streams, float *peak, cudaStream_t st)
+{
+    if (n_streams == 0) return cudaSuccess;
+    af_peak_kernel<<<(n_streams + 3) / 4, 128, 0, st>>>(y, y_stride, n, n_streams, peak);
+    return cudaGetLastError();
+}
+
 // ---- f32 -> PCM16 little endian (websocket.rs:246-251): (x.clamp(-1,1) * 32767.0) as i16 ----
 __global__ void af_pcm16_kernel(const float *__restrict__ in, uint64_t n, int16_t *__restrict__ out)
 {

@@ -59,6 +59,7 @@ cudaError_t launch_session_resample(const SessionResample &J, uint32_t n_streams
 cudaError_t launch_session_setup(StreamDev *tab, TileDev *tiles, uint32_t n_streams, uint32_t n, uint32_t n_frames, uint32_t n_vad,
                                  cudaStream_t st);
 cudaError_t launch_fused(const FusedParams &P, int n_ctas, cudaStream_t st);
+cudaError_t launch_peak(const float *y, uint64_t y_stride, uint32_t n, uint32_t n_streams, float *peak, cudaStream_t st);
 
 cudaError_t launch_to_mono(const float *in, uint64_t n_samples, uint32_t channels, float *out, uint64_t n_frames,
                            cudaStream_t st);

@@ -1114,6 +1114,10 @@ struct af_session {
     std::vector<float> frac_host;
     uint64_t frames_emitted = 0;
     float *ring_stage = nullptr; size_t ring_stage_cap = 0;   // pinned rows for af_session_push_rings
+    // level metering (af_session_enable_levels): peak of the last tick per stream + the detector states, on the host
+    bool levels = false, levels_valid = false;
+    float *d_peak = nullptr, *h_peak = nullptr;
+    VadState *h_vad = nullptr;
 };
 
 extern "C" {
@@ -1135,6 +1139,9 @@ AF_API void af_session_destroy(af_session *s)
     if (s->d_lm) cudaFree(s->d_lm);
     if (s->d_states) cudaFree(s->d_states);
     if (s->ring_stage) cudaFreeHost(s->ring_stage);
+    if (s->d_peak) cudaFree(s->d_peak);
+    if (s->h_peak) cudaFreeHost(s->h_peak);
+    if (s->h_vad) cudaFreeHost(s->h_vad);
     delete s;
 }
 
@@ -1282,6 +1289,11 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
                                   (size_t)n_y_new * sizeof(float), S,
                                   mem == AF_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
 
+    if (s->levels) {
+        AF_CUDA(launch_peak(ycur + s->y_len, s->y_stride, n_y_new, (uint32_t)S, s->d_peak, st));
+        count_launch();
+    }
+
     // ---- 4. frames that became complete: features + VAD ----
     uint32_t T = 0;
     if (s->framing && y_total >= s->frame_len) T = 1 + (y_total - s->frame_len) / s->hop;
@@ -1346,7 +1358,12 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
                 AF_CUDA(cudaMemcpyAsync(o->vad_final, s->d_vad, S * sizeof(VadState), cudaMemcpyDeviceToHost, st));
         }
     }
+    if (s->levels) {
+        AF_CUDA(cudaMemcpyAsync(s->h_peak, s->d_peak, S * sizeof(float), cudaMemcpyDeviceToHost, st));
+        AF_CUDA(cudaMemcpyAsync(s->h_vad, s->d_vad, S * sizeof(VadState), cudaMemcpyDeviceToHost, st));
+    }
     AF_CUDA(cudaStreamSynchronize(st));
+    s->levels_valid = s->levels;
 
     // ---- 5. bookkeeping: drop the consumed chunks and the samples every future frame starts after ----
     if (!s->rec.passthrough) {
@@ -1388,6 +1405,42 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
         if (n_pcm) n_pcm[k] = n_y_new;
         if (n_feat) n_feat[k] = cfg.n_mels ? T : 0;
         if (n_vad) n_vad[k] = cfg.vad_enable ? T : 0;
+    }
+    return AF_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// level metering for the UI events (events/mod.rs:41,73-75 AudioLevel{level, peak}; modules/events/mod.rs:22,182-185
+// VolumeLevel{level, is_speech}): by-products of a session tick
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+AF_API int af_session_enable_levels(af_session *s, int enable)
+{
+    if (!s) return fail(AF_ERR_INVALID, "null session");
+    if (enable && !s->d_peak) {
+        AF_CUDA(cudaMalloc(&s->d_peak, s->S * sizeof(float)));
+        AF_CUDA(cudaHostAlloc((void **)&s->h_peak, s->S * sizeof(float), cudaHostAllocDefault));
+        AF_CUDA(cudaHostAlloc((void **)&s->h_vad, s->S * sizeof(VadState), cudaHostAllocDefault));
+    }
+    s->levels = enable != 0;
+    s->levels_valid = false;
+    return AF_OK;
+}
+
+AF_API int af_session_levels(const af_session *s, float *level_db, float *peak, uint8_t *is_speech)
+{
+    if (!s) return fail(AF_ERR_INVALID, "null session");
+    if (!s->levels_valid) return fail(AF_ERR_INVALID, "no tick has been pushed since af_session_enable_levels");
+    const bool vad = s->pipe->cfg.vad_enable != 0;
+    for (size_t k = 0; k < s->S; ++k) {
+        if (peak) peak[k] = s->h_peak[k];
+        // VoiceActivityDetector::energy_db (vad.rs:192-194) through energy_to_dbfs (vad.rs:171-176), host libm
+        const float e = vad ? s->h_vad[k].smoothed : 0.0f;
+        if (level_db) level_db[k] = e <= 0.0f ? -INFINITY : 20.0f * log10f(e);
+        if (is_speech) is_speech[k] = (vad && s->h_vad[k].state == 1) ? 1 : 0;          // is_speaking, vad.rs:197-199
     }
     return AF_OK;
 }

@@ -245,6 +245,16 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
                            const af_outputs *out, uint32_t *n_pcm, uint32_t *n_feat, uint32_t *n_vad);
 AF_API int af_session_reset(af_session *s);
 
+/* ---- level metering for the UI events ---------------------------------------------------- */
+/* AudioLevel{level, peak} (src-tauri/src/events/mod.rs:41,73-75) and VolumeLevel{level, is_speech}
+ * (src-tauri/src/modules/events/mod.rs:22,182-185) as by-products of a session tick.  The reference only declares
+ * the payloads; the values are defined here: level_db = VoiceActivityDetector::energy_db() (vad.rs:192-194:
+ * 20*log10 of the smoothed energy after the tick's last frame, -inf when it is <= 0 or the VAD is off),
+ * peak = max |y| over the 16 kHz samples the tick produced (0 if none), is_speech = is_speaking() (vad.rs:197-199).
+ * Enable once, then read after every push; host arrays of n_streams, any may be NULL. */
+AF_API int af_session_enable_levels(af_session *s, int enable);
+AF_API int af_session_levels(const af_session *s, float *level_db, float *peak, uint8_t *is_speech);
+
 /* ---- RingBuffer  (src-tauri/src/modules/audio/capture.rs:84-161): capture hand-off ------ */
 /* The cpal callback writes captured f32 samples, the processing task reads them.  Same semantics as the
  * reference: one slot stays free (capacity - 1 usable), a write drops what does not fit and returns the

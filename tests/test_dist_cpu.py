@@ -41,6 +41,11 @@ def _worker(rank, world, port, q):
         states[j, : i + 1] = i % 3
         nf[j] = i + 1
     st, n = shard.gather_vad(states, nf)
+    # the planned exchange (sizes and counts once, one collective per step) must deliver the same thing, repeatedly
+    g = shard.VadGather(hi - lo, 16, nf, torch.device("cpu"))
+    for rep in range(2):
+        st2 = g.run(states)
+        assert torch.equal(st2, st) and torch.equal(g.n_frames, n)
     q.put((rank, (lo, hi), st.numpy().copy(), n.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()

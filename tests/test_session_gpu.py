@@ -102,3 +102,33 @@ def test_session_fed_by_capture_rings(af, orc):
     with pytest.raises(ValueError):                     # AF_ERR_INVALID
         ringed.push_rings(rings, tick)
     assert [r.available() for r in rings] == before
+
+
+def test_session_levels(af, orc):
+    """AudioLevel{level, peak} / VolumeLevel{level, is_speech} (events/mod.rs:41, modules/events/mod.rs:22) per tick:
+    level = energy_db() and is_speech = is_speaking() of the reference detector fed the same frames (vad.rs:192-199),
+    peak = max |y| of the tick's 16 kHz samples -- all three bit-exact."""
+    from audioflow import synth
+    S, tick, n_ticks, rate = 3, 960, 30, 48000
+    xs = [synth.stream(120 + i, tick * n_ticks / rate + 0.01, rate, 1)[: tick * n_ticks] for i in range(S)]
+    ses = af.Session(af.Pipeline(af.pipeline_config(n_mels=80)), S, rate, 1, af.AF_FMT_F32, max_tick_samples=tick)
+    with pytest.raises(ValueError):
+        ses.levels()                                              # not enabled / no tick yet
+    ses.enable_levels()
+    dets = [orc.VoiceActivityDetector() for _ in range(S)]
+    carry = [np.zeros(0, np.float32) for _ in range(S)]
+    for t in range(n_ticks):
+        r = ses.push(np.stack([xs[i][t * tick:(t + 1) * tick] for i in range(S)]))
+        lv = ses.levels()
+        for i in range(S):
+            y = r["pcm"][i]
+            want_peak = np.float32(np.max(np.abs(y))) if len(y) else np.float32(0)
+            assert lv["peak"][i].view(np.uint32) == want_peak.view(np.uint32)
+            carry[i] = np.concatenate([carry[i], y])
+            while len(carry[i]) >= 400:                           # the detector sees every completed 25 ms / 10 ms frame
+                dets[i].detect(carry[i][:400])
+                carry[i] = carry[i][160:]
+            want_db = np.float32(dets[i].energy_db())
+            got_db = lv["level_db"][i]
+            assert (np.isneginf(want_db) and np.isneginf(got_db)) or got_db.view(np.uint32) == want_db.view(np.uint32), (t, i, got_db, want_db)
+            assert bool(lv["is_speech"][i]) == dets[i].is_speaking()
