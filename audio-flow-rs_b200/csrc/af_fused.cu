@@ -340,36 +340,19 @@ struct YSink {
     }
 };
 
-// ---- resampling, interior half steps: every tap comes unchecked from the stage (or the stream) ----
-template <int KIND, bool STAGED>
-__device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, const RsTile &rt, int h, const StreamDev &s, const YSink &out,
-                                                   uint32_t tile_off, int i_lo, int i_hi, int rtid)
+// ---- the hot resampling loop: 48 kHz -> 16 kHz mono f32, interior half step, taps in the stage ----
+// x0 points at the tap y0 of step-buffer sample 0 (output n reads x0[3n .. 3n+3]); outputs [i_lo, i_hi) of the step go
+// to yb (padded) and to pq0[i] (the PCM row, nullptr-based offsets never dereferenced when lim4 is the "no PCM" value).
+__device__ __forceinline__ void resample_quads_48k(const float *__restrict__ x0, float *__restrict__ yb, float *pq0, int lim4,
+                                                   int i_lo, int i_hi, int rtid)
 {
-    // taps come from the shared-memory stage (first staged mono frame f_lo) or, when the half step does not fit the
-    // stage (e.g. stereo f32), unchecked from the stream in global memory (f_lo = 0)
-    const unsigned char *__restrict__ srcp = STAGED ? sm.stage[h] : reinterpret_cast<const unsigned char *>(s.data);
-    const int f_lo = STAGED ? (int)((uint32_t)sm.st_lo[h] / ((KIND == K_F32_2 || KIND == K_I16_2) ? 2u : 1u)) : 0;
-    const uint32_t mode = s.mode;
-    int i = i_lo + rtid;
-    if (mode == RS_PASSTHROUGH) {
-        for (; i < i_hi; i += RS_THREADS) out.put(i, tap_fast<KIND>(srcp, (int)(out.base + i) - f_lo));
-        return;
-    }
-    const uint32_t q = s.q;
-    if (KIND == K_F32_1 && q == 1 && s.p == 3) {
-        // 48 kHz -> 16 kHz mono f32, four outputs per thread and quad: output n reads x[3n-2 .. 3n+1]; for n = 0 mod 4
-        // that is an 8-byte aligned float2 followed by three 16-byte aligned float4 of the stage (14 floats, 13 used).
-        // Two quads per iteration (independent instruction streams), all pointers advanced by constants.
-        // Quads start on a 32-sample boundary of the padded step buffer: every quarter-warp stores 128 contiguous bytes.
-        constexpr int QS = 4 * RS_THREADS;                       // outputs per sweep of the resampler warps (12 x 32)
+        constexpr int QS = 4 * RS_THREADS;                       // outputs per sweep of the resampler warps (7 x 32 quads)
         static_assert(QS % 32 == 0, "a sweep must keep the 32-sample padding phase");
         int i4 = (i_lo & ~31) + 4 * rtid;
         if (i4 < i_lo) i4 += QS;
-        const float *px = reinterpret_cast<const float *>(srcp) + (rt.tile_k + 3 * (int)tile_off - 1 - f_lo) + 3 * i4;
-        float *yq = out.yb + ypad(i4);
-        float *pq = out.pcm + out.base + i4;
-        // a quad at i is stored whole when i + 4 <= (samples of this step the tile owns); never without a PCM output
-        const int lim4 = out.pcm ? (int)min((uint32_t)YLEN, out.wr_end - min(out.wr_end, out.base)) - 4 : -(1 << 30);
+        const float *px = x0 + 3 * i4;
+        float *yq = yb + ypad(i4);
+        float *pq = pq0 + i4;
         auto quad = [&](const float *p, float *ydst, float *pdst, int i) {
             const float2 hh = *reinterpret_cast<const float2 *>(p);
             const float4 a4 = *reinterpret_cast<const float4 *>(p + 2);
@@ -403,6 +386,32 @@ __device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, const Rs
             px += 6 * QS; yq += 2 * ypad(QS); pq += 2 * QS;
         }
         if (i4 < i_hi) quad(px, yq, pq, i4);
+}
+
+// ---- resampling, interior half steps: every tap comes unchecked from the stage (or the stream) ----
+template <int KIND, bool STAGED>
+__device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, const RsTile &rt, int h, const StreamDev &s, const YSink &out,
+                                                   uint32_t tile_off, int i_lo, int i_hi, int rtid)
+{
+    // taps come from the shared-memory stage (first staged mono frame f_lo) or, when the half step does not fit the
+    // stage (e.g. stereo f32), unchecked from the stream in global memory (f_lo = 0)
+    const unsigned char *__restrict__ srcp = STAGED ? sm.stage[h] : reinterpret_cast<const unsigned char *>(s.data);
+    const int f_lo = STAGED ? (int)((uint32_t)sm.st_lo[h] / ((KIND == K_F32_2 || KIND == K_I16_2) ? 2u : 1u)) : 0;
+    const uint32_t mode = s.mode;
+    int i = i_lo + rtid;
+    if (mode == RS_PASSTHROUGH) {
+        for (; i < i_hi; i += RS_THREADS) out.put(i, tap_fast<KIND>(srcp, (int)(out.base + i) - f_lo));
+        return;
+    }
+    const uint32_t q = s.q;
+    if (KIND == K_F32_1 && q == 1 && s.p == 3) {
+        // 48 kHz -> 16 kHz mono f32, four outputs per thread and quad: output n reads x[3n-2 .. 3n+1]; for n = 0 mod 4
+        // that is an 8-byte aligned float2 followed by three 16-byte aligned float4 of the stage (14 floats, 13 used).
+        // Two quads per iteration (independent instruction streams), all pointers advanced by constants.
+        // Quads start on a 32-sample boundary of the padded step buffer: every quarter-warp stores 128 contiguous bytes.
+        const int lim4 = out.pcm ? (int)min((uint32_t)YLEN, out.wr_end - min(out.wr_end, out.base)) - 4 : -(1 << 30);
+        resample_quads_48k(reinterpret_cast<const float *>(srcp) + (rt.tile_k + 3 * (int)tile_off - 1 - f_lo), out.yb,
+                           out.pcm + out.base, lim4, i_lo, i_hi, rtid);
         return;
     }
     const uint32_t a = rt.tile_rem + (tile_off + (uint32_t)i) * s.p;
@@ -962,11 +971,15 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
         // does this tile's fast path hand out output quads to fixed owner threads (see resample_half_fast)?
         const bool quad_tile = s.mode != RS_PASSTHROUGH && ((kind == K_F32_1 && s.q == 1 && s.p == 3) || (kind != K_GENERIC && s.q > 1));
         bool prev_quads = false;
+        // the hot case -- 48 kHz mono f32 -- bypasses the format dispatch: its interior half steps go straight to the quad loop
+        const bool hot = kind == K_F32_1 && s.mode != RS_PASSTHROUGH && s.q == 1 && s.p == 3;
+        const int tile_k = rt.tile_k;
 
         for (uint32_t g = 0; g < t.n_steps; ++g, ++it) {
             const int b = (int)(it & 1u);
             const uint32_t toff = g * STEP_SAMPLES;
             YSink out{sm.ybuf[b], pcm_row, t.n_tile0 + toff, t.tile_end};
+            const int lim4 = pcm_row ? (int)min((uint32_t)YLEN, out.wr_end - min(out.wr_end, out.base)) - 4 : -(1 << 30);
             AF_WAIT(&sm.y_empty[b], ((it >> 1) & 1u) ^ 1u, 0);   // FFT and VAD warps are done with this buffer
             AF_TIC2
             if (g > 0) {
@@ -991,12 +1004,17 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
                 AF_WAIT(&sm.stage_full[h], it & 1u, 1);
                 const int i_lo = half_lo(g, h), i_hi = half_hi(h);
                 AF_TIC2
-                switch (kind) {
-                case K_F32_1: resample_dispatch<K_F32_1>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
-                case K_I16_1: resample_dispatch<K_I16_1>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
-                case K_F32_2: resample_dispatch<K_F32_2>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
-                case K_I16_2: resample_dispatch<K_I16_2>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
-                default: resample_dispatch<K_GENERIC>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                if (hot && sm.st_interior[h] == 1u) {
+                    resample_quads_48k(reinterpret_cast<const float *>(sm.stage[h]) + (tile_k + 3 * (int)toff - 1 - (int)(uint32_t)sm.st_lo[h]),
+                                       out.yb, out.pcm + out.base, lim4, i_lo, i_hi, rtid);
+                } else {
+                    switch (kind) {
+                    case K_F32_1: resample_dispatch<K_F32_1>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                    case K_I16_1: resample_dispatch<K_I16_1>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                    case K_F32_2: resample_dispatch<K_F32_2>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                    case K_I16_2: resample_dispatch<K_I16_2>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                    default: resample_dispatch<K_GENERIC>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                    }
                 }
                 AF_TOC(4)
                 if (h == 1) prev_quads = quad_tile && sm.st_interior[1] != 0u;   // (read before the stage is released)
