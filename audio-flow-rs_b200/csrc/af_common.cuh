@@ -23,7 +23,20 @@ constexpr int SF = 32;                       // frames per step: one per half-wa
 constexpr int STEP_SAMPLES = SF * HOP;       // 5120 new 16 kHz samples per step
 constexpr int CARRY = WIN - HOP;             // 240 samples shared with the next step
 constexpr int YLEN = STEP_SAMPLES + CARRY;   // 5360 samples live per step
-constexpr int HALF_SPLIT = 2688;             // a step's raw input is staged in two fills: outputs [.., 2688) and [2688, YLEN)
+// A step's raw input is staged in N_PARTS fills, one stage buffer each: while the resampler warps work on one part the
+// other N_PARTS - 1 fills are in flight.  The boundaries are multiples of a resampler sweep (4 * RS_THREADS = 896
+// outputs).  Measured (cfg2, same box): two parts 0.577 ms, three parts 0.607 ms -- the third barrier round trip and
+// part prologue per step cost more than the deeper prefetch gains, so two it is (-DAF_N_PARTS=3 builds the other).
+#ifndef AF_N_PARTS
+#define AF_N_PARTS 2
+#endif
+constexpr int N_PARTS = AF_N_PARTS;
+__host__ __device__ constexpr int part_end(int k)   // outputs [part_end(k - 1), part_end(k)) of the step buffer form part k
+{
+    return N_PARTS == 2 ? (k == 0 ? 2688 : 5360) : (k == 0 ? 1792 : (k == 1 ? 3584 : 5360));
+}
+constexpr int PART_MAX_OUT = N_PARTS == 2 ? 2688 : 1792;   // most outputs one part produces
+constexpr int LAST_PART_LO = part_end(N_PARTS - 2);
 constexpr int TILE_FRAMES = 128;             // frames per tile (work unit of one CTA)
 constexpr int TILE_SAMPLES = TILE_FRAMES * HOP;   // 20480
 constexpr int FFT_WARPS = 16;                // "F": window + FFT + power, one frame per half-warp
@@ -106,7 +119,7 @@ constexpr int PB_COLS = PB_ROW;              // bins a padded weight quadruple m
 constexpr int PBUF_FLOATS = SF * PB_ROW;
 __host__ __device__ constexpr int pb_row(int q) { return ((q >> 1) & 3) + 8 * (q >> 3) + 4 * (q & 1); }
 __host__ __device__ constexpr int pb_frame(int row) { return 2 * ((row & 3) + 4 * (row >> 3)) + ((row >> 2) & 1); }
-constexpr int STAGE_BYTES = 32384;           // one TMA-staged half step of raw input (2688 outputs x 3 x 4 B + halo), two of them
+constexpr int STAGE_BYTES = N_PARTS == 2 ? 32384 : 21632;   // one TMA-staged part of raw input (PART_MAX_OUT outputs x 3 x 4 B + halo)
 
 // formats / flags (mirror include/audioflow_gpu.h)
 enum : uint16_t { FMT_F32 = 0, FMT_I16 = 1 };
@@ -140,7 +153,7 @@ struct FillDesc {
                              // staged (unchecked global loads); 0: checked path
     uint32_t pad_[2];
 };
-constexpr int TILE_FILLS = 2 * (TILE_FRAMES / SF);   // half steps per tile
+constexpr int TILE_FILLS = N_PARTS * (TILE_FRAMES / SF);   // parts per tile
 
 // one tile (128 frames of one stream) with everything the kernel would otherwise have to derive with 64-bit
 // divisions: planned once per batch on the host (plan_tile, af_device.cuh), or per tick by the session set-up kernel

@@ -89,12 +89,12 @@ __host__ __device__ inline void plan_tile(const StreamDev &s, uint32_t stream, u
     const uint32_t ch = s.channels, bps = s.format == FMT_I16 ? 2u : 4u;
     const uint32_t left = s.n_out - n_tile0;                       // outputs from the tile start to the stream end
     for (int j = 0; j < TILE_FILLS; ++j) {
-        const uint32_t g = (uint32_t)j >> 1;
-        const int h = j & 1;
+        const uint32_t g = (uint32_t)j / (uint32_t)N_PARTS;
+        const int h = j % N_PARTS;
         FillDesc d;
         d.src = reinterpret_cast<const char *>(s.data); d.bytes = 0; d.lo = 0; d.hi = 0; d.interior = 0; d.pad_[0] = d.pad_[1] = 0;
-        const uint32_t d_first = g * STEP_SAMPLES + (uint32_t)(h == 0 ? (g == 0 ? 0 : CARRY) : HALF_SPLIT);
-        const uint32_t d_full = g * STEP_SAMPLES + (uint32_t)(h == 0 ? HALF_SPLIT : YLEN);
+        const uint32_t d_first = g * STEP_SAMPLES + (uint32_t)(h == 0 ? (g == 0 ? 0 : CARRY) : part_end(h - 1));
+        const uint32_t d_full = g * STEP_SAMPLES + (uint32_t)part_end(h);
         const uint32_t d_last = d_full < left ? d_full : left;
         if (g < t->n_steps && d_first < d_last) {
             // floor(position) of output n_tile0 + d (the host guarantees (TILE_SAMPLES + YLEN) * p + q < 2^32)

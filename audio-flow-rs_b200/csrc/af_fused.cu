@@ -28,7 +28,7 @@ struct RsTile {
 };
 
 struct __align__(128) FusedSmem {
-    unsigned char stage[2][STAGE_BYTES];             // raw interleaved input of the two halves of a step (bulk-copy targets)
+    unsigned char stage[N_PARTS][STAGE_BYTES];       // raw interleaved input of the parts of a step (bulk-copy targets)
     float ybuf[2][YBUF_FLOATS];                      // padded 16 kHz samples of two consecutive steps
     float scr[FFT_WARPS * SCR_FLOATS_PER_WARP];      // per FFT warp transpose scratch
     float pbuf[2][PBUF_FLOATS];                      // 4*|X[k]|^2, [pb_row(frame)][bin], two consecutive steps
@@ -40,12 +40,12 @@ struct __align__(128) FusedSmem {
                                                      // carry the record across the transform (the mel warps lag < 3 steps)
     MelTables mel;
     // pipeline barriers (mbarriers): full = data ready for the consumer, empty = buffer may be overwritten
-    unsigned long long stage_full[2], stage_empty[2];
+    unsigned long long stage_full[N_PARTS], stage_empty[N_PARTS];
     unsigned long long y_full[2], y_empty[2];
     unsigned long long p_full[2], p_empty[2];
     // metadata of the fill held by stage[h], written by the issuing thread before its arrive
-    unsigned long long st_lo[2], st_hi[2];           // interleaved element range [lo, hi) held by the stage
-    uint32_t st_interior[2];                         // 1: every tap of the half step is inside the stage and the stream;
+    unsigned long long st_lo[N_PARTS], st_hi[N_PARTS];   // interleaved element range [lo, hi) held by the stage
+    uint32_t st_interior[N_PARTS];                   // 1: every tap of the half step is inside the stage and the stream;
                                                      // 2: inside the stream but not staged (unchecked global loads)
     // resampler role: every warp keeps its own copy of the tile's stream descriptor and first-output position, so that
     // a new tile needs no synchronisation among the resampler warps
@@ -240,8 +240,8 @@ __device__ __forceinline__ TileGeo tile_geo(const FusedParams &P, uint32_t tile,
     if (n_frames) *n_frames = td->n_frames;
     return t;
 }
-__device__ __forceinline__ int half_lo(uint32_t g, int h) { return h == 0 ? (g == 0 ? 0 : CARRY) : HALF_SPLIT; }
-__device__ __forceinline__ int half_hi(int h) { return h == 0 ? HALF_SPLIT : YLEN; }
+__device__ __forceinline__ int half_lo(uint32_t g, int h) { return h == 0 ? (g == 0 ? 0 : CARRY) : part_end(h - 1); }
+__device__ __forceinline__ int half_hi(int h) { return part_end(h); }
 
 // ---- stage fill (descriptors planned per tile by plan_tile, af_device.cuh) ----
 // issued by ONE thread; always completes one phase of stage_full[h]
@@ -867,7 +867,7 @@ __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, in
     bool fill_live = tile_f < P.n_tiles;
     FillDesc d_next{};
     auto fetch_desc = [&]() {
-        const uint4 *src = reinterpret_cast<const uint4 *>(&P.tiles[tile_f].fill[2 * g_f + h_f]);
+        const uint4 *src = reinterpret_cast<const uint4 *>(&P.tiles[tile_f].fill[N_PARTS * g_f + h_f]);
         const uint4 a = __ldg(src), b = __ldg(src + 1);
         d_next.src = reinterpret_cast<const char *>(((unsigned long long)a.y << 32) | a.x);
         d_next.bytes = a.z; d_next.lo = a.w; d_next.hi = b.x; d_next.interior = b.y;
@@ -879,7 +879,7 @@ __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, in
         else if (!mbar_test(&sm.stage_empty[h_f], (it_f & 1u) ^ 1u)) return;
         AF_TIC
         issue_fill(sm, P, d_next, h_f);
-        if (++h_f == 2) {
+        if (++h_f == N_PARTS) {
             h_f = 0; ++it_f;
             if (++g_f == steps_f) {
                 g_f = 0; tile_f += gridDim.x;
@@ -989,7 +989,7 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
                     // the quad paths give every output quad a fixed owner thread: each thread carries the quad it wrote
                     // itself in the previous step -- no synchronisation among the resampler warps
                     constexpr int QS = 4 * RS_THREADS;
-                    int c4 = HALF_SPLIT + 4 * rtid;
+                    int c4 = LAST_PART_LO + 4 * rtid;
                     c4 += ((STEP_SAMPLES - c4 + QS - 1) / QS) * QS;           // first own quad at or after STEP_SAMPLES
                     if (c4 < YLEN)
                         *reinterpret_cast<float4 *>(out.yb + ypad(c4 - STEP_SAMPLES)) = *reinterpret_cast<const float4 *>(prev + ypad(c4));
@@ -1000,7 +1000,7 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
             }
             AF_TOC(3)
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < N_PARTS; ++h) {
                 AF_WAIT(&sm.stage_full[h], it & 1u, 1);
                 const int i_lo = half_lo(g, h), i_hi = half_hi(h);
                 AF_TIC2
@@ -1017,7 +1017,7 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
                     }
                 }
                 AF_TOC(4)
-                if (h == 1) prev_quads = quad_tile && sm.st_interior[1] != 0u;   // (read before the stage is released)
+                if (h == N_PARTS - 1) prev_quads = quad_tile && sm.st_interior[N_PARTS - 1] != 0u;   // (read before the stage is released)
                 warp_arrive(&sm.stage_empty[h], lane);          // this warp no longer reads stage[h] or its metadata
             }
             if (rtid == 0) {
@@ -1052,9 +1052,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
         for (int i = tid; i < 2 * PBUF_FLOATS; i += FUSED_THREADS) sm.pbuf[0][i] = 0.0f;
     }
     if (tid == 0) {
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < N_PARTS; ++h) {
             mbar_init(&sm.stage_full[h], 1);
             mbar_init(&sm.stage_empty[h], RS_WARPS);
+        }
+        for (int h = 0; h < 2; ++h) {
             mbar_init(&sm.y_full[h], RS_WARPS);
             mbar_init(&sm.y_empty[h], FFT_WARPS + 1);
         }

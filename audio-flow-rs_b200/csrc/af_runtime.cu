@@ -704,8 +704,8 @@ int build_sub(af_batch *b, SubBatch &sb, const void *slot_in_base)
         d.frac = hs.table ? hs.table->d : nullptr;
         {   // does the raw input of one step fit the shared-memory stage of the fused kernel?
             const uint64_t bps = hs.desc.format == AF_FMT_I16 ? 2 : 4;
-            // (a step is staged in two fills of at most HALF_SPLIT outputs each)
-            const uint64_t frames = hs.mode == RS_PASSTHROUGH ? (uint64_t)HALF_SPLIT : ((uint64_t)HALF_SPLIT * hs.p + hs.q - 1) / hs.q;
+            // (a step is staged in N_PARTS fills of at most PART_MAX_OUT outputs each)
+            const uint64_t frames = hs.mode == RS_PASSTHROUGH ? (uint64_t)PART_MAX_OUT : ((uint64_t)PART_MAX_OUT * hs.p + hs.q - 1) / hs.q;
             d.staged = hs.desc.channels <= 2 && (frames + 8) * hs.desc.channels * bps + 32 <= (uint64_t)STAGE_BYTES;
         }
         d.tile_begin = (uint32_t)sb.h_tiles.size();
