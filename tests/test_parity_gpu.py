@@ -446,3 +446,29 @@ def test_parallel_vad_scan_long_streams(af, orc, alpha):
         ref = orc.pipeline_stream(x, ch, rate, None, oc, 400, 160, "f32")
         assert len(ref["vad"]) == 1 + (len(x) - 400) // 160
         _check_stream(g, ref, f"alpha {alpha} stream {i}")
+
+
+@pytest.mark.parametrize("rate,ch", [(48000, 1), (48000, 2), (44100, 1), (32000, 1)])
+def test_resampler_special_values(af, orc, rate, ch):
+    """The frac = 0 shortcut of the 48 kHz path (y = y1 when y1 != 0 and every tap is finite with |x| < 2) and the
+    unfused cubic everywhere else must stay bit-exact on the values that break shortcuts: +-0 taps, exact zeros as y1,
+    |x| >= 2, huge values, subnormals, +-Inf and NaN (NaN positions must match; payloads are implementation-defined)."""
+    from audioflow import synth
+    n = int(1.6 * rate) * ch
+    x = synth.stream(140 + ch, 1.6, rate, ch)[:n].copy()
+    rng = np.random.default_rng(rate + ch)
+    specials = np.array([0.0, -0.0, 2.0, -2.0, 1.9999999, 3.5, -7.25, 1e30, -1e30, 1e-40, -1e-41, 1.17549435e-38,
+                         np.inf, -np.inf, np.nan, 65504.0, 1.0, -1.0], np.float32)
+    # isolated specials, runs of zeros (whole quads with y1 == 0) and runs of large values
+    for k in range(400):
+        x[int(rng.integers(0, n))] = specials[k % len(specials)]
+    for k in range(12):
+        s = int(rng.integers(0, n - 200))
+        x[s:s + int(rng.integers(3, 120))] = (0.0, -0.0, 2.5, 1e-39)[k % 4]
+    got = af.Pipeline(af.pipeline_config(n_mels=0, vad_enable=False)).run_host([(x, rate, ch)])[0]["pcm"]
+    ref = orc.resample_stream(orc.to_mono(x, ch), rate)
+    assert got.shape == ref.shape
+    nan = np.isnan(ref)
+    assert nan.any() and (~nan).sum() > 0.9 * len(ref)
+    assert np.array_equal(np.isnan(got), nan), "NaN positions differ"
+    assert_bit_equal(got[~nan], ref[~nan], f"special values {rate} Hz x{ch}")
