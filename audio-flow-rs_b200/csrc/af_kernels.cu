@@ -446,6 +446,225 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
     }
 }
 
+// ---- long streams: many CTAs per stream ------------------------------------------------------------------------
+// The word walk above is sequential per stream (a one-hour recording: 11 250 words through one thread, 2.5 ms).  It is
+// cut into blocks of SCAN_BLOCK frames that are walked SPECULATIVELY in parallel, every block but the first assuming a
+// fresh machine (Silence, counters 0).  The speculation is exact from the block's first "sync point" on: a speech
+// frame that follows at least silence_timeout + 1 non-speech frames finds the machine in Silence whatever came before
+// (Speech times out after silence_timeout, Ending lasts one frame) and sets (Speech, 1, 0).  A cheap sequential pass
+// then carries the true state from block to block and re-walks only the words in front of each block's sync point
+// (the whole block if it has none); the EMA entering a block is speculated from a warm-up and verified the same way.
+// Scratch per stream: bits [W], per-word entry states [W][3], per block: spec / end EMA, sync frame, exit state [3].
+struct LongScanView {
+    uint32_t *bits, *entry;
+    float *spec, *end;
+    uint32_t *sync, *exit;
+};
+__host__ __device__ inline uint32_t long_scan_words(uint32_t max_frames) { return (max_frames + 31u) / 32u; }
+__host__ __device__ inline uint32_t long_scan_blocks(uint32_t max_frames) { return (max_frames + SCAN_BLOCK - 1u) / SCAN_BLOCK; }
+__host__ __device__ inline size_t long_scan_stride(uint32_t max_frames)
+{
+    return 4 * (size_t)long_scan_words(max_frames) + 6 * (size_t)long_scan_blocks(max_frames);
+}
+__device__ __forceinline__ LongScanView long_scan_view(uint32_t *scratch, uint32_t max_frames, uint32_t s)
+{
+    const size_t W = long_scan_words(max_frames), NB = long_scan_blocks(max_frames);
+    uint32_t *p = scratch + (size_t)s * long_scan_stride(max_frames);
+    LongScanView v;
+    v.bits = p; v.entry = p + W;
+    v.spec = reinterpret_cast<float *>(p + 4 * W); v.end = v.spec + NB;
+    v.sync = p + 4 * W + 2 * NB; v.exit = v.sync + NB;
+    return v;
+}
+size_t scan_scratch_words(uint32_t max_frames) { return long_scan_stride(max_frames); }
+
+constexpr uint32_t NO_SYNC = 0xffffffffu;
+
+// phase A: one CTA per (block, stream): decision bits, speculative walk, sync point, exit state
+__global__ void __launch_bounds__(SCAN_THREADS) af_vad_long_a_kernel(const ScanJob J, uint32_t warm)
+{
+    __shared__ uint32_t s_bits[SCAN_BLOCK / 32];
+    __shared__ float s_spec[SCAN_BLOCK / SCAN_CHUNK], s_end[SCAN_BLOCK / SCAN_CHUNK];
+    __shared__ float s_e[SCAN_WARM_MAX + SCAN_BLOCK];
+    __shared__ int s_bad;
+    const uint32_t blk = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
+    const uint32_t T = J.n_frames ? J.n_frames[s] : J.n_frames_all;
+    const uint32_t b0 = blk * SCAN_BLOCK;
+    if (b0 >= T) return;
+    const LongScanView V = long_scan_view(J.scratch, J.max_frames, s);
+    const float *e = J.energy + (uint64_t)s * J.energy_stride;
+    const VadParams prm = J.prm;
+    const float alpha = prm.alpha, beta = __fsub_rn(1.0f, prm.alpha), e_min = prm.e_min;
+    const bool use_smoothed = alpha > 0.0f;
+    const uint32_t timeout = (uint32_t)prm.silence_timeout, minsp = (uint32_t)prm.min_speech;
+    const uint32_t n = min(SCAN_BLOCK, T - b0);
+    const uint32_t n_chunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK, n_words = (n + 31) / 32;
+    if (tid == 0) s_bad = 0;
+    const uint32_t lead = min(warm, b0);
+    const float *eb = s_e + lead;
+    for (uint32_t i = tid; i < lead + n; i += SCAN_THREADS) s_e[i] = e[b0 - lead + i];
+    __syncthreads();
+    // EMA chunks: every chunk but the stream's very first starts from a warm-up (fresh detector: the stream starts at 0)
+    for (uint32_t c = tid; c < n_chunks; c += SCAN_THREADS) {
+        const uint32_t f_begin = b0 + c * SCAN_CHUNK, f_end = min(f_begin + SCAN_CHUNK, b0 + n);
+        float sm = 0.0f;
+        if (f_begin != 0) {
+            const uint32_t w0 = f_begin >= warm ? f_begin - warm : 0u;
+            for (uint32_t f = w0; f < f_begin; ++f) sm = __fadd_rn(__fmul_rn(alpha, eb[(int)f - (int)b0]), __fmul_rn(beta, sm));
+        }
+        s_spec[c] = sm;
+        for (uint32_t f = f_begin; f < f_end; f += 32) {
+            const uint32_t m = min(32u, f_end - f);
+            uint32_t bits = 0;
+            for (uint32_t j = 0; j < m; ++j) {
+                const float ev = eb[f - b0 + j];
+                sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
+                bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
+            }
+            s_bits[(f - b0) >> 5] = bits;
+        }
+        s_end[c] = sm;
+    }
+    __syncthreads();
+    for (uint32_t c = 1 + tid; c < n_chunks; c += SCAN_THREADS)
+        if (__float_as_uint(s_spec[c]) != __float_as_uint(s_end[c - 1])) s_bad = 1;
+    __syncthreads();
+    if (s_bad && tid == 0) {                                  // (rare) redo the block sequentially from its own start value
+        float sm = s_spec[0];
+        for (uint32_t w = 0; w < n_words; ++w) {
+            const uint32_t m = min(32u, n - w * 32);
+            uint32_t bits = 0;
+            for (uint32_t j = 0; j < m; ++j) {
+                const float ev = eb[w * 32 + j];
+                sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
+                bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
+            }
+            s_bits[w] = bits;
+        }
+        s_end[n_chunks - 1] = sm;
+    }
+    __syncthreads();
+    for (uint32_t w = tid; w < n_words; w += SCAN_THREADS) V.bits[(b0 >> 5) + w] = s_bits[w];
+    if (tid == 0) {
+        V.spec[blk] = s_spec[0]; V.end[blk] = s_end[n_chunks - 1];
+        // speculative walk from a fresh machine + the first sync point
+        VadMachine m{0u, 0u, 0u};
+        EmitNone none;
+        uint32_t zrun = 0, sync = NO_SYNC;
+        const uint32_t need = timeout + 1u;
+        for (uint32_t w = 0; w < n_words; ++w) {
+            const uint32_t bits = s_bits[w], m_n = min(32u, n - w * 32);
+            uint32_t *en = V.entry + 3 * (size_t)((b0 >> 5) + w);
+            en[0] = m.st; en[1] = m.sil; en[2] = m.spk;
+            vad_machine_word_t(m, bits, m_n, none, timeout, minsp);
+            if (sync == NO_SYNC) {                              // (only until the first one is found)
+                for (uint32_t j = 0; j < m_n; ++j) {
+                    if ((bits >> j) & 1u) {
+                        if (zrun >= need) { sync = w * 32 + j; break; }
+                        zrun = 0;
+                    } else ++zrun;
+                }
+            }
+        }
+        V.sync[blk] = sync;
+        V.exit[3 * blk] = m.st; V.exit[3 * blk + 1] = m.sil; V.exit[3 * blk + 2] = m.spk;
+    }
+}
+
+// phase B: one thread per stream carries the true EMA and machine state from block to block
+__global__ void af_vad_long_b_kernel(const ScanJob J)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= J.n_streams) return;
+    const uint32_t T = J.n_frames ? J.n_frames[s] : J.n_frames_all;
+    const LongScanView V = long_scan_view(J.scratch, J.max_frames, s);
+    const float *e = J.energy + (uint64_t)s * J.energy_stride;
+    const VadParams prm = J.prm;
+    const float alpha = prm.alpha, beta = __fsub_rn(1.0f, prm.alpha), e_min = prm.e_min;
+    const bool use_smoothed = alpha > 0.0f;
+    const uint32_t timeout = (uint32_t)prm.silence_timeout, minsp = (uint32_t)prm.min_speech;
+    const uint32_t nb = (T + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    float carry_s = 0.0f;
+    VadMachine m{0u, 0u, 0u};
+    EmitNone none;
+    for (uint32_t blk = 0; blk < nb; ++blk) {
+        const uint32_t b0 = blk * SCAN_BLOCK, n = min(SCAN_BLOCK, T - b0), n_words = (n + 31) / 32;
+        bool rewalk_all = false;
+        if (blk > 0 && __float_as_uint(V.spec[blk]) != __float_as_uint(carry_s)) {
+            // (rare) the warm-up did not reproduce the true EMA: redo this block's decisions from the true value
+            float sm = carry_s;
+            for (uint32_t w = 0; w < n_words; ++w) {
+                const uint32_t mw = min(32u, n - w * 32);
+                uint32_t bits = 0;
+                for (uint32_t j = 0; j < mw; ++j) {
+                    const float ev = e[b0 + w * 32 + j];
+                    sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
+                    bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
+                }
+                V.bits[(b0 >> 5) + w] = bits;
+            }
+            V.end[blk] = sm;
+            rewalk_all = true;
+        }
+        carry_s = V.end[blk];
+        const bool as_assumed = m.st == 0u && m.sil == 0u && m.spk == 0u;
+        if (!rewalk_all && (blk == 0 || as_assumed)) {          // the speculative walk started from the true state
+            m = VadMachine{V.exit[3 * blk], V.exit[3 * blk + 1], V.exit[3 * blk + 2]};
+            continue;
+        }
+        const uint32_t sync = rewalk_all ? NO_SYNC : V.sync[blk];
+        const uint32_t stop = sync == NO_SYNC ? n : sync;       // frames [0, stop) of the block need the true walk
+        for (uint32_t w = 0; w * 32 < stop; ++w) {
+            uint32_t *en = V.entry + 3 * (size_t)((b0 >> 5) + w);
+            en[0] = m.st; en[1] = m.sil; en[2] = m.spk;
+            const uint32_t m_n = min(min(32u, n - w * 32), stop - w * 32);
+            vad_machine_word_t(m, V.bits[(b0 >> 5) + w], m_n, none, timeout, minsp);
+        }
+        if (sync != NO_SYNC) m = VadMachine{V.exit[3 * blk], V.exit[3 * blk + 1], V.exit[3 * blk + 2]};   // exact from the sync point on
+    }
+    VadState v;
+    v.smoothed = carry_s; v.state = (int)m.st; v.silence_frames = m.sil; v.speech_frames = m.spk;
+    if (J.final_out) J.final_out[s] = v;
+}
+
+// phase C: every word expands into state bytes from its (now exact) entry state
+__global__ void __launch_bounds__(SCAN_THREADS) af_vad_long_c_kernel(const ScanJob J)
+{
+    const uint32_t blk = blockIdx.x, s = blockIdx.y;
+    const uint32_t T = J.n_frames ? J.n_frames[s] : J.n_frames_all;
+    const uint32_t b0 = blk * SCAN_BLOCK;
+    if (b0 >= T || !J.states) return;
+    const LongScanView V = long_scan_view(J.scratch, J.max_frames, s);
+    uint8_t *out = J.states + (uint64_t)s * J.states_stride;
+    const bool aligned_out = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const uint32_t timeout = (uint32_t)J.prm.silence_timeout, minsp = (uint32_t)J.prm.min_speech;
+    const uint32_t n = min(SCAN_BLOCK, T - b0), n_words = (n + 31) / 32;
+    for (uint32_t w = threadIdx.x; w < n_words; w += SCAN_THREADS) {
+        const uint32_t *en = V.entry + 3 * (size_t)((b0 >> 5) + w);
+        VadMachine m{en[0], en[1], en[2]};
+        EmitMask em;
+        const uint32_t m_n = min(32u, n - w * 32);
+        vad_machine_word_t(m, V.bits[(b0 >> 5) + w], m_n, em, timeout, minsp);
+        uint32_t by[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t sp = ((em.speech >> (4 * k)) & 0xfu) * 0x00204081u & 0x01010101u;
+            const uint32_t en2 = ((em.ending >> (4 * k)) & 0xfu) * 0x00204081u & 0x01010101u;
+            by[k] = sp + 2u * en2;
+        }
+        uint8_t *dst = out + b0 + w * 32;
+        if (m_n == 32u && aligned_out) {
+            reinterpret_cast<uint4 *>(dst)[0] = make_uint4(by[0], by[1], by[2], by[3]);
+            reinterpret_cast<uint4 *>(dst)[1] = make_uint4(by[4], by[5], by[6], by[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                for (uint32_t i = 0; i < 4; ++i)
+                    if (4u * k + i < m_n) dst[4 * k + i] = (uint8_t)(by[k] >> (8 * i));
+        }
+    }
+}
+
 // warm-up length (frames) after which an EMA started from 0 agrees bit for bit with the true one in practice:
 // (1 - alpha)^warm < 2^-56 (24 bits of mantissa + 32 bits of dynamic range); 0 = no parallel scan for this alpha
 static uint32_t scan_warmup(float alpha)
@@ -466,6 +685,14 @@ cudaError_t launch_vad_scan(const ScanJob &job, cudaStream_t st)
     const bool small = job.prm.silence_timeout < 0x40000000ull && job.prm.min_speech < 0x40000000ull &&
                        job.n_frames_all < 0x40000000u;
     if (warm != 0 && small && job.state_io == nullptr) {
+        if (job.scratch && job.max_frames > 2u * SCAN_BLOCK && job.max_frames < 0x40000000u) {
+            // long streams: speculative block walks in parallel, a cheap sequential carry pass, parallel expansion
+            const dim3 grid(long_scan_blocks(job.max_frames), job.n_streams);
+            af_vad_long_a_kernel<<<grid, SCAN_THREADS, 0, st>>>(job, warm);
+            af_vad_long_b_kernel<<<(job.n_streams + 31) / 32, 32, 0, st>>>(job);
+            af_vad_long_c_kernel<<<grid, SCAN_THREADS, 0, st>>>(job);
+            return cudaGetLastError();
+        }
         af_vad_scan_par_kernel<<<job.n_streams, SCAN_THREADS, 0, st>>>(job, warm);
         return cudaGetLastError();
     }

@@ -33,7 +33,13 @@ struct ScanJob {             // EMA + threshold + state machine, one stream per 
     VadState *final_out;     // optional extra copy of the final state (af_vad_final layout)
     VadParams prm;
     uint32_t n_streams;
+    // long streams (optional): an upper bound of the frame counts known on the host, and scratch of
+    // scan_scratch_words(max_frames) 32-bit words per stream; with both set, streams longer than two scan blocks are
+    // scanned by many CTAs each (launch_vad_scan picks the path)
+    uint32_t max_frames;
+    uint32_t *scratch;
 };
+size_t scan_scratch_words(uint32_t max_frames);
 
 struct SessionIngest {
     const float *old_buf; float *new_buf; uint64_t buf_stride;   // mono f32 input history, ping-pong

@@ -660,6 +660,7 @@ struct SubBatch {                     // a group of streams resident on the devi
     uint32_t *d_nframes = nullptr, *d_nvad = nullptr;
     std::vector<size_t> in_off;       // host mode: byte offset of each stream inside the slot input buffer
     size_t in_bytes = 0;
+    uint32_t *d_scan = nullptr;       // long streams: scratch of the many-CTA VAD scan (launch_vad_scan)
 };
 
 }  // namespace
@@ -769,6 +770,10 @@ int run_sub(af_batch *b, SubBatch &sb, float *pcm, uint64_t pcm_stride, float *l
         sj.energy = energy; sj.energy_stride = energy_stride; sj.n_frames = sb.d_nvad; sj.n_frames_all = 0;
         sj.states = vad; sj.states_stride = vad_stride; sj.state_io = nullptr; sj.final_out = vad_final;
         sj.prm = b->pipe->vad_prm; sj.n_streams = (uint32_t)sb.count;
+        if (b->max_vad > 16384 && b->max_vad < 0x40000000ull) {              // long streams: many CTAs per stream
+            if (!sb.d_scan) AF_CUDA(cudaMalloc(&sb.d_scan, sb.count * scan_scratch_words((uint32_t)b->max_vad) * sizeof(uint32_t)));
+            sj.max_frames = (uint32_t)b->max_vad; sj.scratch = sb.d_scan;
+        }
         AF_CUDA(launch_vad_scan(sj, st));
         count_launch();
     }
@@ -836,6 +841,7 @@ AF_API void af_batch_destroy(af_batch *b)
         if (sb.d_tiles) cudaFree(sb.d_tiles);
         if (sb.d_nframes) cudaFree(sb.d_nframes);
         if (sb.d_nvad) cudaFree(sb.d_nvad);
+        if (sb.d_scan) cudaFree(sb.d_scan);
     }
     if (b->d_energy) cudaFree(b->d_energy);
     if (b->d_pcm_scratch) cudaFree(b->d_pcm_scratch);

@@ -472,3 +472,35 @@ def test_resampler_special_values(af, orc, rate, ch):
     assert nan.any() and (~nan).sum() > 0.9 * len(ref)
     assert np.array_equal(np.isnan(got), nan), "NaN positions differ"
     assert_bit_equal(got[~nan], ref[~nan], f"special values {rate} Hz x{ch}")
+
+
+@pytest.mark.parametrize("alpha", [0.3, 0.0, 1.0])
+def test_many_cta_vad_scan_very_long_streams(af, orc, alpha):
+    """Streams of more than two scan blocks (> 16384 frames) take the many-CTA scan: speculative block walks from a fresh
+    machine, exact from each block's first sync point (speech after silence_timeout + 1 non-speech frames), a sequential
+    carry pass that re-walks the words in front of it.  Against the sequential oracle (vad.rs:97-154), on content built
+    to break every shortcut: speech that runs across whole blocks (no sync point), borderline flicker, silence across
+    block boundaries (entry state Silence with a non-zero counter), and a loud-to-nearly-silent step right before a
+    block boundary (frame 8192 = 81.92 s) so that the EMA warm-up speculation of the next block is wrong."""
+    rng = np.random.default_rng(11)
+    fs = 16000
+    def noise(sec, a): return (a * rng.standard_normal(int(sec * fs))).astype(np.float32).clip(-1, 1)
+    # 1: segments of all four classes, 330 s -> 32 998 frames, five blocks
+    seg = rng.integers(0, 4, 330 * fs // 4000 + 1).repeat(4000)[:330 * fs]
+    x1 = (np.choose(seg, [1e-3, 0.02, 0.08, 0.3]).astype(np.float32) * rng.standard_normal(330 * fs).astype(np.float32)).clip(-1, 1)
+    # 2: 200 s of continuous speech (two whole blocks without a sync point), then silence, then flicker
+    x2 = np.concatenate([noise(5, 1e-3), noise(200, 0.3), noise(40, 1e-3), noise(60, 0.056)])
+    # 3: loud until just before frame 8192, then 1e-6: the next block's EMA warm-up (128 frames) starts inside the loud part
+    x3 = np.concatenate([0.9 * np.ones(int(81.7 * fs), np.float32), noise(120, 1e-6), noise(30, 0.3), noise(30, 1e-3)])
+    # 4: silence across three block boundaries, speech at the very end
+    x4 = np.concatenate([noise(2, 0.3), noise(260, 1e-3), noise(3, 0.3)])
+    vc = af.VadConfig(threshold_db=-50.0, smoothing_factor=alpha, silence_timeout_frames=15, min_speech_frames=3)
+    oc = orc.default_vad_config()
+    oc.threshold_db, oc.smoothing_factor, oc.silence_timeout_frames, oc.min_speech_frames = -50.0, alpha, 15, 3
+    streams = [(x, fs, 1) for x in (x1, x2, x3, x4)] + [(x1[:fs * 20], fs, 1)]     # + a short stream in the same batch
+    got = af.Pipeline(af.pipeline_config(n_mels=0, vad=vc)).run_host(streams)
+    for i, ((x, rate, ch), g) in enumerate(zip(streams, got)):
+        ref = orc.pipeline_stream(x, ch, rate, None, oc, 400, 160, "f32")
+        assert len(ref["vad"]) == 1 + (len(x) - 400) // 160
+        _check_stream(g, ref, f"many-CTA scan, alpha {alpha}, stream {i}")
+        assert g["vad_final"]["state"] == int(ref["vad"][-1])
