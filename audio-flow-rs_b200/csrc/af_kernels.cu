@@ -841,27 +841,50 @@ cudaError_t launch_pcm16(const float *in, uint64_t n, int16_t *out, cudaStream_t
 // ---- VAD segmentation: runs from the first Speech frame to Ending (inclusive) / Silence (exclusive) ----
 // One CTA per stream.  A segment starts at every frame with state Speech whose predecessor is not Speech, and
 // ends at the first later frame that is not Speech; starts and ends alternate, so the k-th start pairs with
-// the k-th end.  Each thread owns a contiguous span of frames: count, block-wide exclusive scan, write.
-__global__ void af_vad_segments_kernel(const uint8_t *__restrict__ states, uint64_t stride,
-                                       const uint32_t *__restrict__ n_frames, uint32_t n_streams,
-                                       uint32_t *__restrict__ seg, uint32_t seg_cap, uint32_t *__restrict__ n_seg)
+// the k-th end.  Each thread owns a contiguous span of frames (a multiple of 16, read 16 states per load and
+// turned into a 16-bit "is Speech" mask): count, block-wide exclusive scan, write.
+constexpr uint32_t SEG_THREADS = 1024;
+__device__ __forceinline__ uint32_t speech_mask16(const uint8_t *st, uint32_t f, uint32_t T, bool vec)
 {
-    __shared__ uint32_t s_starts[1024], s_ends[1024];
+    // bit i: frame f + i is Speech (frames >= T read as not Speech)
+    uint32_t m = 0;
+    if (vec && f + 16 <= T) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(st + f);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t eq = __vcmpeq4(w[k], 0x01010101u) & 0x01010101u;        // 1 per Speech byte
+            m |= (((eq * 0x01020408u) >> 24) & 0xfu) << (4 * k);                     // gather the four flags (byte i -> bit i)
+        }
+    } else {
+        for (uint32_t i = 0; i < 16 && f + i < T; ++i) m |= (st[f + i] == 1 ? 1u : 0u) << i;
+    }
+    return m;
+}
+__global__ void __launch_bounds__(SEG_THREADS) af_vad_segments_kernel(const uint8_t *__restrict__ states, uint64_t stride,
+                                                                      const uint32_t *__restrict__ n_frames, uint32_t n_streams,
+                                                                      uint32_t *__restrict__ seg, uint32_t seg_cap,
+                                                                      uint32_t *__restrict__ n_seg)
+{
+    __shared__ uint32_t s_starts[SEG_THREADS], s_ends[SEG_THREADS];
     const uint32_t s = blockIdx.x;
     if (s >= n_streams) return;
     const uint8_t *st = states + (uint64_t)s * stride;
     uint32_t *sg = seg + (uint64_t)s * seg_cap * 2;
     const uint32_t T = n_frames[s];
     const uint32_t nt = blockDim.x, t = threadIdx.x;
-    const uint32_t span = (T + nt - 1) / nt;
+    const bool vec = (reinterpret_cast<uintptr_t>(st) & 15) == 0;
+    const uint32_t span = (((T + nt - 1) / nt) + 15u) & ~15u;           // frames per thread, a multiple of 16
     const uint32_t lo = min(t * span, T), hi = min(lo + span, T);
     uint32_t ns = 0, ne = 0;
-    uint8_t prev = lo > 0 ? st[lo - 1] : (uint8_t)0;
-    for (uint32_t f = lo; f < hi; ++f) {
-        const uint8_t v = st[f];
-        ns += (v == 1 && prev != 1);
-        ne += (v != 1 && prev == 1);
-        prev = v;
+    uint32_t prev = lo > 0 ? (st[lo - 1] == 1 ? 1u : 0u) : 0u;
+    for (uint32_t f = lo; f < hi; f += 16) {
+        const uint32_t m = speech_mask16(st, f, hi, vec), n = min(16u, hi - f);
+        const uint32_t before = ((m << 1) | prev) & 0xffffu;            // bit i: frame f + i - 1 is Speech
+        const uint32_t valid = n >= 16 ? 0xffffu : ((1u << n) - 1u);
+        ns += __popc(m & ~before & valid);
+        ne += __popc(~m & before & valid);
+        prev = (m >> (n - 1)) & 1u;
     }
     s_starts[t] = ns; s_ends[t] = ne;
     __syncthreads();
@@ -875,12 +898,21 @@ __global__ void af_vad_segments_kernel(const uint8_t *__restrict__ states, uint6
     }
     uint32_t ks = s_starts[t] - ns, ke = s_ends[t] - ne;      // index of this span's first start / end
     const uint32_t total = s_starts[nt - 1], total_ends = s_ends[nt - 1];
-    prev = lo > 0 ? st[lo - 1] : (uint8_t)0;
-    for (uint32_t f = lo; f < hi; ++f) {
-        const uint8_t v = st[f];
-        if (v == 1 && prev != 1) { if (ks < seg_cap) sg[2 * ks] = f; ks++; }
-        if (v != 1 && prev == 1) { if (ke < seg_cap) sg[2 * ke + 1] = v == 2 ? f + 1 : f; ke++; }
-        prev = v;
+    if (ns | ne) {                                            // only spans with a boundary take the second pass
+        prev = lo > 0 ? (st[lo - 1] == 1 ? 1u : 0u) : 0u;
+        for (uint32_t f = lo; f < hi; f += 16) {
+            const uint32_t m = speech_mask16(st, f, hi, vec), n = min(16u, hi - f);
+            const uint32_t before = ((m << 1) | prev) & 0xffffu;
+            const uint32_t valid = n >= 16 ? 0xffffu : ((1u << n) - 1u);
+            uint32_t sb = m & ~before & valid, eb = ~m & before & valid;
+            while (sb) { const uint32_t i = __ffs((int)sb) - 1u; sb &= sb - 1u; if (ks < seg_cap) sg[2 * ks] = f + i; ks++; }
+            while (eb) {
+                const uint32_t i = __ffs((int)eb) - 1u; eb &= eb - 1u;
+                if (ke < seg_cap) sg[2 * ke + 1] = st[f + i] == 2 ? f + i + 1 : f + i;     // Ending belongs to the segment
+                ke++;
+            }
+            prev = (m >> (n - 1)) & 1u;
+        }
     }
     if (t == 0) {
         if (total > total_ends && total - 1 < seg_cap) sg[2 * (total - 1) + 1] = T;    // still speaking at the end
@@ -892,7 +924,7 @@ cudaError_t launch_vad_segments(const uint8_t *states, uint64_t stride, const ui
                                 uint32_t *seg, uint32_t seg_cap, uint32_t *n_seg, cudaStream_t st)
 {
     if (n_streams == 0) return cudaSuccess;
-    af_vad_segments_kernel<<<n_streams, 256, 0, st>>>(states, stride, n_frames, n_streams, seg, seg_cap, n_seg);
+    af_vad_segments_kernel<<<n_streams, SEG_THREADS, 0, st>>>(states, stride, n_frames, n_streams, seg, seg_cap, n_seg);
     return cudaGetLastError();
 }
 
