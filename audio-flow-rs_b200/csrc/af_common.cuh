@@ -23,20 +23,20 @@ constexpr int SF = 32;                       // frames per step: one per half-wa
 constexpr int STEP_SAMPLES = SF * HOP;       // 5120 new 16 kHz samples per step
 constexpr int CARRY = WIN - HOP;             // 240 samples shared with the next step
 constexpr int YLEN = STEP_SAMPLES + CARRY;   // 5360 samples live per step
-// A step's raw input is staged in N_PARTS fills, one stage buffer each: while the resampler warps work on one part the
-// other N_PARTS - 1 fills are in flight.  The boundaries are multiples of a resampler sweep (4 * RS_THREADS = 896
-// outputs).  Measured (cfg2, same box): two parts 0.577 ms, three parts 0.607 ms -- the third barrier round trip and
-// part prologue per step cost more than the deeper prefetch gains, so two it is (-DAF_N_PARTS=3 builds the other).
-#ifndef AF_N_PARTS
-#define AF_N_PARTS 2
-#endif
-constexpr int N_PARTS = AF_N_PARTS;
-__host__ __device__ constexpr int part_end(int k)   // outputs [part_end(k - 1), part_end(k)) of the step buffer form part k
+// A step's raw input is staged in PARTS fills that alternate between the two stage buffers: while the resampler warps
+// work on one part the next fill is in flight.  Two parts per step when half a step of raw input fits a buffer (mono,
+// i16 stereo), four when only a quarter does (f32 stereo at 48 kHz: 1344 outputs x 3 frames x 8 B = 32 256 B); the
+// boundaries are multiples of 32 outputs (the padding phase of the step buffer).  Measured for mono (cfg2, same box):
+// two parts 0.577 ms, three parts over three smaller buffers 0.607 ms -- the extra barrier round trip and part
+// prologue per step cost more than the deeper prefetch gains.
+constexpr int N_STAGE = 2;                   // stage buffers
+constexpr int MAX_PARTS = 4;
+__host__ __device__ constexpr int part_end(int parts, int k)   // outputs [part_end(k - 1), part_end(k)) of the step buffer form part k
 {
-    return N_PARTS == 2 ? (k == 0 ? 2688 : 5360) : (k == 0 ? 1792 : (k == 1 ? 3584 : 5360));
+    return parts == 4 ? (k == 0 ? 1344 : (k == 1 ? 2688 : (k == 2 ? 4032 : 5360))) : (k == 0 ? 2688 : 5360);
 }
-constexpr int PART_MAX_OUT = N_PARTS == 2 ? 2688 : 1792;   // most outputs one part produces
-constexpr int LAST_PART_LO = part_end(N_PARTS - 2);
+__host__ __device__ constexpr int part_max_out(int parts) { return parts == 4 ? 1344 : 2688; }   // most outputs one part produces
+constexpr int LAST_PART_LO2 = 2688;          // first output of the last part of a two-part step (the quad paths run on those)
 constexpr int TILE_FRAMES = 128;             // frames per tile (work unit of one CTA)
 constexpr int TILE_SAMPLES = TILE_FRAMES * HOP;   // 20480
 constexpr int FFT_WARPS = 16;                // "F": window + FFT + power, one frame per half-warp
@@ -119,7 +119,7 @@ constexpr int PB_COLS = PB_ROW;              // bins a padded weight quadruple m
 constexpr int PBUF_FLOATS = SF * PB_ROW;
 __host__ __device__ constexpr int pb_row(int q) { return ((q >> 1) & 3) + 8 * (q >> 3) + 4 * (q & 1); }
 __host__ __device__ constexpr int pb_frame(int row) { return 2 * ((row & 3) + 4 * (row >> 3)) + ((row >> 2) & 1); }
-constexpr int STAGE_BYTES = N_PARTS == 2 ? 32384 : 21632;   // one TMA-staged part of raw input (PART_MAX_OUT outputs x 3 x 4 B + halo)
+constexpr int STAGE_BYTES = 32384;           // one TMA-staged part of raw input (2688 outputs x 3 x 4 B + halo), two of them
 
 // formats / flags (mirror include/audioflow_gpu.h)
 enum : uint16_t { FMT_F32 = 0, FMT_I16 = 1 };
@@ -139,7 +139,8 @@ struct StreamDev {
     const float *frac;       // RS_TABLE: f32 fractional offsets by output index
     uint32_t tile_begin;     // first global tile of this stream
     uint32_t n_tiles;
-    uint32_t staged;         // 1: the step input fits the shared-memory stage (bulk-copy path)
+    uint32_t staged;         // parts per step when the input is staged through shared memory (2 or 4); 0: it does not fit
+                             // (taps come from global memory; the step still runs as two parts)
     uint32_t pad_;
 };
 enum : uint32_t { RS_PASSTHROUGH = 0, RS_EXACT = 1, RS_TABLE = 2 };
@@ -153,7 +154,7 @@ struct FillDesc {
                              // staged (unchecked global loads); 0: checked path
     uint32_t pad_[2];
 };
-constexpr int TILE_FILLS = N_PARTS * (TILE_FRAMES / SF);   // parts per tile
+constexpr int TILE_FILLS = MAX_PARTS * (TILE_FRAMES / SF);   // fill descriptors per tile (fill[parts * step + part])
 
 // one tile (128 frames of one stream) with everything the kernel would otherwise have to derive with 64-bit
 // divisions: planned once per batch on the host (plan_tile, af_device.cuh), or per tick by the session set-up kernel
@@ -165,7 +166,7 @@ struct alignas(16) TileDev {
     uint32_t n_steps;        // steps of 32 frames
     uint32_t tile_end;       // the tile owns stream samples [tile * TILE_SAMPLES, tile_end)
     uint32_t n_frames;       // STFT frames of the stream (copy)
-    uint32_t pad_;
+    uint32_t parts;          // stage fills per step: 2 or 4 (fill[parts * step + part])
     FillDesc fill[TILE_FILLS];
     StreamDev sdesc;         // copy of the stream's descriptor: one level of loads per tile instead of two
     uint32_t inc_k, inc_rem; // position increment of RS_THREADS outputs: (RS_THREADS * p) / q and % q
@@ -248,6 +249,7 @@ struct FusedParams {
     float log_scale;         // ln(2) (natural log) or log10(2): multiplies log2(mel)
     uint32_t use_stage;      // 0: plain global loads everywhere ("sync" variant)
     uint32_t layout;         // warp-to-role layout (warp_role)
+    uint32_t quarters;       // 1: some tile stages its input in quarter steps (TileDev::parts == 4): general kernel instance
 };
 
 }  // namespace af

@@ -74,13 +74,14 @@ __host__ __device__ inline void plan_tile(const StreamDev &s, uint32_t stream, u
 {
     const uint32_t n_tile0 = tile * (uint32_t)TILE_SAMPLES;
     const uint32_t tile_end = s.n_out - n_tile0 < (uint32_t)TILE_SAMPLES ? s.n_out : n_tile0 + (uint32_t)TILE_SAMPLES;
+    const int parts = s.staged == 4u ? 4 : 2;
     t->stream = stream; t->tile = tile;
     long long k0 = 0; uint32_t rem0 = 0;
     if (s.mode != RS_PASSTHROUGH) resample_pos(n_tile0, s.p, s.q, &k0, &rem0);
     t->k0 = (int32_t)k0; t->rem0 = rem0;
     t->n_steps = (tile_end - n_tile0 + STEP_SAMPLES - 1) / STEP_SAMPLES;
     t->tile_end = tile_end;
-    t->n_frames = s.n_frames; t->pad_ = 0;
+    t->n_frames = s.n_frames; t->parts = (uint32_t)parts;
     t->sdesc = s;
     {
         const uint32_t inc = (uint32_t)RS_THREADS * s.p;
@@ -89,12 +90,12 @@ __host__ __device__ inline void plan_tile(const StreamDev &s, uint32_t stream, u
     const uint32_t ch = s.channels, bps = s.format == FMT_I16 ? 2u : 4u;
     const uint32_t left = s.n_out - n_tile0;                       // outputs from the tile start to the stream end
     for (int j = 0; j < TILE_FILLS; ++j) {
-        const uint32_t g = (uint32_t)j / (uint32_t)N_PARTS;
-        const int h = j % N_PARTS;
+        const uint32_t g = (uint32_t)j / (uint32_t)parts;
+        const int h = j % parts;
         FillDesc d;
         d.src = reinterpret_cast<const char *>(s.data); d.bytes = 0; d.lo = 0; d.hi = 0; d.interior = 0; d.pad_[0] = d.pad_[1] = 0;
-        const uint32_t d_first = g * STEP_SAMPLES + (uint32_t)(h == 0 ? (g == 0 ? 0 : CARRY) : part_end(h - 1));
-        const uint32_t d_full = g * STEP_SAMPLES + (uint32_t)part_end(h);
+        const uint32_t d_first = g * STEP_SAMPLES + (uint32_t)(h == 0 ? (g == 0 ? 0 : CARRY) : part_end(parts, h - 1));
+        const uint32_t d_full = g * STEP_SAMPLES + (uint32_t)part_end(parts, h);
         const uint32_t d_last = d_full < left ? d_full : left;
         if (g < t->n_steps && d_first < d_last) {
             // floor(position) of output n_tile0 + d (the host guarantees (TILE_SAMPLES + YLEN) * p + q < 2^32)

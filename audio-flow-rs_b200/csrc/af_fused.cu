@@ -28,7 +28,7 @@ struct RsTile {
 };
 
 struct __align__(128) FusedSmem {
-    unsigned char stage[N_PARTS][STAGE_BYTES];       // raw interleaved input of the parts of a step (bulk-copy targets)
+    unsigned char stage[N_STAGE][STAGE_BYTES];       // raw interleaved input of a part of a step (bulk-copy targets)
     float ybuf[2][YBUF_FLOATS];                      // padded 16 kHz samples of two consecutive steps
     float scr[FFT_WARPS * SCR_FLOATS_PER_WARP];      // per FFT warp transpose scratch
     float pbuf[2][PBUF_FLOATS];                      // 4*|X[k]|^2, [pb_row(frame)][bin], two consecutive steps
@@ -40,12 +40,12 @@ struct __align__(128) FusedSmem {
                                                      // carry the record across the transform (the mel warps lag < 3 steps)
     MelTables mel;
     // pipeline barriers (mbarriers): full = data ready for the consumer, empty = buffer may be overwritten
-    unsigned long long stage_full[N_PARTS], stage_empty[N_PARTS];
+    unsigned long long stage_full[N_STAGE], stage_empty[N_STAGE];
     unsigned long long y_full[2], y_empty[2];
     unsigned long long p_full[2], p_empty[2];
     // metadata of the fill held by stage[h], written by the issuing thread before its arrive
-    unsigned long long st_lo[N_PARTS], st_hi[N_PARTS];   // interleaved element range [lo, hi) held by the stage
-    uint32_t st_interior[N_PARTS];                   // 1: every tap of the half step is inside the stage and the stream;
+    unsigned long long st_lo[N_STAGE], st_hi[N_STAGE];   // interleaved element range [lo, hi) held by the stage
+    uint32_t st_interior[N_STAGE];                   // 1: every tap of the half step is inside the stage and the stream;
                                                      // 2: inside the stream but not staged (unchecked global loads)
     // resampler role: every warp keeps its own copy of the tile's stream descriptor and first-output position, so that
     // a new tile needs no synchronisation among the resampler warps
@@ -225,7 +225,7 @@ __device__ __forceinline__ void tmem_wait_ld(float2 &a) { asm volatile("tcgen05.
 
 // ---- geometry of a tile, recomputed by every role from the same tables ----
 struct TileGeo {
-    uint32_t stream, n_tile0, tile_end, f_tile0, n_steps, n_frames;
+    uint32_t stream, n_tile0, tile_end, f_tile0, n_steps, n_frames, parts;
 };
 __device__ __forceinline__ TileGeo tile_geo(const FusedParams &P, uint32_t tile, uint32_t *n_frames)
 {
@@ -237,11 +237,11 @@ __device__ __forceinline__ TileGeo tile_geo(const FusedParams &P, uint32_t tile,
     t.f_tile0 = td->tile * TILE_FRAMES;
     t.n_steps = td->n_steps;
     t.n_frames = td->n_frames;
+    t.parts = td->parts;
     if (n_frames) *n_frames = td->n_frames;
     return t;
 }
-__device__ __forceinline__ int half_lo(uint32_t g, int h) { return h == 0 ? (g == 0 ? 0 : CARRY) : part_end(h - 1); }
-__device__ __forceinline__ int half_hi(int h) { return part_end(h); }
+__device__ __forceinline__ int part_lo(uint32_t g, int parts, int k) { return k == 0 ? (g == 0 ? 0 : CARRY) : part_end(parts, k - 1); }
 
 // ---- stage fill (descriptors planned per tile by plan_tile, af_device.cuh) ----
 // issued by ONE thread; always completes one phase of stage_full[h]
@@ -851,6 +851,7 @@ __device__ __forceinline__ void role_mel(FusedSmem &sm, const FusedParams &P, in
     else role_mel_run<false, false>(sm, P, mw, lane);
 }
 
+template <bool QUARTERS>
 __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, int lane)
 {
     // Two cursors.  FILLS (lane 0): the bulk copy of a half step is issued as soon as the resampler warps have
@@ -862,29 +863,32 @@ __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, in
     // fill cursor (lane 0): tile, step, half.  The descriptors (source pointer, byte count, staged range) were planned
     // per tile on the host; the next one is fetched right after a fill is issued, so that issuing a fill is a
     // handful of instructions once its stage buffer is released.
-    uint32_t tile_f = blockIdx.x, g_f = 0, it_f = 0, steps_f = 0;
+    // The cursor counts PAIRS of fills (one per stage buffer): a step is one pair, or two when its input is staged in
+    // quarters (fill[parts * step + part] = fill[2 * pair + half]), so a pair index works like the step index did.
+    uint32_t tile_f = blockIdx.x, g_f = 0, it_f = 0, steps_f = 0;   // pair inside the tile, pairs issued so far, pairs of the tile
     int h_f = 0;
     bool fill_live = tile_f < P.n_tiles;
     FillDesc d_next{};
     auto fetch_desc = [&]() {
-        const uint4 *src = reinterpret_cast<const uint4 *>(&P.tiles[tile_f].fill[N_PARTS * g_f + h_f]);
+        const uint4 *src = reinterpret_cast<const uint4 *>(&P.tiles[tile_f].fill[2 * g_f + h_f]);
         const uint4 a = __ldg(src), b = __ldg(src + 1);
         d_next.src = reinterpret_cast<const char *>(((unsigned long long)a.y << 32) | a.x);
         d_next.bytes = a.z; d_next.lo = a.w; d_next.hi = b.x; d_next.interior = b.y;
     };
-    if (lane == 0 && fill_live) { steps_f = P.tiles[tile_f].n_steps; fetch_desc(); }
+    auto tile_pairs = [&]() { return QUARTERS ? P.tiles[tile_f].n_steps * (P.tiles[tile_f].parts >> 1) : P.tiles[tile_f].n_steps; };
+    if (lane == 0 && fill_live) { steps_f = tile_pairs(); fetch_desc(); }
     auto issue_next = [&](bool blocking) {                  // lane 0 only
         if (!fill_live) return;
         if (blocking) { AF_WAIT(&sm.stage_empty[h_f], (it_f & 1u) ^ 1u, 0); }
         else if (!mbar_test(&sm.stage_empty[h_f], (it_f & 1u) ^ 1u)) return;
         AF_TIC
         issue_fill(sm, P, d_next, h_f);
-        if (++h_f == N_PARTS) {
+        if (++h_f == 2) {
             h_f = 0; ++it_f;
             if (++g_f == steps_f) {
                 g_f = 0; tile_f += gridDim.x;
                 fill_live = tile_f < P.n_tiles;
-                if (fill_live) steps_f = P.tiles[tile_f].n_steps;
+                if (fill_live) steps_f = tile_pairs();
             }
         }
         if (fill_live) fetch_desc();
@@ -894,7 +898,7 @@ __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, in
         if (lane == 0) issue_next(false);
         __syncwarp();
     };
-    uint32_t it = 0;
+    uint32_t it = 0, pairs_before = 0;                      // steps so far, and the fill pairs they took
     bool have_prev = false;
     uint32_t prev_f0 = 0, prev_nf = 0, prev_stream = 0, prev_it = 0;
     for (uint32_t tile = blockIdx.x;; tile += gridDim.x) {
@@ -905,7 +909,12 @@ __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, in
         const uint32_t n_steps = live ? t.n_steps : 1u;        // one drain iteration after the last tile
         for (uint32_t g = 0; g < n_steps; ++g) {
             if (live) {
-                if (lane == 0) while (fill_live && it_f <= it) issue_next(true);   // the fills of step `it` are out
+                // the fills of the earlier steps and the first pair of step `it` are out (a second pair, if any, needs the
+                // resampler warps to release the buffers first: it goes out through service() or the next trip here)
+                if (lane == 0) while (fill_live && it_f <= pairs_before) issue_next(true);
+                __syncwarp();
+            } else {
+                if (lane == 0) while (fill_live) issue_next(true);      // drain trip: the last step's later parts, if any
                 __syncwarp();
             }
             if (have_prev) {
@@ -922,6 +931,7 @@ __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, in
                 have_prev = true;
                 prev_f0 = t.f_tile0 + g * SF; prev_nf = n_frames; prev_stream = t.stream; prev_it = it;
                 ++it;
+                pairs_before += QUARTERS ? (t.parts >> 1) : 1u;
             } else {
                 have_prev = false;
             }
@@ -931,9 +941,11 @@ __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, in
     AF_STATS_FLUSH(2, lane);
 }
 
+template <bool QUARTERS>
 __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &P, int rtid, int lane)
 {
     uint32_t it = 0;
+    uint32_t uses0 = 0;                                     // uses of EACH stage buffer before the current step (see role_vad: fills0)
     AF_STATS_DECL
     // the descriptor of a tile's stream is fetched one tile ahead into registers: lanes 0..15 of every warp hold one
     // word of the StreamDev each, lane 16 the planned position of the tile's first output
@@ -950,6 +962,7 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
         nx_t.tile_end = td->tile_end;
         nx_t.n_steps = td->n_steps;
         nx_t.n_frames = td->n_frames;
+        nx_t.parts = td->parts;
         if (lane < (int)(sizeof(StreamDev) / 4)) nx_word = reinterpret_cast<const uint32_t *>(sp)[lane];
         if (lane == 16) { nx_k = td->k0; nx_rem = td->rem0; nx_inck = td->inc_k; nx_incr = td->inc_rem; }   // planned on the host
     };
@@ -974,6 +987,8 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
         // the hot case -- 48 kHz mono f32 -- bypasses the format dispatch: its interior half steps go straight to the quad loop
         const bool hot = kind == K_F32_1 && s.mode != RS_PASSTHROUGH && s.q == 1 && s.p == 3;
         const int tile_k = rt.tile_k;
+        // parts per step: a compile-time 2 in the kernel instance for batches without quarter-staged streams
+        const uint32_t parts = QUARTERS ? t.parts : 2u;
 
         for (uint32_t g = 0; g < t.n_steps; ++g, ++it) {
             const int b = (int)(it & 1u);
@@ -989,7 +1004,7 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
                     // the quad paths give every output quad a fixed owner thread: each thread carries the quad it wrote
                     // itself in the previous step -- no synchronisation among the resampler warps
                     constexpr int QS = 4 * RS_THREADS;
-                    int c4 = LAST_PART_LO + 4 * rtid;
+                    int c4 = LAST_PART_LO2 + 4 * rtid;
                     c4 += ((STEP_SAMPLES - c4 + QS - 1) / QS) * QS;           // first own quad at or after STEP_SAMPLES
                     if (c4 < YLEN)
                         *reinterpret_cast<float4 *>(out.yb + ypad(c4 - STEP_SAMPLES)) = *reinterpret_cast<const float4 *>(prev + ypad(c4));
@@ -1000,9 +1015,10 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
             }
             AF_TOC(3)
 #pragma unroll 1
-            for (int h = 0; h < N_PARTS; ++h) {
-                AF_WAIT(&sm.stage_full[h], it & 1u, 1);
-                const int i_lo = half_lo(g, h), i_hi = half_hi(h);
+            for (int k = 0; k < (int)parts; ++k) {
+                const int h = k & 1;                            // parts alternate between the two stage buffers
+                AF_WAIT(&sm.stage_full[h], (uses0 + ((uint32_t)k >> 1)) & 1u, 1);
+                const int i_lo = part_lo(g, (int)parts, k), i_hi = part_end((int)parts, k);
                 AF_TIC2
                 if (hot && sm.st_interior[h] == 1u) {
                     resample_quads_48k(reinterpret_cast<const float *>(sm.stage[h]) + (tile_k + 3 * (int)toff - 1 - (int)(uint32_t)sm.st_lo[h]),
@@ -1017,7 +1033,7 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
                     }
                 }
                 AF_TOC(4)
-                if (h == N_PARTS - 1) prev_quads = quad_tile && sm.st_interior[N_PARTS - 1] != 0u;   // (read before the stage is released)
+                if (k == (int)parts - 1) prev_quads = quad_tile && parts == 2u && sm.st_interior[1] != 0u;   // (read before the stage is released)
                 warp_arrive(&sm.stage_empty[h], lane);          // this warp no longer reads stage[h] or its metadata
             }
             if (rtid == 0) {
@@ -1031,11 +1047,15 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
                 sm.yinfo[b] = info;
             }
             warp_arrive(&sm.y_full[b], lane);
+            uses0 += parts >> 1;
         }
     }
     AF_STATS_FLUSH(3, lane);
 }
 
+// QUARTERS: some stream of the batch stages its input in quarter steps (f32 stereo); the other instance keeps the
+// two-parts-per-step constants folded in (measured: the general one costs mono batches 1.4 %, 2.8 % with the VAD on)
+template <bool QUARTERS>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1052,7 +1072,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
         for (int i = tid; i < 2 * PBUF_FLOATS; i += FUSED_THREADS) sm.pbuf[0][i] = 0.0f;
     }
     if (tid == 0) {
-        for (int h = 0; h < N_PARTS; ++h) {
+        for (int h = 0; h < N_STAGE; ++h) {
             mbar_init(&sm.stage_full[h], 1);
             mbar_init(&sm.stage_empty[h], RS_WARPS);
         }
@@ -1102,8 +1122,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
     const WarpRole wr = warp_role(P.layout, warp);
     if (wr.role == ROLE_F) role_fft(sm, P, wr.index, lane);
     else if (wr.role == ROLE_M) role_mel(sm, P, wr.index, lane);
-    else if (wr.role == ROLE_V) role_vad(sm, P, lane);
-    else role_resample(sm, P, wr.index * 32 + lane, lane);
+    else if (wr.role == ROLE_V) role_vad<QUARTERS>(sm, P, lane);
+    else role_resample<QUARTERS>(sm, P, wr.index * 32 + lane, lane);
 
     // every role has drained its pipeline: release the tensor memory
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1131,12 +1151,13 @@ cudaError_t launch_fused(const FusedParams &P, int n_ctas, cudaStream_t st)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(af_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(FusedSmem));
+        cudaError_t e = cudaFuncSetAttribute(af_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(af_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    af_fused_kernel<<<n_ctas, FUSED_THREADS, sizeof(FusedSmem), st>>>(P);
+    if (P.quarters) af_fused_kernel<true><<<n_ctas, FUSED_THREADS, sizeof(FusedSmem), st>>>(P);
+    else af_fused_kernel<false><<<n_ctas, FUSED_THREADS, sizeof(FusedSmem), st>>>(P);
     return cudaGetLastError();
 }
 

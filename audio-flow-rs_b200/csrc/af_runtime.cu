@@ -661,6 +661,7 @@ struct SubBatch {                     // a group of streams resident on the devi
     std::vector<size_t> in_off;       // host mode: byte offset of each stream inside the slot input buffer
     size_t in_bytes = 0;
     uint32_t *d_scan = nullptr;       // long streams: scratch of the many-CTA VAD scan (launch_vad_scan)
+    bool quarters = false;            // some stream stages its input in quarter steps (f32 stereo)
 };
 
 }  // namespace
@@ -692,6 +693,7 @@ int build_sub(af_batch *b, SubBatch &sb, const void *slot_in_base)
     // (re)build the device tables of a sub-batch; slot_in_base != null (host mode) rebases the inputs
     sb.h_streams.resize(sb.count);
     sb.h_tiles.clear();
+    sb.quarters = false;
     std::vector<uint32_t> nf(sb.count), nv(sb.count);
     for (size_t i = 0; i < sb.count; ++i) {
         const HostStream &hs = b->streams[sb.first + i];
@@ -705,10 +707,15 @@ int build_sub(af_batch *b, SubBatch &sb, const void *slot_in_base)
         d.frac = hs.table ? hs.table->d : nullptr;
         {   // does the raw input of one step fit the shared-memory stage of the fused kernel?
             const uint64_t bps = hs.desc.format == AF_FMT_I16 ? 2 : 4;
-            // (a step is staged in N_PARTS fills of at most PART_MAX_OUT outputs each)
-            const uint64_t frames = hs.mode == RS_PASSTHROUGH ? (uint64_t)PART_MAX_OUT : ((uint64_t)PART_MAX_OUT * hs.p + hs.q - 1) / hs.q;
-            d.staged = hs.desc.channels <= 2 && (frames + 8) * hs.desc.channels * bps + 32 <= (uint64_t)STAGE_BYTES;
+            // (a step is staged in two fills of half a step each, or in four of a quarter: whichever fits a stage buffer)
+            d.staged = 0;
+            for (int parts = 2; parts <= MAX_PARTS && !d.staged; parts += 2) {
+                const uint64_t outs = (uint64_t)part_max_out(parts);
+                const uint64_t frames = hs.mode == RS_PASSTHROUGH ? outs : (outs * hs.p + hs.q - 1) / hs.q;
+                if (hs.desc.channels <= 2 && (frames + 8) * hs.desc.channels * bps + 32 <= (uint64_t)STAGE_BYTES) d.staged = (uint32_t)parts;
+            }
         }
+        if (d.staged == 4u) sb.quarters = true;
         d.tile_begin = (uint32_t)sb.h_tiles.size();
         d.n_tiles = (hs.n_out + TILE_SAMPLES - 1) / TILE_SAMPLES;
         for (uint32_t t = 0; t < d.n_tiles; ++t) {
@@ -753,6 +760,7 @@ int run_sub(af_batch *b, SubBatch &sb, float *pcm, uint64_t pcm_stride, float *l
         P.log_scale = cfg.log10 ? 0.30102999566398120f : 0.69314718055994531f;   // log10(2) : ln(2)
         P.use_stage = g_ctx.variant == "sync" ? 0u : 1u;
         P.layout = fused_layout(stft_vad);
+        P.quarters = sb.quarters ? 1u : 0u;
         const int n_ctas = (int)std::min<size_t>(sb.h_tiles.size(), (size_t)g_ctx.sm_count);   // one persistent CTA per SM
         AF_CUDA(launch_fused(P, n_ctas, st));
         count_launch();
@@ -1199,7 +1207,7 @@ AF_API int af_session_create(af_pipeline *p, size_t n_streams, uint32_t sample_r
             memset(&d, 0, sizeof(d));
             d.data = s->y_buf[i] + k * s->y_stride;
             d.channels = 1; d.format = FMT_F32; d.p = 1; d.q = 1; d.mode = RS_PASSTHROUGH;
-            d.tile_begin = (uint32_t)k; d.n_tiles = 1; d.staged = 1;
+            d.tile_begin = (uint32_t)k; d.n_tiles = 1; d.staged = 2;
         }
         AF_CUDA(cudaMemcpy(s->d_tab[i], tab.data(), n_streams * sizeof(StreamDev), cudaMemcpyHostToDevice));
     }
