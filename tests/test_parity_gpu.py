@@ -270,6 +270,9 @@ def test_batch_mixed_streams_match_oracle(af, orc, variant):
         (26, 0.002, 48000, 1, "f32"), (27, 0.02, 48000, 1, "f32"), (28, 1.28 + 0.025, 48000, 1, "f32"),
         (29, 1.0, 32000, 1, "i16"), (30, 0.9, 22050, 3, "f32"), (31, 1.28, 48000, 1, "f32"),
         (32, 2.5601, 48000, 1, "i16"), (33, 0.4, 8000, 1, "f32"),
+        # f32 stereo is staged in quarter steps: 44.1 kHz (general-ratio quads), a length that ends inside a quarter,
+        # and one that ends exactly on a step boundary (5120 outputs = 0.32 s)
+        (34, 2.1, 44100, 2, "f32"), (35, 1.28 + 0.333, 48000, 2, "f32"), (36, 0.32 * 3 + 0.0001, 48000, 2, "f32"),
     ]
     streams = []
     for (sid, sec, rate, ch, fmt) in cases:
