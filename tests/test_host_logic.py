@@ -167,3 +167,29 @@ def test_ring_buffer_edges():
     assert got == [float(i) for i in range(len(got))]
     with pytest.raises(Exception):
         af.RingBuffer(0)                                                  # the reference would divide by zero on first use
+
+
+# ---- the other host mirrors stay in step with the header ----
+def test_cpp_mirror_compiles_against_the_header():
+    """host/audioflow.hpp (the C++ stand-in for the Rust types) and its KAT program must compile against
+    include/audioflow_gpu.h; running it needs a GPU, compiling it does not."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    host = os.path.join(ROOT, "audio-flow-rs_b200", "host")
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(host, "test_reference_kat.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_rust_shim_binds_only_declared_symbols():
+    """Every `pub fn af_*` of the Rust extern block (rust/src/ffi.rs; source only here: no Rust toolchain in the image)
+    must be a symbol the header declares and the library exports."""
+    ffi = open(os.path.join(ROOT, "audio-flow-rs_b200", "rust", "src", "ffi.rs")).read()
+    names = set(re.findall(r"pub fn (af_[a-z0-9_]+)\s*\(", ffi))
+    assert len(names) >= 20
+    declared = set(_declared_symbols())
+    missing = sorted(names - declared)
+    assert not missing, f"ffi.rs binds symbols the header does not declare: {missing}"
