@@ -1119,6 +1119,14 @@ struct af_session {
     bool framing = false;
     StreamDev *d_tab[2] = {nullptr, nullptr};
     TileDev *d_tiles = nullptr;
+    // packed ticks (STFT frames): the rows of y_buf are a whole number of hops apart, so `pk_rows` consecutive streams
+    // read as ONE virtual stream whose frame slot r * pk_slots + j is frame j of row r (the slots >= T straddle rows and
+    // are ignored).  A tick of two frames per stream then fills the fused kernel's 32-frame steps instead of leaving
+    // 30 of 32 slots empty, and the tiles are planned once (the virtual streams never change length).
+    bool packed = false;
+    uint32_t pk_slots = 0, pk_rows = 0, pk_n = 0;          // frame slots per row, rows per virtual stream, virtual streams
+    StreamDev *d_ptab[2] = {nullptr, nullptr};
+    TileDev *d_ptiles[2] = {nullptr, nullptr};
     VadState *d_vad = nullptr;
     float *d_energy = nullptr; uint64_t energy_stride = 0;
     float *d_frac = nullptr; size_t frac_cap = 0;
@@ -1144,6 +1152,8 @@ AF_API void af_session_destroy(af_session *s)
         if (s->in_buf[i]) cudaFree(s->in_buf[i]);
         if (s->y_buf[i]) cudaFree(s->y_buf[i]);
         if (s->d_tab[i]) cudaFree(s->d_tab[i]);
+        if (s->d_ptab[i]) cudaFree(s->d_ptab[i]);
+        if (s->d_ptiles[i]) cudaFree(s->d_ptiles[i]);
     }
     if (s->d_tiles) cudaFree(s->d_tiles);
     if (s->d_vad) cudaFree(s->d_vad);
@@ -1192,9 +1202,18 @@ AF_API int af_session_create(af_pipeline *p, size_t n_streams, uint32_t sample_r
     s->in_stride = round_up(2 * RS_POLY + RS_CHUNK + s->max_tick_frames + 8, 4);
     const uint64_t max_new_y = af_resample_max_output(sample_rate, OUT_RATE, s->max_tick_frames + RS_CHUNK) + 8;
     s->y_stride = round_up(s->frame_len + s->hop + max_new_y + 8, 4);
+    s->packed = s->framing && s->frame_len == WIN && s->hop == HOP;
+    if (s->packed) s->y_stride = round_up(s->y_stride, HOP);           // rows a whole number of hops apart (HOP % 4 == 0)
     const uint64_t max_frames = (s->y_stride) / s->hop + 2;
     s->energy_stride = round_up(max_frames, 4);
     s->lm_stride = round_up(max_frames * std::max<uint32_t>(cfg.n_mels, 1), 4);
+    if (s->packed) {
+        s->pk_slots = (uint32_t)(s->y_stride / HOP);
+        s->pk_rows = std::max<uint32_t>(1u, (uint32_t)SF / s->pk_slots);   // about one 32-frame step per virtual stream
+        s->pk_n = (uint32_t)((n_streams + s->pk_rows - 1) / s->pk_rows);
+        s->energy_stride = s->pk_slots;                                  // frame slot pitch of a real stream
+        s->lm_stride = (uint64_t)s->pk_slots * std::max<uint32_t>(cfg.n_mels, 1);
+    }
     s->st_stride = round_up(max_frames, 16);
     for (int i = 0; i < 2; ++i) {
         AF_CUDA(cudaMalloc(&s->in_buf[i], n_streams * s->in_stride * sizeof(float)));
@@ -1210,6 +1229,25 @@ AF_API int af_session_create(af_pipeline *p, size_t n_streams, uint32_t sample_r
             d.tile_begin = (uint32_t)k; d.n_tiles = 1; d.staged = 2;
         }
         AF_CUDA(cudaMemcpy(s->d_tab[i], tab.data(), n_streams * sizeof(StreamDev), cudaMemcpyHostToDevice));
+        if (s->packed) {
+            std::vector<StreamDev> ptab(s->pk_n);
+            std::vector<TileDev> ptiles(s->pk_n);
+            for (uint32_t v = 0; v < s->pk_n; ++v) {
+                StreamDev &d = ptab[v];
+                memset(&d, 0, sizeof(d));
+                const uint64_t rows = std::min<uint64_t>(s->pk_rows, n_streams - (uint64_t)v * s->pk_rows);
+                d.data = s->y_buf[i] + (uint64_t)v * s->pk_rows * s->y_stride;
+                d.n_samples = rows * s->y_stride; d.n_in = d.n_out = (uint32_t)d.n_samples;
+                d.n_frames = d.n_vad_frames = 1 + (d.n_out - WIN) / HOP;
+                d.channels = 1; d.format = FMT_F32; d.p = 1; d.q = 1; d.mode = RS_PASSTHROUGH;
+                d.tile_begin = v; d.n_tiles = 1; d.staged = 2;
+                plan_tile(d, v, 0, &ptiles[v]);
+            }
+            AF_CUDA(cudaMalloc(&s->d_ptab[i], s->pk_n * sizeof(StreamDev)));
+            AF_CUDA(cudaMalloc(&s->d_ptiles[i], s->pk_n * sizeof(TileDev)));
+            AF_CUDA(cudaMemcpy(s->d_ptab[i], ptab.data(), s->pk_n * sizeof(StreamDev), cudaMemcpyHostToDevice));
+            AF_CUDA(cudaMemcpy(s->d_ptiles[i], ptiles.data(), s->pk_n * sizeof(TileDev), cudaMemcpyHostToDevice));
+        }
     }
     if (s->y_stride > (uint64_t)TILE_SAMPLES) return fail(AF_ERR_INVALID, "max_tick_samples too large for a session (%u)", max_tick_samples);
     AF_CUDA(cudaMalloc(&s->d_tiles, n_streams * sizeof(TileDev)));    // planned per tick by the session set-up kernel
@@ -1316,11 +1354,12 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
         float *lm = nullptr; uint64_t lm_stride = 0;
         uint8_t *states = nullptr; uint64_t st_stride = 0;
         if (cfg.n_mels && o->logmel) {
-            if (mem == AF_MEM_HOST) {
+            if (mem == AF_MEM_HOST || s->packed) {              // (packed ticks write every frame slot: internal buffer, then a strided copy)
                 if (!s->d_lm) AF_CUDA(cudaMalloc(&s->d_lm, S * s->lm_stride * sizeof(float)));
                 lm = s->d_lm; lm_stride = s->lm_stride;
             } else { lm = o->logmel; lm_stride = o->logmel_stride; }
-            if (lm_stride < (uint64_t)T * cfg.n_mels) return fail(AF_ERR_CAPACITY, "logmel_stride too small for %u frames", T);
+            if (lm_stride < (uint64_t)T * cfg.n_mels || o->logmel_stride < (uint64_t)T * cfg.n_mels)
+                return fail(AF_ERR_CAPACITY, "logmel_stride too small for %u frames", T);
         }
         if (cfg.vad_enable && o->vad) {
             if (mem == AF_MEM_HOST) {
@@ -1330,13 +1369,20 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
             if (st_stride < T) return fail(AF_ERR_CAPACITY, "vad_stride too small for %u frames", T);
         }
         if (stft_frames) {
-            AF_CUDA(launch_session_setup(s->d_tab[s->y_cur], s->d_tiles, (uint32_t)S, y_total, T, cfg.vad_enable ? T : 0, st));
             FusedParams P{};
-            P.streams = s->d_tab[s->y_cur]; P.tiles = s->d_tiles; P.n_tiles = (uint32_t)S;
+            uint64_t vrows = 1;                                 // real streams per stream of the launch
+            if (s->packed) {
+                if (T + 2 > s->pk_slots) return fail(AF_ERR_CAPACITY, "internal: %u frames do not fit %u frame slots", T, s->pk_slots);
+                P.streams = s->d_ptab[s->y_cur]; P.tiles = s->d_ptiles[s->y_cur]; P.n_tiles = s->pk_n;
+                vrows = s->pk_rows;
+            } else {
+                AF_CUDA(launch_session_setup(s->d_tab[s->y_cur], s->d_tiles, (uint32_t)S, y_total, T, cfg.vad_enable ? T : 0, st));
+                P.streams = s->d_tab[s->y_cur]; P.tiles = s->d_tiles; P.n_tiles = (uint32_t)S;
+            }
             P.fft = g_ctx.d_fft; P.mel = s->pipe->d_mel;
             P.pcm = nullptr; P.pcm_stride = 0;
-            P.logmel = lm; P.logmel_stride = lm_stride;
-            P.energy = cfg.vad_enable ? s->d_energy : nullptr; P.energy_stride = s->energy_stride;
+            P.logmel = lm; P.logmel_stride = lm_stride * vrows;
+            P.energy = cfg.vad_enable ? s->d_energy : nullptr; P.energy_stride = s->energy_stride * vrows;
             P.n_mels = lm ? cfg.n_mels : 0;
             P.do_energy = cfg.vad_enable ? 1 : 0;
             P.log_floor = cfg.log_floor;
@@ -1344,7 +1390,7 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
             P.use_stage = g_ctx.variant == "sync" ? 0u : 1u;
             P.layout = fused_layout(P.do_energy != 0);
             if (P.n_mels || P.do_energy) {
-                AF_CUDA(launch_fused(P, (int)std::min<size_t>(S, (size_t)g_ctx.sm_count), st));
+                AF_CUDA(launch_fused(P, (int)std::min<size_t>(P.n_tiles, (size_t)g_ctx.sm_count), st));
                 count_launch(2);
             }
         } else {
@@ -1364,6 +1410,9 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
             AF_CUDA(launch_vad_scan(sj, st));
             count_launch();
         }
+        if (mem == AF_MEM_DEVICE && lm && lm != o->logmel)
+            AF_CUDA(cudaMemcpy2DAsync(o->logmel, o->logmel_stride * sizeof(float), lm, lm_stride * sizeof(float),
+                                      (size_t)T * cfg.n_mels * sizeof(float), S, cudaMemcpyDeviceToDevice, st));
         if (mem == AF_MEM_HOST) {
             if (lm) AF_CUDA(cudaMemcpy2DAsync(o->logmel, o->logmel_stride * sizeof(float), lm, lm_stride * sizeof(float),
                                               (size_t)T * cfg.n_mels * sizeof(float), S, cudaMemcpyDeviceToHost, st));
