@@ -1115,6 +1115,9 @@ struct af_session {
     // 16 kHz carry (samples not yet covered by an emitted frame), ping-pong
     float *y_buf[2] = {nullptr, nullptr}; uint64_t y_stride = 0; int y_cur = 0;
     uint32_t y_len = 0;
+    // frames / samples at the front of the current buffers that the NEXT tick's ingest / resample kernels skip: the
+    // compaction after a tick costs no kernel of its own
+    uint32_t in_drop = 0, y_drop = 0;
     uint32_t frame_len = WIN, hop = HOP;   // framing of the features / VAD
     bool framing = false;
     StreamDev *d_tab[2] = {nullptr, nullptr};
@@ -1173,7 +1176,7 @@ AF_API int af_session_reset(af_session *s)
 {
     if (!s) return fail(AF_ERR_INVALID, "null session");
     s->rec.init(s->rate, OUT_RATE);
-    s->in_cur = 0; s->y_cur = 0; s->y_len = 0; s->frames_emitted = 0;
+    s->in_cur = 0; s->y_cur = 0; s->y_len = 0; s->frames_emitted = 0; s->in_drop = 0; s->y_drop = 0;
     s->in_len = 2 * RS_POLY;                       // rubato starts with 16 zero frames of history
     s->in_base = -2 * RS_POLY;
     AF_CUDA(cudaMemset(s->in_buf[0], 0, s->S * s->in_stride * sizeof(float)));
@@ -1297,12 +1300,13 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
     const uint32_t chunks = s->rec.passthrough ? 0 : avail / RS_CHUNK;
     SessionIngest ing{};
     ing.old_buf = s->in_buf[s->in_cur]; ing.new_buf = s->in_buf[s->in_cur ^ 1]; ing.buf_stride = s->in_stride;
-    ing.drop = 0; ing.keep = s->in_len;
+    ing.drop = s->in_drop; ing.keep = s->in_len;                  // (the previous tick's consumed chunks are dropped here)
     ing.input = d_in; ing.in_stride_bytes = d_in_stride_bytes; ing.n_samples = n_samples; ing.n_new_frames = n_new;
     ing.channels = s->channels; ing.format = s->format;
     AF_CUDA(launch_session_ingest(ing, (uint32_t)S, st));
     count_launch();
     s->in_cur ^= 1;
+    s->in_drop = 0;
     s->in_len += n_new;
 
     // ---- 2. resample the complete chunks (shared f64 recurrence on the host, fractions uploaded) ----
@@ -1328,7 +1332,7 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
     rs.n_begin = n_begin; rs.n_end = n_end; rs.p = s->rec.p; rs.q = s->rec.q; rs.mode = s->rec.mode();
     rs.frac = s->d_frac;
     rs.y_old = s->y_buf[s->y_cur]; rs.y_new = s->y_buf[s->y_cur ^ 1]; rs.y_stride = s->y_stride;
-    rs.y_drop = 0; rs.y_keep = s->y_len;
+    rs.y_drop = s->y_drop; rs.y_keep = s->y_len;                  // (the samples the previous tick's frames consumed are dropped here)
     AF_CUDA(launch_session_resample(rs, (uint32_t)S, st));
     count_launch();
     s->y_cur ^= 1;
@@ -1428,42 +1432,20 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
     AF_CUDA(cudaStreamSynchronize(st));
     s->levels_valid = s->levels;
 
-    // ---- 5. bookkeeping: drop the consumed chunks and the samples every future frame starts after ----
+    // ---- 5. bookkeeping: the consumed chunks and the samples every future frame starts after are dropped by the next
+    //         tick's ingest / resample kernels (in_drop, y_drop): no kernel and no second synchronisation here ----
     if (!s->rec.passthrough) {
-        const uint32_t consumed = chunks * RS_CHUNK;
-        if (consumed) {
-            // keep [history 16 | new residual]: compact on the next ingest by dropping `consumed` frames
-            SessionIngest cp{};
-            cp.old_buf = s->in_buf[s->in_cur]; cp.new_buf = s->in_buf[s->in_cur ^ 1]; cp.buf_stride = s->in_stride;
-            cp.drop = consumed; cp.keep = s->in_len - consumed; cp.n_new_frames = 0; cp.channels = 1; cp.format = 0;
-            AF_CUDA(launch_session_ingest(cp, (uint32_t)S, st));
-            count_launch();
-            s->in_cur ^= 1; s->in_len -= consumed; s->in_base += consumed;
-        }
+        const uint32_t consumed = chunks * RS_CHUNK;              // keep [history 16 | new residual]
+        s->in_drop = consumed; s->in_len -= consumed; s->in_base += consumed;
     } else {
         // passthrough keeps nothing but the 16-frame history slot
-        SessionIngest cp{};
-        cp.old_buf = s->in_buf[s->in_cur]; cp.new_buf = s->in_buf[s->in_cur ^ 1]; cp.buf_stride = s->in_stride;
-        cp.drop = s->in_len - 2 * RS_POLY; cp.keep = 2 * RS_POLY; cp.n_new_frames = 0; cp.channels = 1; cp.format = 0;
-        AF_CUDA(launch_session_ingest(cp, (uint32_t)S, st));
-        count_launch();
-        s->in_cur ^= 1; s->in_base += (long long)(s->in_len - 2 * RS_POLY); s->in_len = 2 * RS_POLY;
+        s->in_drop = s->in_len - 2 * RS_POLY; s->in_base += (long long)(s->in_len - 2 * RS_POLY); s->in_len = 2 * RS_POLY;
     }
     uint32_t y_drop = s->framing ? T * s->hop : y_total;
     if (y_drop > y_total) y_drop = y_total;
-    if (y_drop) {
-        SessionResample cp{};
-        cp.in_buf = s->in_buf[s->in_cur]; cp.in_stride = s->in_stride; cp.n_begin = cp.n_end = 0; cp.mode = RS_PASSTHROUGH;
-        cp.p = cp.q = 1;
-        cp.y_old = s->y_buf[s->y_cur]; cp.y_new = s->y_buf[s->y_cur ^ 1]; cp.y_stride = s->y_stride;
-        cp.y_drop = y_drop; cp.y_keep = y_total - y_drop;
-        AF_CUDA(launch_session_resample(cp, (uint32_t)S, st));
-        count_launch();
-        s->y_cur ^= 1;
-    }
+    s->y_drop = y_drop;
     s->y_len = y_total - y_drop;
     s->frames_emitted += T;
-    AF_CUDA(cudaStreamSynchronize(st));
     for (size_t k = 0; k < S; ++k) {
         if (n_pcm) n_pcm[k] = n_y_new;
         if (n_feat) n_feat[k] = cfg.n_mels ? T : 0;
