@@ -431,13 +431,16 @@ def main():
         launches = af.kernel_launch_count() - l0
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            timed.per_rank_ms = [round(float(x.item()) / steps, 4) for x in allt]   # evidence: which rank is the slowest
+            ms = max(float(x.item()) for x in allt)
         return ms, launches, sampler.summary()
 
     if args.pipe_stats:
         pipe_stats_clear()
     ms, launches, clocks = timed(batch, outs, args.steps)
+    per_rank_ms = getattr(timed, "per_rank_ms", None)
     ms_per_step = ms / args.steps
     if args.pipe_stats:
         pipe_stats_print()
@@ -525,7 +528,7 @@ def main():
                          "traffic": traffic, "kernel": "af_fused_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "cpu_baseline": cpu,
-            "e2e": e2e,
+            "e2e": e2e, "per_rank_ms_per_step": per_rank_ms,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "with_vad": {"value": world * audio_s_per_step_rank / (ms_v_per_step * 1e-3), "ms_per_step": ms_v_per_step,
