@@ -1,20 +1,23 @@
 // af_fused.cu -- the fused hot-path kernel for sm_100a: one persistent CTA per SM, 28 warps in four
 // roles that run concurrently on different steps (32 frames) of the CTA's tiles and hand buffers to
-// each other through mbarriers -- there is no CTA-wide barrier after start-up:
+// each other through mbarriers -- there is no CTA-wide barrier after start-up.  Which hardware warp
+// plays which role is a launch parameter (warp_role, af_common.cuh):
 //
-//   warp 23      "V"  issues the TMA bulk copies (cp.async.bulk + mbarrier complete_tx) that stage the raw
-//                     interleaved input of each half step in shared memory, two fills ahead; then K4's
-//                     energy part: one bit-exact 400-term sequential mean-square chain per lane (= frame)
-//   warps 24-27  "R"  K1: downmix + cubic (rubato FastFixedIn) resample from the stage into the padded
-//                     16 kHz step buffer (double buffered), PCM written to HBM straight from registers
-//   warps 0-15   "F"  K2: Hann window + 512-point real FFT (packed 256-point complex, 16 x 16 in registers,
-//                     one half-warp per frame, transposed through shared memory, Hermitian split by
-//                     shuffles), power into pbuf[bin][frame]
-//   warps 16-22  "M"  K3: sparse banded mel projection + log, lane = frame, warp-uniform weight quads
+//   1 warp   "V"  issues the TMA bulk copies (cp.async.bulk + mbarrier complete_tx) that stage the raw
+//                 interleaved input of each part of a step in shared memory from host-planned descriptors;
+//                 then K4's energy part: one bit-exact 400-term sequential mean-square chain per lane (= frame)
+//   7 warps  "R"  K1: downmix + cubic (rubato FastFixedIn) resample from the stage into the padded
+//                 16 kHz step buffer (double buffered), PCM written to HBM straight from registers;
+//                 publishes a StepInfo record per step for the roles downstream
+//   16 warps "F"  K2: Hann window + 512-point real FFT (packed 256-point complex, 16 x 16 in registers in
+//                 f32x2 arithmetic, one half-warp per frame, transposed through shared memory, Hermitian
+//                 split by shuffles), power into pbuf[frame][bin]; per-lane constants from tensor memory
+//   4 warps  "M"  K3: sparse banded mel projection + log, lane = frame, warp-uniform weight quads served
+//                 from tensor memory (tcgen05.ld)
 //
 // Replaces capture.rs:30-42, resampler.rs:71-93/132-166 (+ rubato) and the O(len) part of
 // vad.rs:157-168; the STFT/mel stages are spec-defined.  The sequential EMA/state
-// machine of vad.rs:101-153 runs in af_vad_scan_kernel (af_kernels.cu).
+// machine of vad.rs:101-153 runs in the scan kernels (af_kernels.cu).
 #include "af_device.cuh"
 #include "af_launch.h"
 
