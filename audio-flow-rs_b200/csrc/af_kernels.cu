@@ -777,6 +777,63 @@ cudaError_t launch_session_resample(const SessionResample &J, uint32_t n_streams
     return cudaGetLastError();
 }
 
+// ingest + resample of one tick in ONE launch: a CTA per stream appends the tick's frames to its input history, then
+// resamples the complete chunks out of the row it has just written (same arithmetic as the two kernels above; the row
+// is read with plain loads after a CTA barrier, never through the read-only path)
+__device__ __forceinline__ float session_resample_one(const SessionResample &J, const float *in, uint32_t i_new)
+{
+    const unsigned long long n = J.n_begin + i_new;
+    if (J.mode == RS_PASSTHROUGH) {
+        const long long idx = (long long)n;
+        return (idx < J.data_base || idx >= J.n_valid_end) ? 0.0f : in[idx - J.data_base];
+    }
+    long long k; uint32_t rem;
+    resample_pos(n, J.p, J.q, &k, &rem);
+    float frac;
+    if (J.mode == RS_TABLE) {
+        frac = J.frac[i_new];
+        k += __float2int_rn((float)rem * (1.0f / (float)J.q) - frac);
+    } else {
+        frac = (float)rem * (1.0f / (float)J.q);
+    }
+    float y[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const long long idx = k - 1 + t;
+        y[t] = (idx < J.data_base || idx >= J.n_valid_end) ? 0.0f : in[idx - J.data_base];
+    }
+    return interp_cubic(frac, y[0], y[1], y[2], y[3]);
+}
+
+__global__ void __launch_bounds__(256) af_session_tick_kernel(const SessionIngest I, const SessionResample R)
+{
+    const uint32_t s = blockIdx.x;
+    {
+        const float *old = I.old_buf + (uint64_t)s * I.buf_stride;
+        float *neu = I.new_buf + (uint64_t)s * I.buf_stride;
+        const char *in = reinterpret_cast<const char *>(I.input) + (uint64_t)s * I.in_stride_bytes;
+        const uint32_t total = I.keep + I.n_new_frames;
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x)
+            neu[i] = i < I.keep ? old[I.drop + i] : load_mono(in, I.n_samples, I.n_new_frames, I.channels, I.format, (int)(i - I.keep));
+    }
+    __syncthreads();                                   // the row written above is read below by other threads of this CTA
+    {
+        const float *in = R.in_buf + (uint64_t)s * R.in_stride;
+        const float *yold = R.y_old + (uint64_t)s * R.y_stride;
+        float *ynew = R.y_new + (uint64_t)s * R.y_stride;
+        const uint32_t total = R.y_keep + (uint32_t)(R.n_end - R.n_begin);
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x)
+            ynew[i] = i < R.y_keep ? yold[R.y_drop + i] : session_resample_one(R, in, i - R.y_keep);
+    }
+}
+
+cudaError_t launch_session_tick(const SessionIngest &I, const SessionResample &R, uint32_t n_streams, cudaStream_t st)
+{
+    if (n_streams == 0) return cudaSuccess;
+    af_session_tick_kernel<<<n_streams, 256, 0, st>>>(I, R);
+    return cudaGetLastError();
+}
+
 // every stream of a session has the same lengths: refresh the fused kernel's stream table in place
 __global__ void af_session_setup_kernel(StreamDev *tab, TileDev *tiles, uint32_t n_streams, uint32_t n, uint32_t n_frames,
                                         uint32_t n_vad)

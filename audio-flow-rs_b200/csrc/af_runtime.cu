@@ -1303,9 +1303,7 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
     ing.drop = s->in_drop; ing.keep = s->in_len;                  // (the previous tick's consumed chunks are dropped here)
     ing.input = d_in; ing.in_stride_bytes = d_in_stride_bytes; ing.n_samples = n_samples; ing.n_new_frames = n_new;
     ing.channels = s->channels; ing.format = s->format;
-    AF_CUDA(launch_session_ingest(ing, (uint32_t)S, st));
-    count_launch();
-    s->in_cur ^= 1;
+    s->in_cur ^= 1;                                              // (launched below, together with the resampling of the tick)
     s->in_drop = 0;
     s->in_len += n_new;
 
@@ -1333,7 +1331,7 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
     rs.frac = s->d_frac;
     rs.y_old = s->y_buf[s->y_cur]; rs.y_new = s->y_buf[s->y_cur ^ 1]; rs.y_stride = s->y_stride;
     rs.y_drop = s->y_drop; rs.y_keep = s->y_len;                  // (the samples the previous tick's frames consumed are dropped here)
-    AF_CUDA(launch_session_resample(rs, (uint32_t)S, st));
+    AF_CUDA(launch_session_tick(ing, rs, (uint32_t)S, st));      // ingest + resample: one CTA per stream, one launch
     count_launch();
     s->y_cur ^= 1;
     const uint32_t y_total = s->y_len + n_y_new;
