@@ -702,84 +702,10 @@ cudaError_t launch_vad_scan(const ScanJob &job, cudaStream_t st)
 }
 
 // ---- streaming sessions (all streams advance in lockstep) ----
-// ingest: carry the retained input frames to the front of the new buffer and append the downmixed new frames
-__global__ void af_session_ingest_kernel(const SessionIngest J)
-{
-    const uint32_t s = blockIdx.y;
-    const float *old = J.old_buf + (uint64_t)s * J.buf_stride;
-    float *neu = J.new_buf + (uint64_t)s * J.buf_stride;
-    const char *in = reinterpret_cast<const char *>(J.input) + (uint64_t)s * J.in_stride_bytes;
-    const uint32_t total = J.keep + J.n_new_frames;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        float v;
-        if (i < J.keep) v = old[J.drop + i];
-        else v = load_mono(in, J.n_samples, J.n_new_frames, J.channels, J.format, (int)(i - J.keep));
-        neu[i] = v;
-    }
-}
-
-cudaError_t launch_session_ingest(const SessionIngest &J, uint32_t n_streams, cudaStream_t st)
-{
-    const uint32_t total = J.keep + J.n_new_frames;
-    if (n_streams == 0 || total == 0) return cudaSuccess;
-    dim3 grid((total + 255) / 256, n_streams);
-    af_session_ingest_kernel<<<grid, 256, 0, st>>>(J);
-    return cudaGetLastError();
-}
-
-// resample the complete chunks of this tick for every stream; carries the unconsumed 16 kHz tail forward
-__global__ void af_session_resample_kernel(const SessionResample J)
-{
-    const uint32_t s = blockIdx.y;
-    const float *in = J.in_buf + (uint64_t)s * J.in_stride;
-    const float *yold = J.y_old + (uint64_t)s * J.y_stride;
-    float *ynew = J.y_new + (uint64_t)s * J.y_stride;
-    const uint32_t n_new = (uint32_t)(J.n_end - J.n_begin);
-    const uint32_t total = J.y_keep + n_new;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        float v;
-        if (i < J.y_keep) {
-            v = yold[J.y_drop + i];
-        } else {
-            const unsigned long long n = J.n_begin + (i - J.y_keep);
-            if (J.mode == RS_PASSTHROUGH) {
-                const long long idx = (long long)n;
-                v = (idx < J.data_base || idx >= J.n_valid_end) ? 0.0f : in[idx - J.data_base];
-            } else {
-                long long k; uint32_t rem;
-                resample_pos(n, J.p, J.q, &k, &rem);
-                float frac;
-                if (J.mode == RS_TABLE) {
-                    frac = J.frac[i - J.y_keep];
-                    k += __float2int_rn((float)rem * (1.0f / (float)J.q) - frac);
-                } else {
-                    frac = (float)rem * (1.0f / (float)J.q);
-                }
-                float y[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const long long idx = k - 1 + t;
-                    y[t] = (idx < J.data_base || idx >= J.n_valid_end) ? 0.0f : in[idx - J.data_base];
-                }
-                v = interp_cubic(frac, y[0], y[1], y[2], y[3]);
-            }
-        }
-        ynew[i] = v;
-    }
-}
-
-cudaError_t launch_session_resample(const SessionResample &J, uint32_t n_streams, cudaStream_t st)
-{
-    const uint32_t total = J.y_keep + (uint32_t)(J.n_end - J.n_begin);
-    if (n_streams == 0 || total == 0) return cudaSuccess;
-    dim3 grid((total + 255) / 256, n_streams);
-    af_session_resample_kernel<<<grid, 256, 0, st>>>(J);
-    return cudaGetLastError();
-}
-
 // ingest + resample of one tick in ONE launch: a CTA per stream appends the tick's frames to its input history, then
-// resamples the complete chunks out of the row it has just written (same arithmetic as the two kernels above; the row
-// is read with plain loads after a CTA barrier, never through the read-only path)
+// resamples the complete chunks out of the row it has just written (the row is read with plain loads after a CTA
+// barrier, never through the read-only path); both also carry the retained part of the ping-pong buffers forward,
+// skipping what the previous tick consumed (drop / y_drop)
 __device__ __forceinline__ float session_resample_one(const SessionResample &J, const float *in, uint32_t i_new)
 {
     const unsigned long long n = J.n_begin + i_new;

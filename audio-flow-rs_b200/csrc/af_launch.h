@@ -60,8 +60,6 @@ struct SessionResample {
 
 size_t fused_smem_bytes();
 cudaError_t fused_pipe_stats(unsigned long long out[32]);
-cudaError_t launch_session_ingest(const SessionIngest &J, uint32_t n_streams, cudaStream_t st);
-cudaError_t launch_session_resample(const SessionResample &J, uint32_t n_streams, cudaStream_t st);
 cudaError_t launch_session_tick(const SessionIngest &I, const SessionResample &R, uint32_t n_streams, cudaStream_t st);
 cudaError_t launch_session_setup(StreamDev *tab, TileDev *tiles, uint32_t n_streams, uint32_t n, uint32_t n_frames, uint32_t n_vad,
                                  cudaStream_t st);
