@@ -60,6 +60,11 @@ class VadFinalC(C.Structure):
                 ("speech_frames", C.c_uint64)]
 
 
+class GateOutputsC(C.Structure):
+    _fields_ = [("pcm", C.c_void_p), ("pcm_stride", C.c_uint64), ("logmel", C.c_void_p), ("logmel_stride", C.c_uint64),
+                ("seg_offset", C.c_void_p), ("n_frames", C.c_void_p)]
+
+
 class OutputsC(C.Structure):
     _fields_ = [("pcm", C.c_void_p), ("pcm_stride", C.c_uint64), ("logmel", C.c_void_p), ("logmel_stride", C.c_uint64),
                 ("vad", C.c_void_p), ("vad_stride", C.c_uint64), ("energy", C.c_void_p), ("energy_stride", C.c_uint64),
@@ -119,6 +124,8 @@ def load_library():
         "af_pipeline_run": (C.c_int, [vp, C.POINTER(StreamDescC), sz, C.POINTER(OutputsC)]),
         "af_set_kernel_variant": (C.c_int, [C.c_char_p]),
         "af_vad_segments": (C.c_int, [vp, C.c_uint64, vp, sz, vp, C.c_uint32, vp, vp]),
+        "af_vad_gate": (C.c_int, [vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, sz,
+                                  C.POINTER(GateOutputsC), vp]),
         "af_debug_vad_energy_threshold": (C.c_float, [C.c_float]),
         "af_debug_resample_plan": (sz, [C.c_uint32, C.c_uint32, sz, fp, sz, C.POINTER(C.c_int)]),
         "af_session_create": (C.c_int, [vp, sz, C.c_uint32, C.c_uint16, C.c_uint16, C.c_uint32, C.POINTER(vp)]),

@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
 // The word walk above is sequential per stream (a one-hour recording: 11 250 words through one thread, 2.5 ms).  It is
 // cut into blocks of SCAN_BLOCK frames that are walked SPECULATIVELY in parallel, every block but the first assuming a
 // fresh machine (Silence, counters 0).  The speculation is exact from the block's first "sync point" on: a speech
-// frame that follows at least silence_timeout + 1 non-speech frames finds the machine in Silence whatever came before
+// frame that follows at least max(silence_timeout, 1) + 1 non-speech frames finds the machine in Silence whatever came before
 // (Speech times out after silence_timeout, Ending lasts one frame) and sets (Speech, 1, 0).  A cheap sequential pass
 // then carries the true state from block to block and re-walks only the words in front of each block's sync point
 // (the whole block if it has none); the EMA entering a block is speculated from a warm-up and verified the same way.
@@ -551,7 +551,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_long_a_kernel(const ScanJ
         VadMachine m{0u, 0u, 0u};
         EmitNone none;
         uint32_t zrun = 0, sync = NO_SYNC;
-        const uint32_t need = timeout + 1u;
+        // silence_timeout == 0 behaves like 1 here: the first non-speech frame moves Speech to Ending / Silence, and it takes
+        // a second one to leave Ending -- a speech frame right after a single zero would be swallowed by Ending -> Silence
+        // (vad.rs:147-151), which a fresh machine does not reproduce
+        const uint32_t need = max(timeout, 1u) + 1u;
         for (uint32_t w = 0; w < n_words; ++w) {
             const uint32_t bits = s_bits[w], m_n = min(32u, n - w * 32);
             uint32_t *en = V.entry + 3 * (size_t)((b0 >> 5) + w);
@@ -909,6 +912,104 @@ cudaError_t launch_vad_segments(const uint8_t *states, uint64_t stride, const ui
     if (n_streams == 0) return cudaSuccess;
     af_vad_segments_kernel<<<n_streams, SEG_THREADS, 0, st>>>(states, stride, n_frames, n_streams, seg, seg_cap, n_seg);
     return cudaGetLastError();
+}
+
+// ---- VAD-gated output (intent: specs/0001-spec.md:466 "filter the silent stretches before sending") ----
+// The segments [start, end) of a stream select the frames whose audio is kept: frame f contributes its hop, samples
+// [f hop, (f + 1) hop), and its log-mel row.  The kept frames of a stream are packed in order; segment k starts at
+// compacted frame off[k] = sum of the lengths of the segments before it (off[n_seg] = total).
+// (1) offsets: one CTA per stream, block-wide exclusive scan of the segment lengths.
+constexpr uint32_t GATE_THREADS = 256;
+__global__ void __launch_bounds__(GATE_THREADS) af_gate_offsets_kernel(const uint32_t *__restrict__ seg, uint32_t seg_cap,
+                                                                       const uint32_t *__restrict__ n_seg, uint32_t *__restrict__ off,
+                                                                       uint32_t *__restrict__ total)
+{
+    __shared__ uint32_t s_part[GATE_THREADS];
+    const uint32_t s = blockIdx.x, t = threadIdx.x;
+    const uint32_t n = min(n_seg[s], seg_cap);
+    const uint32_t *sg = seg + (uint64_t)s * seg_cap * 2;
+    uint32_t *of = off + (uint64_t)s * (seg_cap + 1);
+    const uint32_t per = (n + GATE_THREADS - 1) / GATE_THREADS;
+    const uint32_t lo = min(t * per, n), hi = min(lo + per, n);
+    uint32_t sum = 0;
+    for (uint32_t k = lo; k < hi; ++k) sum += sg[2 * k + 1] - sg[2 * k];
+    s_part[t] = sum;
+    __syncthreads();
+    for (uint32_t d = 1; d < GATE_THREADS; d <<= 1) {
+        const uint32_t a = t >= d ? s_part[t - d] : 0u;
+        __syncthreads();
+        s_part[t] += a;
+        __syncthreads();
+    }
+    uint32_t run = s_part[t] - sum;
+    for (uint32_t k = lo; k < hi; ++k) { of[k] = run; run += sg[2 * k + 1] - sg[2 * k]; }
+    if (t == GATE_THREADS - 1) { of[n] = s_part[t]; total[s] = s_part[t]; }
+}
+// (2) copy: one warp per compacted frame (binary search of its segment, then 16-byte copies of its hop of PCM and its
+// log-mel row); grid.y = stream, the warps of grid.x stride over the stream's compacted frames
+__global__ void __launch_bounds__(GATE_THREADS) af_gate_copy_kernel(const float *__restrict__ pcm, uint64_t pcm_stride,
+                                                                    const float *__restrict__ logmel, uint64_t logmel_stride,
+                                                                    uint32_t n_mels, const uint32_t *__restrict__ n_out, uint32_t hop,
+                                                                    const uint32_t *__restrict__ seg, uint32_t seg_cap,
+                                                                    const uint32_t *__restrict__ n_seg, const uint32_t *__restrict__ off,
+                                                                    float *__restrict__ out_pcm, uint64_t out_pcm_stride,
+                                                                    float *__restrict__ out_lm, uint64_t out_lm_stride)
+{
+    const uint32_t s = blockIdx.y, lane = threadIdx.x & 31;
+    const uint32_t n = min(n_seg[s], seg_cap);
+    const uint32_t *sg = seg + (uint64_t)s * seg_cap * 2;
+    const uint32_t *of = off + (uint64_t)s * (seg_cap + 1);
+    const uint32_t total = of[n];
+    const uint32_t n_samples = n_out ? n_out[s] : 0xffffffffu;
+    const float *src_p = pcm ? pcm + (uint64_t)s * pcm_stride : nullptr;
+    float *dst_p = out_pcm ? out_pcm + (uint64_t)s * out_pcm_stride : nullptr;
+    const float *src_l = logmel ? logmel + (uint64_t)s * logmel_stride : nullptr;
+    float *dst_l = out_lm ? out_lm + (uint64_t)s * out_lm_stride : nullptr;
+    const bool vec_p = (hop & 3u) == 0 && ((reinterpret_cast<uintptr_t>(src_p) | reinterpret_cast<uintptr_t>(dst_p)) & 15) == 0;
+    const bool vec_l = (n_mels & 3u) == 0 && ((reinterpret_cast<uintptr_t>(src_l) | reinterpret_cast<uintptr_t>(dst_l)) & 15) == 0;
+    const uint32_t warps = gridDim.x * (GATE_THREADS / 32);
+    for (uint32_t j = blockIdx.x * (GATE_THREADS / 32) + (threadIdx.x >> 5); j < total; j += warps) {
+        uint32_t a = 0, b = n;                               // largest k with off[k] <= j (segments are never empty)
+        while (b - a > 1) { const uint32_t m = (a + b) >> 1; if (of[m] <= j) a = m; else b = m; }
+        const uint32_t f = sg[2 * a] + (j - of[a]);          // source frame
+        if (src_p && dst_p) {
+            const uint64_t so = (uint64_t)f * hop, dof = (uint64_t)j * hop;
+            const uint32_t cnt = so >= n_samples ? 0u : (uint32_t)min((uint64_t)hop, (uint64_t)n_samples - so);
+            if (vec_p && cnt == hop) {
+                const float4 *sp = reinterpret_cast<const float4 *>(src_p + so);
+                float4 *dp = reinterpret_cast<float4 *>(dst_p + dof);
+                for (uint32_t i = lane; i < hop / 4; i += 32) __stcs(dp + i, __ldcs(sp + i));
+            } else {
+                for (uint32_t i = lane; i < hop; i += 32) dst_p[dof + i] = i < cnt ? src_p[so + i] : 0.0f;
+            }
+        }
+        if (src_l && dst_l && n_mels) {
+            const uint64_t so = (uint64_t)f * n_mels, dof = (uint64_t)j * n_mels;
+            if (vec_l) {
+                const float4 *sp = reinterpret_cast<const float4 *>(src_l + so);
+                float4 *dp = reinterpret_cast<float4 *>(dst_l + dof);
+                for (uint32_t i = lane; i < n_mels / 4; i += 32) __stcs(dp + i, __ldcs(sp + i));
+            } else {
+                for (uint32_t i = lane; i < n_mels; i += 32) dst_l[dof + i] = src_l[so + i];
+            }
+        }
+    }
+}
+
+cudaError_t launch_vad_gate(const GateJob &J, cudaStream_t st)
+{
+    if (J.n_streams == 0) return cudaSuccess;
+    af_gate_offsets_kernel<<<J.n_streams, GATE_THREADS, 0, st>>>(J.seg, J.seg_cap, J.n_seg, J.off, J.total);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if ((J.pcm && J.out_pcm) || (J.logmel && J.out_lm)) {
+        const uint32_t gx = std::max<uint32_t>(1u, std::min<uint32_t>(1024u, (8u * 148u + J.n_streams - 1) / J.n_streams));
+        af_gate_copy_kernel<<<dim3(gx, J.n_streams), GATE_THREADS, 0, st>>>(J.pcm, J.pcm_stride, J.logmel, J.logmel_stride, J.n_mels, J.n_out,
+                                                                            J.hop, J.seg, J.seg_cap, J.n_seg, J.off, J.out_pcm,
+                                                                            J.out_pcm_stride, J.out_lm, J.out_lm_stride);
+        e = cudaGetLastError();
+    }
+    return e;
 }
 
 }  // namespace af

@@ -58,6 +58,20 @@ struct SessionResample {
     uint32_t y_drop, y_keep;
 };
 
+struct GateJob {             // VAD-gated compaction (all device pointers)
+    const float *pcm; uint64_t pcm_stride;           // 16 kHz rows (or nullptr)
+    const float *logmel; uint64_t logmel_stride;     // [frame][mel] rows (or nullptr)
+    uint32_t n_mels, hop;
+    const uint32_t *n_out;                           // per-stream PCM lengths (or nullptr: unchecked)
+    const uint32_t *seg; uint32_t seg_cap; const uint32_t *n_seg;   // af_vad_segments output
+    uint32_t *off;                                   // [n_streams][seg_cap + 1] compacted frame offset of every segment
+    uint32_t *total;                                 // [n_streams] kept frames
+    float *out_pcm; uint64_t out_pcm_stride;
+    float *out_lm; uint64_t out_lm_stride;
+    uint32_t n_streams;
+};
+cudaError_t launch_vad_gate(const GateJob &job, cudaStream_t st);
+
 size_t fused_smem_bytes();
 cudaError_t fused_pipe_stats(unsigned long long out[32]);
 cudaError_t launch_session_tick(const SessionIngest &I, const SessionResample &R, uint32_t n_streams, cudaStream_t st);

@@ -632,6 +632,31 @@ AF_API int af_vad_segments(const uint8_t *states, uint64_t vad_stride, const uin
     return AF_OK;
 }
 
+AF_API int af_vad_gate(const float *pcm, uint64_t pcm_stride, const float *logmel, uint64_t logmel_stride, uint32_t n_mels,
+                       const uint32_t *n_out, uint32_t hop, const uint32_t *seg, uint32_t seg_cap, const uint32_t *n_seg,
+                       size_t n_streams, const af_gate_outputs *out, void *cuda_stream)
+{
+    if (!seg || !n_seg || !out || !out->seg_offset || !out->n_frames) return fail(AF_ERR_INVALID, "null argument");
+    if (hop == 0) return fail(AF_ERR_INVALID, "hop must be positive");
+    if ((out->pcm && !pcm) || (out->logmel && (!logmel || n_mels == 0))) return fail(AF_ERR_INVALID, "gated output requested without its source");
+    int rc = require_ctx();
+    if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_ctx.stream;
+    GateJob J{};
+    J.pcm = out->pcm ? pcm : nullptr; J.pcm_stride = pcm_stride;
+    J.logmel = out->logmel ? logmel : nullptr; J.logmel_stride = logmel_stride;
+    J.n_mels = n_mels; J.hop = hop; J.n_out = n_out;
+    J.seg = seg; J.seg_cap = seg_cap; J.n_seg = n_seg;
+    J.off = out->seg_offset; J.total = out->n_frames;
+    J.out_pcm = out->pcm; J.out_pcm_stride = out->pcm_stride;
+    J.out_lm = out->logmel; J.out_lm_stride = out->logmel_stride;
+    J.n_streams = (uint32_t)n_streams;
+    AF_CUDA(launch_vad_gate(J, st));
+    count_launch((J.out_pcm || J.out_lm) ? 2 : 1);
+    if (!cuda_stream) AF_CUDA(cudaStreamSynchronize(st));
+    return AF_OK;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------
@@ -871,7 +896,8 @@ AF_API int af_batch_create(af_pipeline *p, const af_stream_desc *streams, size_t
     if (mem != AF_MEM_DEVICE && mem != AF_MEM_HOST) return fail(AF_ERR_INVALID, "bad memory kind %d", mem);
     int rc = require_ctx();
     if (rc) return rc;
-    std::unique_ptr<af_batch> b(new af_batch);
+    // (af_batch_destroy frees the slots, tables and streams allocated so far on every early return)
+    std::unique_ptr<af_batch, void (*)(af_batch *)> b(new af_batch, af_batch_destroy);
     b->pipe = p; b->mem = mem;
     b->streams.resize(n_streams);
     const af_pipeline_config &cfg = p->cfg;
@@ -984,6 +1010,8 @@ static int check_outputs(const af_batch *b, const af_outputs *o)
 {
     const af_pipeline_config &cfg = b->pipe->cfg;
     if (!o) return fail(AF_ERR_INVALID, "null outputs");
+    // the fused kernel stores PCM and log-mel rows with 16-byte vector stores
+    if (o->pcm && b->mem == AF_MEM_DEVICE && (reinterpret_cast<uintptr_t>(o->pcm) & 15)) return fail(AF_ERR_INVALID, "device pcm pointer must be 16-byte aligned");
     if (o->pcm && (o->pcm_stride < b->max_out || (o->pcm_stride & 3))) return fail(AF_ERR_CAPACITY, "pcm_stride %llu too small or not a multiple of 4 (need >= %llu)", (unsigned long long)o->pcm_stride, (unsigned long long)b->max_out);
     if (o->logmel && cfg.n_mels && (o->logmel_stride < b->max_frames * cfg.n_mels || (o->logmel_stride & 3))) return fail(AF_ERR_CAPACITY, "logmel_stride too small or not a multiple of 4");
     if (o->vad && o->vad_stride < b->max_vad) return fail(AF_ERR_CAPACITY, "vad_stride too small");
@@ -1269,6 +1297,7 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
                            const af_outputs *o, uint32_t *n_pcm, uint32_t *n_feat, uint32_t *n_vad)
 {
     if (!s || (!data && n_samples)) return fail(AF_ERR_INVALID, "null argument");
+    if (mem != AF_MEM_DEVICE && mem != AF_MEM_HOST) return fail(AF_ERR_INVALID, "bad memory kind %d", mem);
     if (n_samples % s->channels) return fail(AF_ERR_INVALID, "a tick must hold whole frames (n_samples %% channels == 0)");
     const uint32_t n_new = n_samples / s->channels;
     if (n_new > s->max_tick_frames) return fail(AF_ERR_CAPACITY, "tick of %u frames exceeds max_tick_samples", n_new);
@@ -1280,7 +1309,51 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
     af_outputs none{};
     if (!o) o = &none;
 
-    // ---- 1. input: host ticks are staged; then carry history + residual and append the downmixed frames ----
+    // ---- 0. plan the tick on COPIES of the session state and validate every caller-supplied size: a recoverable error
+    //         (a stride that is too small) must leave the session exactly as it was ----
+    // frames held: [history 16 | residual r | new n_new]; chunks formed from residual + new
+    const uint32_t residual = s->in_len - 2 * RS_POLY;
+    const uint32_t avail = residual + n_new;
+    const uint32_t chunks = s->rec.passthrough ? 0 : avail / RS_CHUNK;
+    RsRecurrence rec = s->rec;                                   // the shared f64 recurrence, advanced on a copy
+    const uint64_t n_begin = rec.passthrough ? (uint64_t)(s->in_base + 2 * RS_POLY + residual) : rec.n_out;
+    uint64_t n_end = n_begin;
+    s->frac_host.clear();                                        // (scratch, not state)
+    if (rec.passthrough) n_end = n_begin + n_new;
+    else {
+        for (uint32_t c = 0; c < chunks; ++c) rec.step(rec.exact ? nullptr : &s->frac_host);
+        n_end = rec.n_out;
+    }
+    const uint32_t n_y_new = (uint32_t)(n_end - n_begin);
+    if (s->y_len + n_y_new > s->y_stride) return fail(AF_ERR_CAPACITY, "internal: 16 kHz carry overflow");
+    if (s->frac_host.size() > s->frac_cap) return fail(AF_ERR_CAPACITY, "internal: fraction buffer overflow");
+    const uint32_t y_total = s->y_len + n_y_new;
+    uint32_t T = 0;
+    if (s->framing && y_total >= s->frame_len) T = 1 + (y_total - s->frame_len) / s->hop;
+    const bool want_pcm = cfg.write_pcm && o->pcm && n_y_new;
+    const bool want_lm = T && cfg.n_mels && o->logmel;
+    const bool want_states = T && cfg.vad_enable && o->vad;
+    if (want_pcm && o->pcm_stride < n_y_new) return fail(AF_ERR_CAPACITY, "pcm_stride %llu too small for %u samples", (unsigned long long)o->pcm_stride, n_y_new);
+    if (want_lm && o->logmel_stride < (uint64_t)T * cfg.n_mels) return fail(AF_ERR_CAPACITY, "logmel_stride too small for %u frames", T);
+    if (want_states && o->vad_stride < T) return fail(AF_ERR_CAPACITY, "vad_stride too small for %u frames", T);
+    if (T && s->packed && T + 2 > s->pk_slots) return fail(AF_ERR_CAPACITY, "internal: %u frames do not fit %u frame slots", T, s->pk_slots);
+    // internal staging buffers (allocation failures are reported before anything changes, too)
+    float *lm = nullptr; uint64_t lm_stride = 0;
+    uint8_t *states = nullptr; uint64_t st_stride = 0;
+    if (want_lm) {
+        if (mem == AF_MEM_HOST || s->packed) {                  // (packed ticks write every frame slot: internal buffer, then a strided copy)
+            if (!s->d_lm) AF_CUDA(cudaMalloc(&s->d_lm, S * s->lm_stride * sizeof(float)));
+            lm = s->d_lm; lm_stride = s->lm_stride;
+        } else { lm = o->logmel; lm_stride = o->logmel_stride; }
+        if (lm_stride < (uint64_t)T * cfg.n_mels) return fail(AF_ERR_CAPACITY, "internal: log-mel staging too small for %u frames", T);
+    }
+    if (want_states) {
+        if (mem == AF_MEM_HOST) {
+            if (!s->d_states) AF_CUDA(cudaMalloc(&s->d_states, S * s->st_stride));
+            states = s->d_states; st_stride = s->st_stride;
+        } else { states = o->vad; st_stride = o->vad_stride; }
+        if (st_stride < T) return fail(AF_ERR_CAPACITY, "internal: state staging too small for %u frames", T);
+    }
     const void *d_in = data;
     uint64_t d_in_stride_bytes = in_stride * bps;
     if (mem == AF_MEM_HOST && n_samples) {
@@ -1291,13 +1364,28 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
             AF_CUDA(cudaMalloc(&s->d_in_stage, row * S));
             s->in_stage_bytes = row * S;
         }
-        AF_CUDA(cudaMemcpy2DAsync(s->d_in_stage, row, data, in_stride * bps, (size_t)n_samples * bps, S, cudaMemcpyHostToDevice, st));
         d_in = s->d_in_stage; d_in_stride_bytes = row;
     }
-    // frames held: [history 16 | residual r | new n_new]; chunks formed from residual + new
-    const uint32_t residual = s->in_len - 2 * RS_POLY;
-    const uint32_t avail = residual + n_new;
-    const uint32_t chunks = s->rec.passthrough ? 0 : avail / RS_CHUNK;
+
+    // From here on only CUDA failures can occur.  The bookkeeping is restored if one does (the ping-pong buffers keep
+    // the previous tick intact); the detector states on the device may already have advanced -- af_session_reset
+    // after an AF_ERR_CUDA.
+    struct Restore {
+        af_session *s; bool armed = true;
+        RsRecurrence rec; int in_cur, y_cur; uint32_t in_len, in_drop, y_len, y_drop; long long in_base; uint64_t frames_emitted;
+        explicit Restore(af_session *s_) : s(s_), rec(s_->rec), in_cur(s_->in_cur), y_cur(s_->y_cur), in_len(s_->in_len), in_drop(s_->in_drop),
+                                          y_len(s_->y_len), y_drop(s_->y_drop), in_base(s_->in_base), frames_emitted(s_->frames_emitted) {}
+        ~Restore()
+        {
+            if (!armed) return;
+            s->rec = rec; s->in_cur = in_cur; s->y_cur = y_cur; s->in_len = in_len; s->in_drop = in_drop; s->y_len = y_len;
+            s->y_drop = y_drop; s->in_base = in_base; s->frames_emitted = frames_emitted;
+        }
+    } restore(s);
+
+    // ---- 1. input: host ticks are staged; then carry history + residual and append the downmixed frames ----
+    if (mem == AF_MEM_HOST && n_samples)
+        AF_CUDA(cudaMemcpy2DAsync(s->d_in_stage, d_in_stride_bytes, data, in_stride * bps, (size_t)n_samples * bps, S, cudaMemcpyHostToDevice, st));
     SessionIngest ing{};
     ing.old_buf = s->in_buf[s->in_cur]; ing.new_buf = s->in_buf[s->in_cur ^ 1]; ing.buf_stride = s->in_stride;
     ing.drop = s->in_drop; ing.keep = s->in_len;                  // (the previous tick's consumed chunks are dropped here)
@@ -1308,20 +1396,9 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
     s->in_len += n_new;
 
     // ---- 2. resample the complete chunks (shared f64 recurrence on the host, fractions uploaded) ----
-    const uint64_t n_begin = s->rec.passthrough ? (uint64_t)(s->in_base + 2 * RS_POLY + residual) : s->rec.n_out;
-    uint64_t n_end = n_begin;
-    s->frac_host.clear();
-    if (s->rec.passthrough) n_end = n_begin + n_new;
-    else {
-        for (uint32_t c = 0; c < chunks; ++c) s->rec.step(s->rec.exact ? nullptr : &s->frac_host);
-        n_end = s->rec.n_out;
-    }
-    const uint32_t n_y_new = (uint32_t)(n_end - n_begin);
-    if (s->y_len + n_y_new > s->y_stride) return fail(AF_ERR_CAPACITY, "internal: 16 kHz carry overflow");
-    if (!s->frac_host.empty()) {
-        if (s->frac_host.size() > s->frac_cap) return fail(AF_ERR_CAPACITY, "internal: fraction buffer overflow");
+    s->rec = rec;
+    if (!s->frac_host.empty())
         AF_CUDA(cudaMemcpyAsync(s->d_frac, s->frac_host.data(), s->frac_host.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-    }
     SessionResample rs{};
     rs.in_buf = s->in_buf[s->in_cur]; rs.in_stride = s->in_stride;
     rs.data_base = s->in_base;
@@ -1334,11 +1411,10 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
     AF_CUDA(launch_session_tick(ing, rs, (uint32_t)S, st));      // ingest + resample: one CTA per stream, one launch
     count_launch();
     s->y_cur ^= 1;
-    const uint32_t y_total = s->y_len + n_y_new;
     float *ycur = s->y_buf[s->y_cur];
 
     // ---- 3. PCM of this tick ----
-    if (cfg.write_pcm && o->pcm && n_y_new)
+    if (want_pcm)
         AF_CUDA(cudaMemcpy2DAsync(o->pcm, o->pcm_stride * sizeof(float), ycur + s->y_len, s->y_stride * sizeof(float),
                                   (size_t)n_y_new * sizeof(float), S,
                                   mem == AF_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
@@ -1349,32 +1425,12 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
     }
 
     // ---- 4. frames that became complete: features + VAD ----
-    uint32_t T = 0;
-    if (s->framing && y_total >= s->frame_len) T = 1 + (y_total - s->frame_len) / s->hop;
     const bool stft_frames = (s->frame_len == WIN && s->hop == HOP);
     if (T) {
-        float *lm = nullptr; uint64_t lm_stride = 0;
-        uint8_t *states = nullptr; uint64_t st_stride = 0;
-        if (cfg.n_mels && o->logmel) {
-            if (mem == AF_MEM_HOST || s->packed) {              // (packed ticks write every frame slot: internal buffer, then a strided copy)
-                if (!s->d_lm) AF_CUDA(cudaMalloc(&s->d_lm, S * s->lm_stride * sizeof(float)));
-                lm = s->d_lm; lm_stride = s->lm_stride;
-            } else { lm = o->logmel; lm_stride = o->logmel_stride; }
-            if (lm_stride < (uint64_t)T * cfg.n_mels || o->logmel_stride < (uint64_t)T * cfg.n_mels)
-                return fail(AF_ERR_CAPACITY, "logmel_stride too small for %u frames", T);
-        }
-        if (cfg.vad_enable && o->vad) {
-            if (mem == AF_MEM_HOST) {
-                if (!s->d_states) AF_CUDA(cudaMalloc(&s->d_states, S * s->st_stride));
-                states = s->d_states; st_stride = s->st_stride;
-            } else { states = o->vad; st_stride = o->vad_stride; }
-            if (st_stride < T) return fail(AF_ERR_CAPACITY, "vad_stride too small for %u frames", T);
-        }
         if (stft_frames) {
             FusedParams P{};
             uint64_t vrows = 1;                                 // real streams per stream of the launch
             if (s->packed) {
-                if (T + 2 > s->pk_slots) return fail(AF_ERR_CAPACITY, "internal: %u frames do not fit %u frame slots", T, s->pk_slots);
                 P.streams = s->d_ptab[s->y_cur]; P.tiles = s->d_ptiles[s->y_cur]; P.n_tiles = s->pk_n;
                 vrows = s->pk_rows;
             } else {
@@ -1428,6 +1484,7 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
         AF_CUDA(cudaMemcpyAsync(s->h_vad, s->d_vad, S * sizeof(VadState), cudaMemcpyDeviceToHost, st));
     }
     AF_CUDA(cudaStreamSynchronize(st));
+    restore.armed = false;
     s->levels_valid = s->levels;
 
     // ---- 5. bookkeeping: the consumed chunks and the samples every future frame starts after are dropped by the next

@@ -80,6 +80,10 @@ impl AudioResampler {
     pub fn create_48k_to_16k() -> Result<Self, AudioError> { Self::new(48000, 16000) }
 
     pub fn process(&mut self, input: &[f32]) -> Result<Vec<f32>, AudioError> {
+        if self.h.is_null() {
+            // the `Default` fallback (resampler.rs:169-178: `resampler: None`) passes its input through (resampler.rs:72-75)
+            return Ok(input.to_vec());
+        }
         let cap = input.len().max(unsafe { ffi::af_resample_max_output(self.input_rate, self.output_rate, 128) });
         let mut out = vec![0.0f32; cap];
         let mut n = 0usize;
@@ -93,11 +97,15 @@ impl AudioResampler {
 }
 
 impl Drop for AudioResampler {
-    fn drop(&mut self) { unsafe { ffi::af_resampler_destroy(self.h) } }
+    fn drop(&mut self) { if !self.h.is_null() { unsafe { ffi::af_resampler_destroy(self.h) } } }
 }
 
+/// resampler.rs:169-178: `new(48000, 16000)`, and when that fails an object WITHOUT a resampler (it then passes its
+/// input through) -- never a panic.
 impl Default for AudioResampler {
-    fn default() -> Self { Self::new(48000, 16000).expect("no CUDA device") }
+    fn default() -> Self {
+        Self::new(48000, 16000).unwrap_or_else(|_| Self { h: ptr::null_mut(), input_rate: 48000, output_rate: 16000 })
+    }
 }
 
 /// resampler.rs:115-166

@@ -166,7 +166,8 @@ typedef struct af_vad_final {   /* detector state after the last frame of a stre
 } af_vad_final;
 
 typedef struct af_outputs {
-    float *pcm;               /* [n_streams][pcm_stride]    resampled mono 16 kHz (or NULL) */
+    float *pcm;               /* [n_streams][pcm_stride]    resampled mono 16 kHz (or NULL); device pointers must be
+                               * 16-byte aligned (vector stores), else AF_ERR_INVALID */
     uint64_t pcm_stride;      /* floats per row, multiple of 4 */
     float *logmel;            /* [n_streams][logmel_stride] rows of [frame][mel] (or NULL) */
     uint64_t logmel_stride;   /* floats per row, multiple of 4 */
@@ -220,6 +221,26 @@ AF_API int af_set_kernel_variant(const char *name);
 AF_API int af_vad_segments(const uint8_t *states, uint64_t vad_stride, const uint32_t *n_frames,
                            size_t n_streams, uint32_t *seg, uint32_t seg_cap, uint32_t *n_seg,
                            void *cuda_stream);
+
+/* ---- VAD-gated output (second half) ------------------------------------- */
+/* What the reference's spec wants in front of the wire (specs/0001-spec.md:466: drop the silent stretches before
+ * ScribeClient::send_audio, src-tauri/src/modules/network/scribe_client.rs:194-196): only the audio and the feature
+ * rows of the speech segments, packed.  Frame f of a segment [start, end) contributes its hop -- samples
+ * [f*hop, (f+1)*hop) of the 16 kHz row -- and log-mel row f; the kept frames of a stream are stored back to back in
+ * order.  seg_offset[s][k] is the compacted frame index where segment k starts (PCM offset = that times hop),
+ * seg_offset[s][n_seg] == n_frames[s] is the number of kept frames.  All pointers are device pointers;
+ * seg / n_seg are af_vad_segments' outputs (segments beyond seg_cap are ignored). */
+typedef struct af_gate_outputs {
+    float *pcm;               /* [n_streams][pcm_stride]    gated 16 kHz samples (or NULL) */
+    uint64_t pcm_stride;
+    float *logmel;            /* [n_streams][logmel_stride] gated rows of [frame][mel] (or NULL) */
+    uint64_t logmel_stride;
+    uint32_t *seg_offset;     /* [n_streams][seg_cap + 1] */
+    uint32_t *n_frames;       /* [n_streams] kept frames */
+} af_gate_outputs;
+AF_API int af_vad_gate(const float *pcm, uint64_t pcm_stride, const float *logmel, uint64_t logmel_stride, uint32_t n_mels,
+                       const uint32_t *n_out, uint32_t hop, const uint32_t *seg, uint32_t seg_cap, const uint32_t *n_seg,
+                       size_t n_streams, const af_gate_outputs *out, void *cuda_stream);
 
 /* ---- host-side planning diagnostics (no GPU needed; used by the CPU test-suite) ---------- */
 /* smallest f32 energy e with 20*log10f(e) > threshold_db under the host libm (NaN if none):

@@ -703,6 +703,33 @@ ORC_API size_t orc_vad_segments(const uint8_t *states, size_t T, uint32_t *seg, 
 }
 
 /* ------------------------------------------------------------------------- */
+/* VAD-gated output (intent specs/0001-spec.md:466): keep only  */
+/* the audio and the feature rows of the speech segments, packed in order.      */
+/* Frame f of a segment contributes samples [f*hop, (f+1)*hop) and log-mel row f */
+/* (samples beyond n read as 0).  off[k] = compacted frame where segment k       */
+/* starts, off[n_seg] = kept frames (returned).                                  */
+/* ------------------------------------------------------------------------- */
+ORC_API size_t orc_vad_gate(const float *pcm, size_t n, const float *logmel, uint32_t n_mels, uint32_t hop,
+                            const uint32_t *seg, size_t n_seg, float *out_pcm, float *out_logmel, uint32_t *off)
+{
+    size_t kept = 0;
+    for (size_t k = 0; k < n_seg; ++k) {
+        if (off) off[k] = (uint32_t)kept;
+        for (uint32_t f = seg[2 * k]; f < seg[2 * k + 1]; ++f, ++kept) {
+            if (pcm && out_pcm)
+                for (uint32_t i = 0; i < hop; ++i) {
+                    const size_t src = (size_t)f * hop + i;
+                    out_pcm[kept * hop + i] = src < n ? pcm[src] : 0.0f;
+                }
+            if (logmel && out_logmel)
+                memcpy(out_logmel + kept * n_mels, logmel + (size_t)f * n_mels, sizeof(float) * n_mels);
+        }
+    }
+    if (off) off[n_seg] = (uint32_t)kept;
+    return kept;
+}
+
+/* ------------------------------------------------------------------------- */
 /* Whole-path CPU baseline for one stream (what bench.py times):               */
 /* downmix -> BatchResampler(all)+flush -> [logmel f32] -> framed VAD.         */
 /* scratch buffers are caller-provided so the timing excludes malloc.          */

@@ -107,6 +107,8 @@ def lib():
     L.orc_pcm16_encode.argtypes = [fp, sz, C.POINTER(C.c_int16)]
     L.orc_vad_segments.restype = sz
     L.orc_vad_segments.argtypes = [u8p, sz, C.POINTER(C.c_uint32), sz]
+    L.orc_vad_gate.restype = sz
+    L.orc_vad_gate.argtypes = [fp, sz, fp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), sz, fp, fp, C.POINTER(C.c_uint32)]
     L.orc_pipeline_stream.restype = sz
     L.orc_pipeline_stream.argtypes = [fp, sz, C.c_uint, C.c_uint32, C.c_void_p, C.POINTER(VadConfig),
                                       C.c_uint32, C.c_uint32, fp, fp, sz, fp, u8p, C.POINTER(sz)]
@@ -332,6 +334,24 @@ def vad_segments(states) -> np.ndarray:
     n = lib().orc_vad_segments(s.ctypes.data_as(C.POINTER(C.c_uint8)), len(s),
                                seg.ctypes.data_as(C.POINTER(C.c_uint32)), cap)
     return seg[:n].copy()
+
+
+def vad_gate(pcm, logmel, seg, hop: int = 160):
+    """Speech-only PCM / log-mel of the segments `seg` ([n, 2] frames), packed: (pcm, logmel, off[n + 1])."""
+    seg = np.ascontiguousarray(seg, dtype=np.uint32).reshape(-1, 2)
+    kept = int((seg[:, 1] - seg[:, 0]).sum()) if len(seg) else 0
+    pcm = _f32(pcm) if pcm is not None else None
+    lm = np.ascontiguousarray(logmel, dtype=np.float32) if logmel is not None else None
+    M = lm.shape[1] if lm is not None else 0
+    out_p = np.zeros(kept * hop, np.float32) if pcm is not None else None
+    out_l = np.zeros((kept, M), np.float32) if lm is not None else None
+    off = np.zeros(len(seg) + 1, np.uint32)
+    n = lib().orc_vad_gate(_fp(pcm) if pcm is not None else None, len(pcm) if pcm is not None else 0,
+                           _fp(lm) if lm is not None else None, M, hop, seg.ctypes.data_as(C.POINTER(C.c_uint32)), len(seg),
+                           _fp(out_p) if out_p is not None else None, _fp(out_l) if out_l is not None else None,
+                           off.ctypes.data_as(C.POINTER(C.c_uint32)))
+    assert n == kept
+    return out_p, out_l, off
 
 
 def pipeline_stream(samples, channels: int, in_rate: int, feat: FeatConfig | None, vad: VadConfig | None,

@@ -180,6 +180,25 @@ def test_segments(orc):
     assert orc.vad_segments(st).tolist() == [[1, 5], [7, 9], [10, 11]]
 
 
+def test_vad_gate(orc):
+    """f1, second half: only the hops and feature rows of the speech segments, packed (spec intent 0001-spec.md:466)."""
+    st = np.array([0, 1, 1, 1, 2, 0, 0, 1, 1, 0, 1], np.uint8)
+    seg = orc.vad_segments(st)
+    hop = 4
+    pcm = np.arange(11 * hop + 3, dtype=np.float32)               # frame f owns samples [4f, 4f + 4)
+    lm = np.arange(11 * 3, dtype=np.float32).reshape(11, 3)
+    p, l, off = orc.vad_gate(pcm, lm, seg, hop)
+    frames = [1, 2, 3, 4, 7, 8, 10]
+    assert off.tolist() == [0, 4, 6, 7]
+    assert p.tolist() == [float(4 * f + i) for f in frames for i in range(hop)]
+    assert l.tolist() == [lm[f].tolist() for f in frames]
+    # a last frame whose hop leaves the signal is zero padded; no segments -> nothing
+    p2, _, off2 = orc.vad_gate(pcm[:42], None, seg, hop)
+    assert p2[-4:].tolist() == [40.0, 41.0, 0.0, 0.0] and off2.tolist() == off.tolist()
+    p3, l3, off3 = orc.vad_gate(pcm, lm, np.zeros((0, 2), np.uint32), hop)
+    assert len(p3) == 0 and l3.shape == (0, 3) and off3.tolist() == [0]
+
+
 # ---- committed golden vectors pin the oracle ----
 def test_oracle_matches_committed_golden(orc):
     from audioflow import synth
