@@ -200,7 +200,9 @@ AF_API int af_batch_strides(const af_batch *b, uint64_t *pcm_stride, uint64_t *l
 
 /* Device-resident run: outputs are device pointers.  Enqueues on `cuda_stream`
  * (a cudaStream_t passed as void*, NULL = the library's own stream) and returns without
- * synchronising when cuda_stream != NULL. */
+ * synchronising when cuda_stream != NULL.  The library's own stream is non-blocking: with cuda_stream == NULL the
+ * caller must have finished (synchronised) whatever produced the inputs or still touches the output buffers on
+ * other streams, the legacy default stream included. */
 AF_API int af_batch_run(af_batch *b, const af_outputs *out, void *cuda_stream);
 /* Host-buffer run (the reference-facing call): copies the streams H2D (chunked, overlapped
  * with compute), runs the pipeline and copies the requested outputs back; blocking. */
