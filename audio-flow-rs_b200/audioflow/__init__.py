@@ -47,7 +47,7 @@ class _VadConfigC(C.Structure):
 class PipelineConfigC(C.Structure):
     _fields_ = [("n_mels", C.c_uint32), ("f_min", C.c_float), ("f_max", C.c_float), ("log_floor", C.c_float),
                 ("log10", C.c_uint32), ("vad_enable", C.c_uint32), ("vad", _VadConfigC),
-                ("vad_frame_len", C.c_uint32), ("vad_hop", C.c_uint32), ("write_pcm", C.c_uint32)]
+                ("vad_frame_len", C.c_uint32), ("vad_hop", C.c_uint32), ("write_pcm", C.c_uint32), ("pcm16", C.c_uint32)]
 
 
 class StreamDescC(C.Structure):
@@ -69,6 +69,13 @@ class OutputsC(C.Structure):
     _fields_ = [("pcm", C.c_void_p), ("pcm_stride", C.c_uint64), ("logmel", C.c_void_p), ("logmel_stride", C.c_uint64),
                 ("vad", C.c_void_p), ("vad_stride", C.c_uint64), ("energy", C.c_void_p), ("energy_stride", C.c_uint64),
                 ("vad_final", C.c_void_p)]
+
+
+AF_MAX_GPUS = 16
+
+
+class ShardedOutputsC(C.Structure):
+    _fields_ = [("shard", OutputsC * AF_MAX_GPUS)]
 
 
 _lib = None
@@ -126,6 +133,21 @@ def load_library():
         "af_vad_segments": (C.c_int, [vp, C.c_uint64, vp, sz, vp, C.c_uint32, vp, vp]),
         "af_vad_gate": (C.c_int, [vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, sz,
                                   C.POINTER(GateOutputsC), vp]),
+        "af_current_device": (C.c_int, []), "af_set_stream": (C.c_int, [vp]), "af_init_multi": (C.c_int, [C.c_int]),
+        "af_comm_unique_id": (C.c_int, [u8p]), "af_comm_init_rank": (C.c_int, [C.c_int, C.c_int, u8p]),
+        "af_comm_size": (C.c_int, []), "af_comm_shutdown": (C.c_int, []),
+        "af_shard_partition": (C.c_int, [C.POINTER(StreamDescC), sz, C.c_int, szp]),
+        "af_sharded_batch_create": (C.c_int, [vp, C.POINTER(StreamDescC), sz, C.c_int, C.POINTER(vp)]),
+        "af_sharded_batch_destroy": (None, [vp]),
+        "af_sharded_batch_shard": (C.c_int, [vp, C.c_int, szp, szp, C.POINTER(C.c_int)]),
+        "af_sharded_batch_local": (vp, [vp, C.c_int]),
+        "af_sharded_batch_run": (C.c_int, [vp, C.POINTER(ShardedOutputsC), C.c_int, C.c_int]),
+        "af_sharded_batch_wait": (C.c_int, [vp]),
+        "af_sharded_batch_gathered": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                                C.POINTER(C.c_uint32)]),
+        "af_sharded_batch_gathered_host": (C.c_int, [vp, C.c_int, u8p, C.c_uint64]),
+        "af_sharded_batch_gather_ms": (C.c_int, [vp, C.c_int, fp]),
+        "af_sharded_batch_run_host": (C.c_int, [vp, C.POINTER(OutputsC)]),
         "af_debug_vad_energy_threshold": (C.c_float, [C.c_float]),
         "af_debug_resample_plan": (sz, [C.c_uint32, C.c_uint32, sz, fp, sz, C.POINTER(C.c_int)]),
         "af_session_create": (C.c_int, [vp, sz, C.c_uint32, C.c_uint16, C.c_uint16, C.c_uint32, C.POINTER(vp)]),
@@ -377,7 +399,7 @@ def pcm16_encode(samples) -> np.ndarray:
 # ---------------------------------------------------------------------------------------------
 def pipeline_config(n_mels: int = 80, vad: VadConfig | None = None, vad_enable: bool = True, vad_frame_len: int = 0,
                     vad_hop: int = 0, write_pcm: bool = True, log10: bool = False, f_min: float = 0.0,
-                    f_max: float = 8000.0, log_floor: float = 1e-10) -> PipelineConfigC:
+                    f_max: float = 8000.0, log_floor: float = 1e-10, pcm16: bool = False) -> PipelineConfigC:
     c = PipelineConfigC()
     load_library().af_pipeline_config_default(C.byref(c))
     c.n_mels = n_mels
@@ -387,6 +409,7 @@ def pipeline_config(n_mels: int = 80, vad: VadConfig | None = None, vad_enable: 
         c.vad = vad._c()
     c.vad_frame_len, c.vad_hop = vad_frame_len, vad_hop
     c.write_pcm = int(write_pcm)
+    c.pcm16 = int(pcm16)
     return c
 
 
@@ -422,15 +445,23 @@ class Pipeline:
         return b.split(out)
 
 
+def _desc_array(descs):
+    arr = (StreamDescC * max(len(descs), 1))()
+    for i, (ptr, n_samples, rate, ch, fmt) in enumerate(descs):
+        arr[i] = StreamDescC(ptr or None, n_samples, rate, ch, fmt)
+    return arr
+
+
 class Batch:
-    def __init__(self, pipe: Pipeline, descs, mem: int):
+    def __init__(self, pipe: Pipeline, descs, mem: int, _handle=None, _n=None):
         self.pipe = pipe
-        self.n = len(descs)
-        arr = (StreamDescC * max(self.n, 1))()
-        for i, (ptr, n_samples, rate, ch, fmt) in enumerate(descs):
-            arr[i] = StreamDescC(ptr, n_samples, rate, ch, fmt)
-        h = C.c_void_p()
-        _check(load_library().af_batch_create(pipe._h, arr, self.n, mem, C.byref(h)))
+        self._owned = _handle is None
+        if _handle is None:
+            self.n = len(descs)
+            h = C.c_void_p()
+            _check(load_library().af_batch_create(pipe._h, _desc_array(descs), self.n, mem, C.byref(h)))
+        else:                       # a shard of a ShardedBatch: the sharded batch owns the handle
+            self.n, h = _n, C.c_void_p(_handle)
         self._h = h
         self.mem = mem
         self.n_out = np.zeros(max(self.n, 1), np.uint32)
@@ -445,14 +476,14 @@ class Batch:
         self.energy_stride = (max(int(self.n_vad.max()) if self.n else 0, 4) + 3) // 4 * 4
 
     def __del__(self):
-        if getattr(self, "_h", None) and _lib is not None:
+        if getattr(self, "_h", None) and _lib is not None and getattr(self, "_owned", True):
             _lib.af_batch_destroy(self._h)
             self._h = None
 
     def alloc_host_outputs(self) -> dict:
         cfg = self.pipe.cfg
         n = max(self.n, 1)
-        out = {"pcm": np.zeros((n, self.pcm_stride), np.float32) if cfg.write_pcm else None,
+        out = {"pcm": np.zeros((n, self.pcm_stride), np.int16 if cfg.pcm16 else np.float32) if cfg.write_pcm else None,
                "logmel": np.zeros((n, self.logmel_stride), np.float32) if cfg.n_mels else None,
                "vad": np.zeros((n, self.vad_stride), np.uint8) if cfg.vad_enable else None,
                "energy": np.zeros((n, self.energy_stride), np.float32) if cfg.vad_enable else None,
@@ -497,6 +528,94 @@ class Batch:
                                       speech_frames=int(f.speech_frames), silence_frames=int(f.silence_frames))
             res.append(r)
         return res
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-GPU: stream sharding + NCCL result gather behind the C ABI
+# ---------------------------------------------------------------------------------------------
+def init_multi(n_gpus: int = 0):
+    """ONE process drives GPUs 0..n-1 (ncclCommInitAll inside the library)."""
+    _check(load_library().af_init_multi(n_gpus))
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    _check(load_library().af_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_init_rank(n_ranks: int, rank: int, uid: bytes | None):
+    buf = (C.c_uint8 * 128)(*uid) if uid is not None else None
+    _check(load_library().af_comm_init_rank(n_ranks, rank, buf))
+
+
+def comm_shutdown():
+    _check(load_library().af_comm_shutdown())
+
+
+def shard_partition(descs, n_shards: int):
+    """Contiguous blocks of stream indices balanced by input bytes: list of (lo, hi)."""
+    first = (C.c_size_t * (n_shards + 1))()
+    _check(load_library().af_shard_partition(_desc_array(descs), len(descs), n_shards, first))
+    return [(int(first[r]), int(first[r + 1])) for r in range(n_shards)]
+
+
+class ShardedBatch:
+    """n global streams over the ranks of the communicator; this process runs the shards of the ranks it owns."""
+
+    def __init__(self, pipe: Pipeline, descs, mem: int):
+        self.pipe, self.n, self.mem = pipe, len(descs), mem
+        h = C.c_void_p()
+        _check(load_library().af_sharded_batch_create(pipe._h, _desc_array(descs), self.n, mem, C.byref(h)))
+        self._h = h
+        self.n_ranks = max(int(load_library().af_comm_size()), 1)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.af_sharded_batch_destroy(self._h)
+            self._h = None
+
+    def shard(self, rank: int):
+        """(first, count, device) -- device is -1 when another process owns the rank."""
+        a, b, d = C.c_size_t(0), C.c_size_t(0), C.c_int(-1)
+        _check(load_library().af_sharded_batch_shard(self._h, rank, C.byref(a), C.byref(b), C.byref(d)))
+        return int(a.value), int(b.value), int(d.value)
+
+    def local(self, rank: int) -> Batch | None:
+        h = load_library().af_sharded_batch_local(self._h, rank)
+        if not h:
+            return None
+        return Batch(self.pipe, None, self.mem, _handle=h, _n=self.shard(rank)[1])
+
+    def run(self, outs: ShardedOutputsC, gather: bool = True, wait: bool = True):
+        _check(load_library().af_sharded_batch_run(self._h, C.byref(outs), int(gather), 0 if wait else 1))
+
+    def wait(self):
+        _check(load_library().af_sharded_batch_wait(self._h))
+
+    def gathered(self, rank: int):
+        """(device pointer, row stride, rows per rank, n_vad_frames[n]) of the last gather on a local rank's GPU."""
+        p, st, rows = C.c_void_p(), C.c_uint64(0), C.c_uint64(0)
+        nv = np.zeros(max(self.n, 1), np.uint32)
+        _check(load_library().af_sharded_batch_gathered(self._h, rank, C.byref(p), C.byref(st), C.byref(rows),
+                                                        nv.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return p.value, int(st.value), int(rows.value), nv[:self.n]
+
+    def gathered_host(self, rank: int) -> np.ndarray:
+        """[n_streams, stride] u8 states of ALL streams, global order, copied from the rank's GPU."""
+        _, _, _, nv = self.gathered(rank)
+        stride = (max(int(nv.max()) if self.n else 0, 16) + 15) // 16 * 16
+        out = np.zeros((max(self.n, 1), stride), np.uint8)
+        _check(load_library().af_sharded_batch_gathered_host(self._h, rank, out.ctypes.data_as(C.POINTER(C.c_uint8)), stride))
+        return out[:self.n]
+
+    def gather_ms(self, rank: int) -> float:
+        ms = C.c_float(0)
+        _check(load_library().af_sharded_batch_gather_ms(self._h, rank, C.byref(ms)))
+        return float(ms.value)
+
+    def run_host(self, o: OutputsC):
+        _check(load_library().af_sharded_batch_run_host(self._h, C.byref(o)))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -18,10 +18,14 @@
 // Replaces capture.rs:30-42, resampler.rs:71-93/132-166 (+ rubato) and the O(len) part of
 // vad.rs:157-168; the STFT/mel stages are spec-defined.  The sequential EMA/state
 // machine of vad.rs:101-153 runs in the scan kernels (af_kernels.cu).
+#include <atomic>
+
 #include "af_device.cuh"
 #include "af_launch.h"
 
 namespace af {
+
+constexpr int AF_MAX_GPUS_INTERNAL = 16;
 
 struct RsTile {
     StreamDev stream;
@@ -1152,12 +1156,17 @@ cudaError_t fused_pipe_stats(unsigned long long out[32])
 
 cudaError_t launch_fused(const FusedParams &P, int n_ctas, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(af_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+    // the attribute is per device: one flag per GPU of the process (af_init_multi drives several from one process)
+    static std::atomic<bool> attr_set[AF_MAX_GPUS_INTERNAL] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= AF_MAX_GPUS_INTERNAL) return cudaErrorInvalidDevice;
+    if (!attr_set[dev].load(std::memory_order_acquire)) {
+        e = cudaFuncSetAttribute(af_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(af_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set[dev].store(true, std::memory_order_release);
     }
     if (P.quarters) af_fused_kernel<true><<<n_ctas, FUSED_THREADS, sizeof(FusedSmem), st>>>(P);
     else af_fused_kernel<false><<<n_ctas, FUSED_THREADS, sizeof(FusedSmem), st>>>(P);

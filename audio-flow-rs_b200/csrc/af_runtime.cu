@@ -1,32 +1,29 @@
 // af_runtime.cu -- the C ABI of libaudioflow_gpu.so (include/audioflow_gpu.h): library context,
 // compat objects mirroring the reference's Rust types, and the batched pipeline host runtime.
 #include <algorithm>
-#include <atomic>
 #include <cmath>
-#include <cstdarg>
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <map>
-#include <memory>
-#include <mutex>
-#include <string>
-#include <vector>
 
-#include "../../include/audioflow_gpu.h"
-#include "af_device.cuh"
-#include "af_launch.h"
-#include "af_plan.h"
+#include "af_internal.h"
 
 using namespace af;
+using namespace afrt;
 
 // ------------------------------------------------------------------------------------------
-// context
+// contexts: one per GPU the process uses
 // ------------------------------------------------------------------------------------------
+namespace afrt {
+
 namespace {
-
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
+Context g_ctxs[MAX_DEV];
+std::mutex g_init_mu;                 // serialises device initialisation / shutdown
+std::atomic<int> g_default_dev{-1};   // the first device initialised: what a thread without a selection of its own uses
+thread_local int t_dev = -1;          // the device this thread works on
+std::string g_variant = "auto";
+}  // namespace
 
 int fail(int code, const char *fmt, ...)
 {
@@ -39,63 +36,96 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
-#define AF_CUDA(expr)                                                                              \
-    do {                                                                                           \
-        cudaError_t _e = (expr);                                                                   \
-        if (_e != cudaSuccess) return fail(AF_ERR_CUDA, "CUDA error %s at %s:%d: %s", #expr, __FILE__, __LINE__, \
-                                           cudaGetErrorString(_e));                                \
-    } while (0)
+Context &cur_ctx() { return g_ctxs[t_dev >= 0 ? t_dev : 0]; }
+int cur_device() { return t_dev; }
+Context *device_ctx(int device) { return (device >= 0 && device < MAX_DEV && g_ctxs[device].ready) ? &g_ctxs[device] : nullptr; }
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+const std::string &kernel_variant() { return g_variant; }
 
-struct DevBuf {                       // grow-only device buffer
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
+int init_device(int device)
+{
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        return fail(AF_ERR_NO_DEVICE, "no CUDA device available (%s); libaudioflow_gpu has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-struct FracTable {                    // device copy of the f32 fractional offsets of one rate pair
-    float *d = nullptr;
-    size_t n = 0;
-    ~FracTable() { if (d) cudaFree(d); }
-};
-
-struct RatePlan {                     // batch-path plan of one (in, out) pair, grown on demand
-    RsRecurrence rec;                 // state after cum.size() - 1 chunks
-    std::vector<uint64_t> cum{0};     // cum[c] = outputs after c chunks (table mode)
-    std::vector<float> frac;          // host copy (table mode)
-    std::shared_ptr<FracTable> dev;   // device copy covering frac.size() entries
-};
-
-struct Context {
-    bool ready = false;
-    int device = -1;
-    int sm_count = 148;
-    cudaStream_t stream = nullptr;
-    FftTables *d_fft = nullptr;
-    std::mutex mu;                    // guards the scratch buffers and the plan cache
-    DevBuf scratch_in, scratch_out, scratch_aux, scratch_jobs;
-    std::map<uint64_t, RatePlan> plans;
-    std::string variant = "auto";
-};
-Context g_ctx;
+    if (device < 0 || device >= n || device >= MAX_DEV) return fail(AF_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+    Context &c = g_ctxs[device];
+    if (c.ready) return AF_OK;
+    int prev = 0;
+    (void)cudaGetDevice(&prev);
+    struct Back { int d; ~Back() { (void)cudaSetDevice(d); } } back{prev};
+    AF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    AF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(AF_ERR_NO_DEVICE, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU", device, prop.name,
+                    prop.major, prop.minor);
+    c.sm_count = prop.multiProcessorCount;
+    AF_CUDA(cudaStreamCreateWithFlags(&c.own, cudaStreamNonBlocking));
+    c.stream = c.own;
+    // the gather stream has the lowest priority: when a collective kernel and the next batch's fused kernel become
+    // runnable together, the SMs go to the fused kernel (one persistent CTA per SM) first
+    int prio_lo = 0, prio_hi = 0;
+    AF_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    AF_CUDA(cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, prio_lo));
+    FftTables *h = new FftTables;
+    build_fft_tables(h);
+    cudaError_t ce = cudaMalloc(&c.d_fft, sizeof(FftTables));
+    if (ce == cudaSuccess) ce = cudaMemcpy(c.d_fft, h, sizeof(FftTables), cudaMemcpyHostToDevice);
+    delete h;
+    AF_CUDA(ce);
+    c.device = device;
+    c.ready = true;
+    int none = -1;
+    g_default_dev.compare_exchange_strong(none, device);
+    return AF_OK;
+}
 
 int require_ctx()
 {
-    if (!g_ctx.ready) {
-        int rc = af_init(-1);
+    int dev = t_dev >= 0 ? t_dev : g_default_dev.load();
+    if (dev < 0) {                                    // nothing initialised yet: the calling thread's current CUDA device
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) { (void)cudaGetLastError(); cur = 0; }
+        dev = cur;
+    }
+    if (!g_ctxs[dev < MAX_DEV ? dev : 0].ready) {
+        int rc = init_device(dev);
         if (rc != AF_OK) return rc;
     }
+    t_dev = dev;
+    AF_CUDA(cudaSetDevice(dev));
     return AF_OK;
 }
+
+DevScope::DevScope(int dev_) : prev_lib(t_dev), prev_cuda(-1), dev(dev_), rc(AF_OK)
+{
+    if (cudaGetDevice(&prev_cuda) != cudaSuccess) { (void)cudaGetLastError(); prev_cuda = -1; }
+    if (dev < 0 || dev >= MAX_DEV || !g_ctxs[dev].ready) { rc = fail(AF_ERR_INVALID, "handle belongs to device %d, which is not initialised", dev); return; }
+    t_dev = dev;
+    if (prev_cuda != dev && cudaSetDevice(dev) != cudaSuccess) rc = fail(AF_ERR_CUDA, "cudaSetDevice(%d) failed", dev);
+}
+DevScope::~DevScope()
+{
+    t_dev = prev_lib;
+    if (prev_cuda >= 0 && prev_cuda != dev) (void)cudaSetDevice(prev_cuda);
+}
+
+int device_of_pointer(const void *p)
+{
+    if (!p) return -1;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
+}
+
+}  // namespace afrt
+
+namespace {
 
 // warp-to-role layout of the fused kernel (warp_role, af_common.cuh): the V warp gets a lighter scheduler when it
 // has energy chains to run.  AF_LAYOUT=<n> overrides (experiments).
@@ -105,8 +135,6 @@ uint32_t fused_layout(bool energies)
     if (forced >= 0 && forced < N_LAYOUTS) return (uint32_t)forced;
     return energies ? 2u : 0u;
 }
-
-inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // exact output length of BatchResampler::process(all) + flush() and (optionally) the frac table
 int plan_rate(uint32_t in_rate, uint32_t out_rate, uint64_t n_in, uint64_t *n_out, uint32_t *mode, uint32_t *p,
@@ -122,8 +150,8 @@ int plan_rate(uint32_t in_rate, uint32_t out_rate, uint64_t n_in, uint64_t *n_ou
                     in_rate, out_rate, probe.t);
     const uint64_t chunks = (n_in + RS_CHUNK - 1) / RS_CHUNK;
     if (probe.exact) { *n_out = rs_exact_count(probe, chunks); return AF_OK; }
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    RatePlan &pl = g_ctx.plans[((uint64_t)in_rate << 32) | out_rate];
+    std::lock_guard<std::mutex> lk(cur_ctx().mu);
+    RatePlan &pl = cur_ctx().plans[((uint64_t)in_rate << 32) | out_rate];
     if (pl.rec.in_rate == 0) pl.rec.init(in_rate, out_rate);
     bool grew = false;
     while (pl.cum.size() - 1 < chunks) {
@@ -189,55 +217,51 @@ AF_API int af_debug_pipe_stats(uint64_t out[32])
 
 AF_API int af_init(int device)
 {
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) {
-        (void)cudaGetLastError();
-        return fail(AF_ERR_NO_DEVICE, "no CUDA device available (%s); libaudioflow_gpu has no CPU fallback",
-                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-    }
-    if (device < 0) {
-        if (g_ctx.ready) return AF_OK;
-        int cur = 0;
-        if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
-        device = cur;
-    }
-    if (device >= n) return fail(AF_ERR_INVALID, "device %d out of range (%d devices)", device, n);
-    if (g_ctx.ready && g_ctx.device == device) return AF_OK;
-    if (g_ctx.ready) return fail(AF_ERR_INVALID, "already initialised on device %d", g_ctx.device);
+    // selects `device` for the calling thread (initialising it on first use); device < 0: keep the thread's / the
+    // process default, or take the thread's current CUDA device when nothing is initialised yet
+    if (device < 0) return require_ctx();
+    int rc = init_device(device);
+    if (rc != AF_OK) return rc;
+    t_dev = device;
     AF_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    AF_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
-        return fail(AF_ERR_NO_DEVICE, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU", device, prop.name,
-                    prop.major, prop.minor);
-    g_ctx.sm_count = prop.multiProcessorCount;
-    AF_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
-    FftTables *h = new FftTables;
-    build_fft_tables(h);
-    cudaError_t ce = cudaMalloc(&g_ctx.d_fft, sizeof(FftTables));
-    if (ce == cudaSuccess) ce = cudaMemcpy(g_ctx.d_fft, h, sizeof(FftTables), cudaMemcpyHostToDevice);
-    delete h;
-    AF_CUDA(ce);
-    g_ctx.device = device;
-    g_ctx.ready = true;
+    return AF_OK;
+}
+
+AF_API int af_current_device(void) { return t_dev >= 0 ? t_dev : g_default_dev.load(); }
+
+AF_API int af_set_stream(void *cuda_stream)
+{
+    int rc = require_ctx();
+    if (rc) return rc;
+    Context &c = cur_ctx();
+    c.stream = cuda_stream ? (cudaStream_t)cuda_stream : c.own;
     return AF_OK;
 }
 
 AF_API int af_shutdown(void)
 {
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    if (!g_ctx.ready) return AF_OK;
-    cudaDeviceSynchronize();
-    g_ctx.plans.clear();
-    g_ctx.scratch_in.release(); g_ctx.scratch_out.release(); g_ctx.scratch_aux.release(); g_ctx.scratch_jobs.release();
-    if (g_ctx.d_fft) cudaFree(g_ctx.d_fft);
-    g_ctx.d_fft = nullptr;
-    if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
-    g_ctx.stream = nullptr;
-    g_ctx.ready = false;
-    g_ctx.device = -1;
+    comm_shutdown_all();
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    int prev = 0;
+    (void)cudaGetDevice(&prev);
+    for (int d = 0; d < MAX_DEV; ++d) {
+        Context &c = g_ctxs[d];
+        if (!c.ready) continue;
+        (void)cudaSetDevice(d);
+        cudaDeviceSynchronize();
+        c.plans.clear();
+        c.scratch_in.release(); c.scratch_out.release(); c.scratch_aux.release(); c.scratch_jobs.release();
+        if (c.d_fft) cudaFree(c.d_fft);
+        c.d_fft = nullptr;
+        if (c.own) cudaStreamDestroy(c.own);
+        if (c.side) cudaStreamDestroy(c.side);
+        c.stream = nullptr; c.own = nullptr; c.side = nullptr;
+        c.ready = false;
+        c.device = -1;
+    }
+    (void)cudaSetDevice(prev);
+    g_default_dev.store(-1);
+    t_dev = -1;
     return AF_OK;
 }
 
@@ -246,7 +270,7 @@ AF_API int af_host_alloc(void **ptr, size_t bytes)
     if (!ptr) return fail(AF_ERR_INVALID, "null pointer");
     int rc = require_ctx();
     if (rc) return rc;
-    AF_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    AF_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));    // pinned for every device of the process
     return AF_OK;
 }
 
@@ -261,7 +285,7 @@ AF_API int af_set_kernel_variant(const char *name)
     if (!name) return fail(AF_ERR_INVALID, "null variant name");
     std::string v(name);
     if (v != "auto" && v != "sync" && v != "tma") return fail(AF_ERR_INVALID, "unknown kernel variant '%s'", name);
-    g_ctx.variant = v;
+    g_variant = v;
     return AF_OK;
 }
 
@@ -279,14 +303,14 @@ AF_API int af_to_mono(const float *samples, size_t n_samples, uint16_t channels,
     if (out_cap < frames) return fail(AF_ERR_CAPACITY, "output capacity %zu < %zu frames", out_cap, frames);
     if (n_out) *n_out = frames;
     if (frames == 0) return AF_OK;
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    AF_CUDA(g_ctx.scratch_in.reserve(n_samples * sizeof(float)));
-    AF_CUDA(g_ctx.scratch_out.reserve(frames * sizeof(float)));
-    cudaStream_t st = g_ctx.stream;
-    AF_CUDA(cudaMemcpyAsync(g_ctx.scratch_in.p, samples, n_samples * sizeof(float), cudaMemcpyHostToDevice, st));
-    AF_CUDA(launch_to_mono((const float *)g_ctx.scratch_in.p, n_samples, channels, (float *)g_ctx.scratch_out.p, frames, st));
+    std::lock_guard<std::mutex> lk(cur_ctx().mu);
+    AF_CUDA(cur_ctx().scratch_in.reserve(n_samples * sizeof(float)));
+    AF_CUDA(cur_ctx().scratch_out.reserve(frames * sizeof(float)));
+    cudaStream_t st = cur_ctx().stream;
+    AF_CUDA(cudaMemcpyAsync(cur_ctx().scratch_in.p, samples, n_samples * sizeof(float), cudaMemcpyHostToDevice, st));
+    AF_CUDA(launch_to_mono((const float *)cur_ctx().scratch_in.p, n_samples, channels, (float *)cur_ctx().scratch_out.p, frames, st));
     count_launch();
-    AF_CUDA(cudaMemcpyAsync(out, g_ctx.scratch_out.p, frames * sizeof(float), cudaMemcpyDeviceToHost, st));
+    AF_CUDA(cudaMemcpyAsync(out, cur_ctx().scratch_out.p, frames * sizeof(float), cudaMemcpyDeviceToHost, st));
     AF_CUDA(cudaStreamSynchronize(st));
     return AF_OK;
 }
@@ -295,6 +319,7 @@ AF_API int af_to_mono(const float *samples, size_t n_samples, uint16_t channels,
 // AudioResampler / BatchResampler (resampler.rs)
 // ------------------------------------------------------------------------------------------
 struct af_resampler {
+    int device = -1;                  // the GPU the object was created on
     RsRecurrence rec;
     float hist[2 * RS_POLY];          // the last 16 input frames (rubato's buffer head)
     std::vector<float> frac;          // scratch
@@ -305,6 +330,7 @@ static int resampler_run_chunks(af_resampler *r, const float *input, size_t n_ch
                                 size_t *n_out)
 {
     // runs n_chunks complete 128-frame chunks through the GPU; input has n_chunks * 128 frames
+    AF_SCOPE(r->device);
     const uint64_t c0 = r->rec.chunks;
     const uint64_t n_begin = r->rec.n_out;
     RsRecurrence saved = r->rec;
@@ -321,29 +347,29 @@ static int resampler_run_chunks(af_resampler *r, const float *input, size_t n_ch
     memcpy(r->stage.data(), r->hist, sizeof(r->hist));
     memcpy(r->stage.data() + 2 * RS_POLY, input, n_in * sizeof(float));
 
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    cudaStream_t st = g_ctx.stream;
+    std::lock_guard<std::mutex> lk(cur_ctx().mu);
+    cudaStream_t st = cur_ctx().stream;
     const size_t in_bytes = r->stage.size() * sizeof(float);
     const size_t frac_bytes = r->frac.size() * sizeof(float);
-    AF_CUDA(g_ctx.scratch_in.reserve(in_bytes));
-    AF_CUDA(g_ctx.scratch_aux.reserve(frac_bytes + 16));
-    AF_CUDA(g_ctx.scratch_out.reserve(produced * sizeof(float) + 16));
-    AF_CUDA(g_ctx.scratch_jobs.reserve(sizeof(ResampleJob)));
-    AF_CUDA(cudaMemcpyAsync(g_ctx.scratch_in.p, r->stage.data(), in_bytes, cudaMemcpyHostToDevice, st));
-    if (frac_bytes) AF_CUDA(cudaMemcpyAsync(g_ctx.scratch_aux.p, r->frac.data(), frac_bytes, cudaMemcpyHostToDevice, st));
+    AF_CUDA(cur_ctx().scratch_in.reserve(in_bytes));
+    AF_CUDA(cur_ctx().scratch_aux.reserve(frac_bytes + 16));
+    AF_CUDA(cur_ctx().scratch_out.reserve(produced * sizeof(float) + 16));
+    AF_CUDA(cur_ctx().scratch_jobs.reserve(sizeof(ResampleJob)));
+    AF_CUDA(cudaMemcpyAsync(cur_ctx().scratch_in.p, r->stage.data(), in_bytes, cudaMemcpyHostToDevice, st));
+    if (frac_bytes) AF_CUDA(cudaMemcpyAsync(cur_ctx().scratch_aux.p, r->frac.data(), frac_bytes, cudaMemcpyHostToDevice, st));
     ResampleJob job;
-    job.data = (const float *)g_ctx.scratch_in.p;
+    job.data = (const float *)cur_ctx().scratch_in.p;
     job.data_base = (long long)(c0 * RS_CHUNK) - 2 * RS_POLY;
     job.n_valid_end = (long long)((c0 + n_chunks) * RS_CHUNK);
     job.n_begin = n_begin; job.n_end = n_end;
     job.p = r->rec.p; job.q = r->rec.q; job.mode = r->rec.mode();
-    job.frac = (const float *)g_ctx.scratch_aux.p - n_begin;      // indexed by the global output index
-    job.out = (float *)g_ctx.scratch_out.p;
-    AF_CUDA(cudaMemcpyAsync(g_ctx.scratch_jobs.p, &job, sizeof(job), cudaMemcpyHostToDevice, st));
+    job.frac = (const float *)cur_ctx().scratch_aux.p - n_begin;      // indexed by the global output index
+    job.out = (float *)cur_ctx().scratch_out.p;
+    AF_CUDA(cudaMemcpyAsync(cur_ctx().scratch_jobs.p, &job, sizeof(job), cudaMemcpyHostToDevice, st));
     if (produced) {
-        AF_CUDA(launch_resample_jobs((const ResampleJob *)g_ctx.scratch_jobs.p, 1, (uint32_t)produced, st));
+        AF_CUDA(launch_resample_jobs((const ResampleJob *)cur_ctx().scratch_jobs.p, 1, (uint32_t)produced, st));
         count_launch();
-        AF_CUDA(cudaMemcpyAsync(out, g_ctx.scratch_out.p, produced * sizeof(float), cudaMemcpyDeviceToHost, st));
+        AF_CUDA(cudaMemcpyAsync(out, cur_ctx().scratch_out.p, produced * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     AF_CUDA(cudaStreamSynchronize(st));
     memcpy(r->hist, r->stage.data() + r->stage.size() - 2 * RS_POLY, sizeof(r->hist));
@@ -358,6 +384,7 @@ AF_API int af_resampler_create(uint32_t input_rate, uint32_t output_rate, af_res
     int rc = require_ctx();
     if (rc) return rc;
     af_resampler *r = new af_resampler;
+    r->device = cur_device();
     r->rec.init(input_rate, output_rate);
     memset(r->hist, 0, sizeof(r->hist));
     if (!r->rec.passthrough && r->rec.end_idx <= 0) {
@@ -463,6 +490,7 @@ AF_API int af_batch_resampler_flush(af_batch_resampler *b, float *out, size_t ou
 // VoiceActivityDetector (vad.rs)
 // ------------------------------------------------------------------------------------------
 struct af_vad {
+    int device = -1;                  // the GPU the detector state lives on
     af_vad_config cfg;
     VadParams prm;
     VadState host;                    // mirror of the device state after the last call
@@ -494,6 +522,7 @@ AF_API int af_vad_create(const af_vad_config *cfg, af_vad **out)
     int rc = require_ctx();
     if (rc) return rc;
     af_vad *v = new af_vad;
+    v->device = cur_device();
     if (cfg) v->cfg = *cfg; else af_vad_config_default(&v->cfg);
     v->prm = make_vad_params(v->cfg);
     memset(&v->host, 0, sizeof(v->host));
@@ -507,7 +536,7 @@ AF_API int af_vad_create(const af_vad_config *cfg, af_vad **out)
 AF_API void af_vad_destroy(af_vad *v)
 {
     if (!v) return;
-    if (v->dev) cudaFree(v->dev);
+    if (v->dev) { DevScope scope_(v->device); cudaFree(v->dev); }
     delete v;
 }
 
@@ -521,23 +550,24 @@ AF_API int af_vad_detect_frames(af_vad *v, const float *samples, size_t n, uint3
     if (n_frames) *n_frames = T;
     if (T == 0) return AF_OK;
     if (states && states_cap < T) return fail(AF_ERR_CAPACITY, "states capacity %zu < %zu frames", states_cap, T);
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    cudaStream_t st = g_ctx.stream;
-    AF_CUDA(g_ctx.scratch_in.reserve(n * sizeof(float)));
-    AF_CUDA(g_ctx.scratch_aux.reserve(T * sizeof(float)));
-    AF_CUDA(g_ctx.scratch_out.reserve(T));
-    AF_CUDA(cudaMemcpyAsync(g_ctx.scratch_in.p, samples, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    AF_SCOPE(v->device);
+    std::lock_guard<std::mutex> lk(cur_ctx().mu);
+    cudaStream_t st = cur_ctx().stream;
+    AF_CUDA(cur_ctx().scratch_in.reserve(n * sizeof(float)));
+    AF_CUDA(cur_ctx().scratch_aux.reserve(T * sizeof(float)));
+    AF_CUDA(cur_ctx().scratch_out.reserve(T));
+    AF_CUDA(cudaMemcpyAsync(cur_ctx().scratch_in.p, samples, n * sizeof(float), cudaMemcpyHostToDevice, st));
     EnergyJob ej{};
-    ej.y = (const float *)g_ctx.scratch_in.p; ej.y_stride = 0; ej.n_frames = nullptr; ej.n_frames_all = (uint32_t)T;
-    ej.frame_len = frame_len; ej.hop = hop; ej.energy = (float *)g_ctx.scratch_aux.p; ej.energy_stride = 0; ej.n_streams = 1;
+    ej.y = (const float *)cur_ctx().scratch_in.p; ej.y_stride = 0; ej.n_frames = nullptr; ej.n_frames_all = (uint32_t)T;
+    ej.frame_len = frame_len; ej.hop = hop; ej.energy = (float *)cur_ctx().scratch_aux.p; ej.energy_stride = 0; ej.n_streams = 1;
     AF_CUDA(launch_frame_energy(ej, st));
     ScanJob sj{};
-    sj.energy = (const float *)g_ctx.scratch_aux.p; sj.energy_stride = 0; sj.n_frames = nullptr; sj.n_frames_all = (uint32_t)T;
-    sj.states = (uint8_t *)g_ctx.scratch_out.p; sj.states_stride = 0; sj.state_io = v->dev; sj.final_out = nullptr;
+    sj.energy = (const float *)cur_ctx().scratch_aux.p; sj.energy_stride = 0; sj.n_frames = nullptr; sj.n_frames_all = (uint32_t)T;
+    sj.states = (uint8_t *)cur_ctx().scratch_out.p; sj.states_stride = 0; sj.state_io = v->dev; sj.final_out = nullptr;
     sj.prm = v->prm; sj.n_streams = 1;
     AF_CUDA(launch_vad_scan(sj, st));
     count_launch(2);
-    if (states) AF_CUDA(cudaMemcpyAsync(states, g_ctx.scratch_out.p, T, cudaMemcpyDeviceToHost, st));
+    if (states) AF_CUDA(cudaMemcpyAsync(states, cur_ctx().scratch_out.p, T, cudaMemcpyDeviceToHost, st));
     AF_CUDA(cudaMemcpyAsync(&v->host, v->dev, sizeof(VadState), cudaMemcpyDeviceToHost, st));
     AF_CUDA(cudaStreamSynchronize(st));
     return AF_OK;
@@ -566,6 +596,7 @@ AF_API int af_vad_reset(af_vad *v)
 {
     if (!v) return fail(AF_ERR_INVALID, "null detector");
     memset(&v->host, 0, sizeof(v->host));
+    AF_SCOPE(v->device);
     AF_CUDA(cudaMemset(v->dev, 0, sizeof(VadState)));
     return AF_OK;
 }
@@ -586,17 +617,17 @@ AF_API int af_vad_frame_energy(const float *frame, size_t n, float *energy)
     int rc = require_ctx();
     if (rc) return rc;
     if (n == 0) { *energy = 0.0f; return AF_OK; }
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    cudaStream_t st = g_ctx.stream;
-    AF_CUDA(g_ctx.scratch_in.reserve(n * sizeof(float)));
-    AF_CUDA(g_ctx.scratch_aux.reserve(sizeof(float)));
-    AF_CUDA(cudaMemcpyAsync(g_ctx.scratch_in.p, frame, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    std::lock_guard<std::mutex> lk(cur_ctx().mu);
+    cudaStream_t st = cur_ctx().stream;
+    AF_CUDA(cur_ctx().scratch_in.reserve(n * sizeof(float)));
+    AF_CUDA(cur_ctx().scratch_aux.reserve(sizeof(float)));
+    AF_CUDA(cudaMemcpyAsync(cur_ctx().scratch_in.p, frame, n * sizeof(float), cudaMemcpyHostToDevice, st));
     EnergyJob ej{};
-    ej.y = (const float *)g_ctx.scratch_in.p; ej.n_frames_all = 1; ej.frame_len = (uint32_t)n; ej.hop = (uint32_t)n;
-    ej.energy = (float *)g_ctx.scratch_aux.p; ej.n_streams = 1;
+    ej.y = (const float *)cur_ctx().scratch_in.p; ej.n_frames_all = 1; ej.frame_len = (uint32_t)n; ej.hop = (uint32_t)n;
+    ej.energy = (float *)cur_ctx().scratch_aux.p; ej.n_streams = 1;
     AF_CUDA(launch_frame_energy(ej, st));
     count_launch();
-    AF_CUDA(cudaMemcpyAsync(energy, g_ctx.scratch_aux.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+    AF_CUDA(cudaMemcpyAsync(energy, cur_ctx().scratch_aux.p, sizeof(float), cudaMemcpyDeviceToHost, st));
     AF_CUDA(cudaStreamSynchronize(st));
     return AF_OK;
 }
@@ -607,14 +638,14 @@ AF_API int af_pcm16_encode(const float *samples, size_t n, int16_t *out)
     int rc = require_ctx();
     if (rc) return rc;
     if (n == 0) return AF_OK;
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    cudaStream_t st = g_ctx.stream;
-    AF_CUDA(g_ctx.scratch_in.reserve(n * sizeof(float)));
-    AF_CUDA(g_ctx.scratch_out.reserve(n * sizeof(int16_t)));
-    AF_CUDA(cudaMemcpyAsync(g_ctx.scratch_in.p, samples, n * sizeof(float), cudaMemcpyHostToDevice, st));
-    AF_CUDA(launch_pcm16((const float *)g_ctx.scratch_in.p, n, (int16_t *)g_ctx.scratch_out.p, st));
+    std::lock_guard<std::mutex> lk(cur_ctx().mu);
+    cudaStream_t st = cur_ctx().stream;
+    AF_CUDA(cur_ctx().scratch_in.reserve(n * sizeof(float)));
+    AF_CUDA(cur_ctx().scratch_out.reserve(n * sizeof(int16_t)));
+    AF_CUDA(cudaMemcpyAsync(cur_ctx().scratch_in.p, samples, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    AF_CUDA(launch_pcm16((const float *)cur_ctx().scratch_in.p, n, (int16_t *)cur_ctx().scratch_out.p, st));
     count_launch();
-    AF_CUDA(cudaMemcpyAsync(out, g_ctx.scratch_out.p, n * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    AF_CUDA(cudaMemcpyAsync(out, cur_ctx().scratch_out.p, n * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
     AF_CUDA(cudaStreamSynchronize(st));
     return AF_OK;
 }
@@ -625,7 +656,9 @@ AF_API int af_vad_segments(const uint8_t *states, uint64_t vad_stride, const uin
     if (!states || !n_frames || !seg || !n_seg) return fail(AF_ERR_INVALID, "null argument");
     int rc = require_ctx();
     if (rc) return rc;
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_ctx.stream;
+    const int owner = device_of_pointer(states);                 // the GPU that holds the states (else the thread's device)
+    AF_SCOPE(owner >= 0 && device_ctx(owner) ? owner : cur_device());
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : cur_ctx().stream;
     AF_CUDA(launch_vad_segments(states, vad_stride, n_frames, (uint32_t)n_streams, seg, seg_cap, n_seg, st));
     count_launch();
     if (!cuda_stream) AF_CUDA(cudaStreamSynchronize(st));
@@ -641,7 +674,9 @@ AF_API int af_vad_gate(const float *pcm, uint64_t pcm_stride, const float *logme
     if ((out->pcm && !pcm) || (out->logmel && (!logmel || n_mels == 0))) return fail(AF_ERR_INVALID, "gated output requested without its source");
     int rc = require_ctx();
     if (rc) return rc;
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_ctx.stream;
+    const int owner = device_of_pointer(seg);
+    AF_SCOPE(owner >= 0 && device_ctx(owner) ? owner : cur_device());
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : cur_ctx().stream;
     GateJob J{};
     J.pcm = out->pcm ? pcm : nullptr; J.pcm_stride = pcm_stride;
     J.logmel = out->logmel ? logmel : nullptr; J.logmel_stride = logmel_stride;
@@ -665,8 +700,30 @@ AF_API int af_vad_gate(const float *pcm, uint64_t pcm_stride, const float *logme
 struct af_pipeline {
     af_pipeline_config cfg;
     VadParams vad_prm;
-    MelTables *d_mel = nullptr;
+    MelTables h_mel;                              // built once on the host ...
+    MelTables *d_mel[MAX_DEV] = {};               // ... and copied to every device that runs the pipeline, on first use
+    std::mutex mu;
 };
+
+namespace {
+// the pipeline's mel tables on the calling thread's device (nullptr without features or on a CUDA failure)
+MelTables *pipe_mel(af_pipeline *p)
+{
+    if (!p->cfg.n_mels) return nullptr;
+    const int dev = cur_device();
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (!p->d_mel[dev]) {
+        cudaError_t e = cudaMalloc(&p->d_mel[dev], sizeof(MelTables));
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_mel[dev], &p->h_mel, sizeof(MelTables), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            if (p->d_mel[dev]) cudaFree(p->d_mel[dev]);
+            p->d_mel[dev] = nullptr;
+            fail(AF_ERR_CUDA, "mel tables: %s", cudaGetErrorString(e));
+        }
+    }
+    return p->d_mel[dev];
+}
+}  // namespace
 
 namespace {
 
@@ -693,6 +750,8 @@ struct SubBatch {                     // a group of streams resident on the devi
 
 struct af_batch {
     af_pipeline *pipe = nullptr;
+    int device = -1;                  // the GPU the batch was planned for
+    MelTables *d_mel = nullptr;       // the pipeline's mel tables on that GPU
     int mem = AF_MEM_DEVICE;
     std::vector<HostStream> streams;
     std::vector<SubBatch> subs;
@@ -703,7 +762,7 @@ struct af_batch {
     float *d_pcm_scratch = nullptr; size_t pcm_scratch_rows = 0;
     // host mode slots
     struct Slot {
-        void *d_in = nullptr; float *d_pcm = nullptr; float *d_logmel = nullptr; uint8_t *d_vad = nullptr;
+        void *d_in = nullptr; float *d_pcm = nullptr; int16_t *d_pcm16 = nullptr; float *d_logmel = nullptr; uint8_t *d_vad = nullptr;
         float *d_energy = nullptr; VadState *d_final = nullptr;
         cudaStream_t st = nullptr;
     };
@@ -775,7 +834,7 @@ int run_sub(af_batch *b, SubBatch &sb, float *pcm, uint64_t pcm_stride, float *l
     if (!sb.h_tiles.empty()) {
         FusedParams P{};
         P.streams = sb.d_streams; P.tiles = sb.d_tiles; P.n_tiles = (uint32_t)sb.h_tiles.size();
-        P.fft = g_ctx.d_fft; P.mel = b->pipe->d_mel;
+        P.fft = cur_ctx().d_fft; P.mel = b->d_mel;
         P.pcm = pcm; P.pcm_stride = pcm_stride;
         P.logmel = cfg.n_mels ? logmel : nullptr; P.logmel_stride = logmel_stride;
         P.energy = stft_vad ? energy : nullptr; P.energy_stride = energy_stride;
@@ -783,10 +842,10 @@ int run_sub(af_batch *b, SubBatch &sb, float *pcm, uint64_t pcm_stride, float *l
         P.do_energy = stft_vad ? 1 : 0;
         P.log_floor = cfg.log_floor;
         P.log_scale = cfg.log10 ? 0.30102999566398120f : 0.69314718055994531f;   // log10(2) : ln(2)
-        P.use_stage = g_ctx.variant == "sync" ? 0u : 1u;
+        P.use_stage = kernel_variant() == "sync" ? 0u : 1u;
         P.layout = fused_layout(stft_vad);
         P.quarters = sb.quarters ? 1u : 0u;
-        const int n_ctas = (int)std::min<size_t>(sb.h_tiles.size(), (size_t)g_ctx.sm_count);   // one persistent CTA per SM
+        const int n_ctas = (int)std::min<size_t>(sb.h_tiles.size(), (size_t)cur_ctx().sm_count);   // one persistent CTA per SM
         AF_CUDA(launch_fused(P, n_ctas, st));
         count_launch();
     }
@@ -831,6 +890,7 @@ AF_API void af_pipeline_config_default(af_pipeline_config *cfg)
     af_vad_config_default(&cfg->vad);
     cfg->vad_frame_len = 0; cfg->vad_hop = 0;
     cfg->write_pcm = 1;
+    cfg->pcm16 = 0;
 }
 
 AF_API int af_pipeline_create(const af_pipeline_config *cfg, af_pipeline **out)
@@ -847,12 +907,8 @@ AF_API int af_pipeline_create(const af_pipeline_config *cfg, af_pipeline **out)
     p->cfg = c;
     p->vad_prm = make_vad_params(c.vad);
     if (c.n_mels) {
-        MelTables *h = new MelTables;
-        if (!build_mel_tables(c.n_mels, c.f_min, c.f_max, h)) { delete h; delete p; return fail(AF_ERR_INVALID, "mel table construction failed"); }
-        cudaError_t e = cudaMalloc(&p->d_mel, sizeof(MelTables));
-        if (e == cudaSuccess) e = cudaMemcpy(p->d_mel, h, sizeof(MelTables), cudaMemcpyHostToDevice);
-        delete h;
-        if (e != cudaSuccess) { delete p; AF_CUDA(e); }
+        if (!build_mel_tables(c.n_mels, c.f_min, c.f_max, &p->h_mel)) { delete p; return fail(AF_ERR_INVALID, "mel table construction failed"); }
+        if (!pipe_mel(p)) { delete p; return AF_ERR_CUDA; }
     }
     *out = p;
     return AF_OK;
@@ -861,13 +917,15 @@ AF_API int af_pipeline_create(const af_pipeline_config *cfg, af_pipeline **out)
 AF_API void af_pipeline_destroy(af_pipeline *p)
 {
     if (!p) return;
-    if (p->d_mel) cudaFree(p->d_mel);
+    for (int d = 0; d < MAX_DEV; ++d)
+        if (p->d_mel[d] && device_ctx(d)) { DevScope scope_(d); cudaFree(p->d_mel[d]); }
     delete p;
 }
 
 AF_API void af_batch_destroy(af_batch *b)
 {
     if (!b) return;
+    DevScope scope_(b->device);
     cudaDeviceSynchronize();
     for (auto &sb : b->subs) {
         if (sb.d_streams) cudaFree(sb.d_streams);
@@ -881,6 +939,7 @@ AF_API void af_batch_destroy(af_batch *b)
     for (auto &s : b->slots) {
         if (s.d_in) cudaFree(s.d_in);
         if (s.d_pcm) cudaFree(s.d_pcm);
+        if (s.d_pcm16) cudaFree(s.d_pcm16);
         if (s.d_logmel) cudaFree(s.d_logmel);
         if (s.d_vad) cudaFree(s.d_vad);
         if (s.d_energy) cudaFree(s.d_energy);
@@ -896,9 +955,29 @@ AF_API int af_batch_create(af_pipeline *p, const af_stream_desc *streams, size_t
     if (mem != AF_MEM_DEVICE && mem != AF_MEM_HOST) return fail(AF_ERR_INVALID, "bad memory kind %d", mem);
     int rc = require_ctx();
     if (rc) return rc;
+    // device batches run on the GPU that holds their input (every stream must live on the same one); host batches on
+    // the calling thread's device
+    int device = cur_device();
+    if (mem == AF_MEM_DEVICE) {
+        int owner = -1;
+        for (size_t i = 0; i < n_streams; ++i) {
+            if (!streams[i].data) continue;
+            const int d = device_of_pointer(streams[i].data);
+            if (d < 0) continue;
+            if (owner < 0) owner = d;
+            else if (owner != d) return fail(AF_ERR_INVALID, "stream %zu lives on GPU %d, stream(s) before it on GPU %d: one batch, one GPU (see af_sharded_batch_create)", i, d, owner);
+        }
+        if (owner >= 0) {
+            rc = init_device(owner);
+            if (rc) return rc;
+            device = owner;
+        }
+    }
+    AF_SCOPE(device);
     // (af_batch_destroy frees the slots, tables and streams allocated so far on every early return)
     std::unique_ptr<af_batch, void (*)(af_batch *)> b(new af_batch, af_batch_destroy);
-    b->pipe = p; b->mem = mem;
+    b->pipe = p; b->mem = mem; b->device = device;
+    if (p->cfg.n_mels && !(b->d_mel = pipe_mel(p))) return AF_ERR_CUDA;
     b->streams.resize(n_streams);
     const af_pipeline_config &cfg = p->cfg;
     for (size_t i = 0; i < n_streams; ++i) {
@@ -968,6 +1047,7 @@ AF_API int af_batch_create(af_pipeline *p, const af_stream_desc *streams, size_t
             AF_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
             AF_CUDA(cudaMalloc(&s.d_in, std::max<size_t>(max_in, 256)));
             AF_CUDA(cudaMalloc(&s.d_pcm, std::max<size_t>(max_rows * b->pcm_stride * sizeof(float), 256)));
+            if (cfg.pcm16) AF_CUDA(cudaMalloc(&s.d_pcm16, std::max<size_t>(max_rows * b->pcm_stride * sizeof(int16_t), 256)));
             if (cfg.n_mels) AF_CUDA(cudaMalloc(&s.d_logmel, std::max<size_t>(max_rows * b->logmel_stride * sizeof(float), 256)));
             if (cfg.vad_enable) {
                 AF_CUDA(cudaMalloc(&s.d_vad, std::max<size_t>(max_rows * b->vad_stride, 256)));
@@ -1019,15 +1099,43 @@ static int check_outputs(const af_batch *b, const af_outputs *o)
     return AF_OK;
 }
 
-AF_API int af_batch_run(af_batch *b, const af_outputs *o, void *cuda_stream)
+}  // extern "C"
+
+namespace afrt {
+
+int batch_device(const af_batch *b) { return b ? b->device : -1; }
+int batch_check_outputs(const af_batch *b, const af_outputs *o) { return check_outputs(b, o); }
+const af_pipeline_config &pipeline_cfg(const af_pipeline *p) { return p->cfg; }
+
+// the counts af_batch_create derives for one stream, without creating anything on a device (a rank plans the streams of
+// the other ranks this way: every rank knows every row of the gathered result)
+int plan_stream_counts(const af_pipeline_config &cfg, const af_stream_desc &d, uint32_t *n_out_, uint32_t *n_frames_, uint32_t *n_vad_)
 {
-    if (!b) return fail(AF_ERR_INVALID, "null batch");
-    if (b->mem != AF_MEM_DEVICE) return fail(AF_ERR_INVALID, "batch was planned for host buffers; use af_batch_run_host");
-    int rc = check_outputs(b, o);
+    if (d.channels == 0) return fail(AF_ERR_INVALID, "channels must be >= 1");
+    const uint64_t n_in = (d.n_samples + d.channels - 1) / d.channels;
+    if (n_in >= (1ull << 31)) return fail(AF_ERR_INVALID, "stream too long (%llu frames)", (unsigned long long)n_in);
+    uint64_t n_out = 0; uint32_t mode, p, q;
+    int rc = plan_rate(d.sample_rate, OUT_RATE, n_in, &n_out, &mode, &p, &q, nullptr);
     if (rc) return rc;
+    if (n_out >= (1ull << 31)) return fail(AF_ERR_INVALID, "output too long");
+    const uint32_t n_frames = n_out >= WIN ? (uint32_t)(1 + (n_out - WIN) / HOP) : 0;
+    uint32_t n_vad = 0;
+    if (!cfg.vad_enable) n_vad = 0;
+    else if (cfg.vad_frame_len == 0) n_vad = n_frames;
+    else n_vad = n_out >= cfg.vad_frame_len ? (uint32_t)(1 + (n_out - cfg.vad_frame_len) / cfg.vad_hop) : 0;
+    if (n_out_) *n_out_ = (uint32_t)n_out;
+    if (n_frames_) *n_frames_ = n_frames;
+    if (n_vad_) *n_vad_ = n_vad;
+    return AF_OK;
+}
+uint64_t batch_max_vad(const af_batch *b) { return b ? b->max_vad : 0; }
+
+// the body of af_batch_run: enqueues on `st` (the batch's device must be current), never synchronises; the VAD states
+// go to `vad` / `vad_stride`, which the sharded batches point into their gather buffer
+int batch_run_on(af_batch *b, const af_outputs *o, uint8_t *vad, uint64_t vad_stride, cudaStream_t st)
+{
     if (b->streams.empty()) return AF_OK;
     const af_pipeline_config &cfg = b->pipe->cfg;
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_ctx.stream;
     const size_t S = b->streams.size();
     float *energy = o->energy; uint64_t energy_stride = o->energy_stride;
     if (cfg.vad_enable && !energy) {
@@ -1035,12 +1143,35 @@ AF_API int af_batch_run(af_batch *b, const af_outputs *o, void *cuda_stream)
         energy = b->d_energy; energy_stride = b->energy_stride;
     }
     float *pcm = cfg.write_pcm ? o->pcm : nullptr; uint64_t pcm_stride = o->pcm_stride;
-    if (cfg.vad_enable && cfg.vad_frame_len != 0 && !pcm) {      // custom VAD frames read the PCM back
+    const bool wire16 = cfg.pcm16 && pcm;                        // PCM leaves as i16 wire samples: f32 rows stay internal
+    if (wire16) pcm = nullptr;
+    if ((wire16 || (cfg.vad_enable && cfg.vad_frame_len != 0)) && !pcm) {      // custom VAD frames read the PCM back
         if (!b->d_pcm_scratch) AF_CUDA(cudaMalloc(&b->d_pcm_scratch, std::max<size_t>(S * b->pcm_stride * sizeof(float), 256)));
         pcm = b->d_pcm_scratch; pcm_stride = b->pcm_stride;
     }
-    rc = run_sub(b, b->subs[0], pcm, pcm_stride, o->logmel, o->logmel_stride, o->vad, o->vad_stride, energy,
-                 energy_stride, reinterpret_cast<VadState *>(o->vad_final), st);
+    int rc = run_sub(b, b->subs[0], pcm, pcm_stride, o->logmel, o->logmel_stride, vad, vad_stride, energy, energy_stride,
+                     reinterpret_cast<VadState *>(o->vad_final), st);
+    if (rc) return rc;
+    if (wire16) {                                                // websocket.rs:246-251 on the rows, 2 bytes per sample out
+        AF_CUDA(launch_pcm16_rows(pcm, pcm_stride, reinterpret_cast<int16_t *>(o->pcm), o->pcm_stride, (uint32_t)b->max_out, (uint32_t)S, st));
+        count_launch();
+    }
+    return AF_OK;
+}
+
+}  // namespace afrt
+
+extern "C" {
+
+AF_API int af_batch_run(af_batch *b, const af_outputs *o, void *cuda_stream)
+{
+    if (!b) return fail(AF_ERR_INVALID, "null batch");
+    if (b->mem != AF_MEM_DEVICE) return fail(AF_ERR_INVALID, "batch was planned for host buffers; use af_batch_run_host");
+    int rc = check_outputs(b, o);
+    if (rc) return rc;
+    AF_SCOPE(b->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : cur_ctx().stream;
+    rc = batch_run_on(b, o, o->vad, o->vad_stride, st);
     if (rc) return rc;
     if (!cuda_stream) AF_CUDA(cudaStreamSynchronize(st));
     return AF_OK;
@@ -1052,6 +1183,7 @@ AF_API int af_batch_run_host(af_batch *b, const af_outputs *o)
     if (b->mem != AF_MEM_HOST) return fail(AF_ERR_INVALID, "batch was planned for device buffers; use af_batch_run");
     int rc = check_outputs(b, o);
     if (rc) return rc;
+    AF_SCOPE(b->device);
     const af_pipeline_config &cfg = b->pipe->cfg;
     const size_t n_slots = b->slots.size();
     for (size_t g = 0; g < b->subs.size(); ++g) {
@@ -1077,7 +1209,14 @@ AF_API int af_batch_run_host(af_batch *b, const af_outputs *o)
                      b->vad_stride, sl.d_energy, b->energy_stride, sl.d_final, st);
         if (rc) return rc;
         const size_t r0 = sb.first;
-        if (cfg.write_pcm && o->pcm)
+        if (cfg.write_pcm && o->pcm && cfg.pcm16) {
+            AF_CUDA(launch_pcm16_rows(sl.d_pcm, b->pcm_stride, sl.d_pcm16, b->pcm_stride, (uint32_t)b->max_out, (uint32_t)sb.count, st));
+            count_launch();
+            int16_t *dst = reinterpret_cast<int16_t *>(o->pcm);
+            AF_CUDA(cudaMemcpy2DAsync(dst + r0 * o->pcm_stride, o->pcm_stride * sizeof(int16_t), sl.d_pcm16,
+                                      b->pcm_stride * sizeof(int16_t), b->max_out * sizeof(int16_t), sb.count,
+                                      cudaMemcpyDeviceToHost, st));
+        } else if (cfg.write_pcm && o->pcm)
             AF_CUDA(cudaMemcpy2DAsync(o->pcm + r0 * o->pcm_stride, o->pcm_stride * sizeof(float), sl.d_pcm,
                                       b->pcm_stride * sizeof(float), b->max_out * sizeof(float), sb.count,
                                       cudaMemcpyDeviceToHost, st));
@@ -1133,6 +1272,8 @@ AF_API size_t af_debug_resample_plan(uint32_t input_rate, uint32_t output_rate, 
 // ------------------------------------------------------------------------------------------
 struct af_session {
     af_pipeline *pipe = nullptr;
+    int device = -1;                  // the GPU that holds the session state
+    MelTables *d_mel = nullptr;
     size_t S = 0;
     uint32_t rate = 0, channels = 1, format = 0, max_tick_frames = 0;
     RsRecurrence rec;                 // shared by every stream (same number of frames pushed to all)
@@ -1178,6 +1319,7 @@ extern "C" {
 AF_API void af_session_destroy(af_session *s)
 {
     if (!s) return;
+    DevScope scope_(s->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < 2; ++i) {
         if (s->in_buf[i]) cudaFree(s->in_buf[i]);
@@ -1203,6 +1345,7 @@ AF_API void af_session_destroy(af_session *s)
 AF_API int af_session_reset(af_session *s)
 {
     if (!s) return fail(AF_ERR_INVALID, "null session");
+    AF_SCOPE(s->device);
     s->rec.init(s->rate, OUT_RATE);
     s->in_cur = 0; s->y_cur = 0; s->y_len = 0; s->frames_emitted = 0; s->in_drop = 0; s->y_drop = 0;
     s->in_len = 2 * RS_POLY;                       // rubato starts with 16 zero frames of history
@@ -1223,7 +1366,10 @@ AF_API int af_session_create(af_pipeline *p, size_t n_streams, uint32_t sample_r
     const af_pipeline_config &cfg = p->cfg;
     if (cfg.n_mels && cfg.vad_enable && cfg.vad_frame_len != 0 && (cfg.vad_frame_len != WIN || cfg.vad_hop != HOP))
         return fail(AF_ERR_INVALID, "sessions need the VAD on the STFT frames when features are enabled");
+    if (cfg.pcm16) return fail(AF_ERR_INVALID, "sessions deliver f32 PCM (pcm16 is a batch option; af_pcm16_encode converts a tick)");
     std::unique_ptr<af_session, void (*)(af_session *)> s(new af_session, af_session_destroy);
+    s->device = cur_device();
+    if (p->cfg.n_mels && !(s->d_mel = pipe_mel(p))) return AF_ERR_CUDA;
     s->pipe = p; s->S = n_streams; s->rate = sample_rate; s->channels = channels; s->format = format;
     s->max_tick_frames = (max_tick_samples + channels - 1) / channels;
     s->rec.init(sample_rate, OUT_RATE);
@@ -1302,8 +1448,9 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
     const uint32_t n_new = n_samples / s->channels;
     if (n_new > s->max_tick_frames) return fail(AF_ERR_CAPACITY, "tick of %u frames exceeds max_tick_samples", n_new);
     if (in_stride < n_samples) return fail(AF_ERR_INVALID, "in_stride smaller than n_samples");
+    AF_SCOPE(s->device);
     const af_pipeline_config &cfg = s->pipe->cfg;
-    cudaStream_t st = g_ctx.stream;
+    cudaStream_t st = cur_ctx().stream;
     const size_t S = s->S;
     const uint32_t bps = s->format == AF_FMT_I16 ? 2 : 4;
     af_outputs none{};
@@ -1437,7 +1584,7 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
                 AF_CUDA(launch_session_setup(s->d_tab[s->y_cur], s->d_tiles, (uint32_t)S, y_total, T, cfg.vad_enable ? T : 0, st));
                 P.streams = s->d_tab[s->y_cur]; P.tiles = s->d_tiles; P.n_tiles = (uint32_t)S;
             }
-            P.fft = g_ctx.d_fft; P.mel = s->pipe->d_mel;
+            P.fft = cur_ctx().d_fft; P.mel = s->d_mel;
             P.pcm = nullptr; P.pcm_stride = 0;
             P.logmel = lm; P.logmel_stride = lm_stride * vrows;
             P.energy = cfg.vad_enable ? s->d_energy : nullptr; P.energy_stride = s->energy_stride * vrows;
@@ -1445,10 +1592,10 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
             P.do_energy = cfg.vad_enable ? 1 : 0;
             P.log_floor = cfg.log_floor;
             P.log_scale = cfg.log10 ? 0.30102999566398120f : 0.69314718055994531f;
-            P.use_stage = g_ctx.variant == "sync" ? 0u : 1u;
+            P.use_stage = kernel_variant() == "sync" ? 0u : 1u;
             P.layout = fused_layout(P.do_energy != 0);
             if (P.n_mels || P.do_energy) {
-                AF_CUDA(launch_fused(P, (int)std::min<size_t>(P.n_tiles, (size_t)g_ctx.sm_count), st));
+                AF_CUDA(launch_fused(P, (int)std::min<size_t>(P.n_tiles, (size_t)cur_ctx().sm_count), st));
                 count_launch(2);
             }
         } else {
@@ -1520,6 +1667,7 @@ extern "C" {
 AF_API int af_session_enable_levels(af_session *s, int enable)
 {
     if (!s) return fail(AF_ERR_INVALID, "null session");
+    AF_SCOPE(s->device);
     if (enable && !s->d_peak) {
         AF_CUDA(cudaMalloc(&s->d_peak, s->S * sizeof(float)));
         AF_CUDA(cudaHostAlloc((void **)&s->h_peak, s->S * sizeof(float), cudaHostAllocDefault));
@@ -1578,7 +1726,7 @@ AF_API int af_ring_create(size_t capacity_samples, af_ring **out)
     r->capacity = capacity_samples;
     // pinned when a device is bound (the session copies straight out of it), plain memory otherwise: the ring is a
     // host container, not a compute path
-    if (g_ctx.ready && cudaHostAlloc((void **)&r->buf, capacity_samples * sizeof(float), cudaHostAllocDefault) == cudaSuccess) r->pinned = true;
+    if (cur_device() >= 0 && cur_ctx().ready && cudaHostAlloc((void **)&r->buf, capacity_samples * sizeof(float), cudaHostAllocPortable) == cudaSuccess) r->pinned = true;
     else {
         cudaGetLastError();
         r->buf = static_cast<float *>(malloc(capacity_samples * sizeof(float)));

@@ -44,7 +44,16 @@ typedef enum af_status {
 } af_status;
 
 /* ---- library ------------------------------------------------------------------------- */
-AF_API int af_init(int device);                 /* binds the calling process to one GPU */
+#define AF_MAX_GPUS 16
+/* Selects GPU `device` for the calling THREAD, initialising the library's context on it at first use (device < 0:
+ * keep the thread's selection / the process default).  A process may use several GPUs: objects remember the GPU they
+ * were created on and every call that takes a handle runs there, whatever the calling thread has selected. */
+AF_API int af_init(int device);
+AF_API int af_current_device(void);             /* the calling thread's GPU, -1 before any af_init */
+/* Makes `cuda_stream` (a cudaStream_t) the stream the library enqueues on for the calling thread's GPU wherever an
+ * entry point has no stream argument of its own (sessions, sharded batches, the NULL-stream form of af_batch_run);
+ * NULL restores the library's own non-blocking stream.  The caller keeps the stream alive. */
+AF_API int af_set_stream(void *cuda_stream);
 AF_API int af_shutdown(void);
 AF_API size_t af_last_error(char *buf, size_t cap);   /* returns strlen of the full message */
 AF_API int af_device_count(int *count);
@@ -146,6 +155,9 @@ typedef struct af_pipeline_config {
     uint32_t vad_frame_len;   /* 0 -> the STFT frames (400 / 160); else e.g. 320 / 320 (20 ms) */
     uint32_t vad_hop;
     uint32_t write_pcm;       /* write the resampled 16 kHz PCM */
+    uint32_t pcm16;           /* batch runs: deliver the PCM as i16 wire samples, (x.clamp(-1,1) * 32767) as i16
+                               * (websocket.rs:246-251): af_outputs.pcm then points at int16_t rows and pcm_stride counts
+                               * int16_t elements (still a multiple of 4).  Halves the PCM bytes that leave the GPU. */
 } af_pipeline_config;
 
 AF_API void af_pipeline_config_default(af_pipeline_config *cfg);
@@ -243,6 +255,59 @@ typedef struct af_gate_outputs {
 AF_API int af_vad_gate(const float *pcm, uint64_t pcm_stride, const float *logmel, uint64_t logmel_stride, uint32_t n_mels,
                        const uint32_t *n_out, uint32_t hop, const uint32_t *seg, uint32_t seg_cap, const uint32_t *n_seg,
                        size_t n_streams, const af_gate_outputs *out, void *cuda_stream);
+
+/* ======================================================================================= */
+/* Multi-GPU: independent streams sharded over the GPUs of one box, results gathered with NCCL  */
+/* (SURVEY 8(e)).  Streams never talk to each other, so the data path has NO collective; the only */
+/* exchange is the gather of the per-stream VAD states to every GPU, issued on a side stream so    */
+/* that the next batch never waits for it.  Two ways to form the communicator:                     */
+/*   - af_init_multi(n): ONE process (e.g. the Rust host) drives GPUs 0..n-1 (ncclCommInitAll);    */
+/*   - one process per GPU: af_init(local_gpu), rank 0 calls af_comm_unique_id, the host ships the  */
+/*     128 bytes to the other ranks by any channel, every rank calls af_comm_init_rank.             */
+/* NCCL is loaded at run time (libnccl.so.2); single-GPU use never touches it.                      */
+/* ======================================================================================= */
+AF_API int af_init_multi(int n_gpus);
+AF_API int af_comm_unique_id(uint8_t id[128]);
+AF_API int af_comm_init_rank(int n_ranks, int rank, const uint8_t id[128]);
+AF_API int af_comm_size(void);                  /* ranks of the communicator, 0 when there is none */
+AF_API int af_comm_shutdown(void);
+/* Contiguous blocks of stream indices, balanced by input BYTES (44.1 kHz and 48 kHz streams differ by 8 %):
+ * shard r owns streams [first[r], first[r + 1]); first has n_shards + 1 entries.  Pure host code. */
+AF_API int af_shard_partition(const af_stream_desc *streams, size_t n_streams, int n_shards, size_t *first);
+
+typedef struct af_sharded_batch af_sharded_batch;
+typedef struct af_sharded_outputs {             /* per rank; only the entries of this process's ranks are read */
+    af_outputs shard[AF_MAX_GPUS];              /* device pointers on the rank's GPU, rows = the rank's streams */
+} af_sharded_outputs;
+/* Plans n_streams GLOBAL streams over the communicator's ranks (af_shard_partition) and builds the batches of the
+ * ranks this process owns (all of them after af_init_multi, one after af_comm_init_rank).  Every process passes the
+ * same descriptor list; the `data` of streams owned elsewhere is not used (may be NULL).  mem as in af_batch_create;
+ * AF_MEM_DEVICE data must live on the owner's GPU. */
+AF_API int af_sharded_batch_create(af_pipeline *p, const af_stream_desc *streams, size_t n_streams, int mem,
+                                   af_sharded_batch **out);
+AF_API void af_sharded_batch_destroy(af_sharded_batch *b);
+/* rank r owns streams [*first, *first + *count); *device = its GPU when this process owns the rank, else -1 */
+AF_API int af_sharded_batch_shard(const af_sharded_batch *b, int rank, size_t *first, size_t *count, int *device);
+AF_API af_batch *af_sharded_batch_local(af_sharded_batch *b, int rank);   /* the rank's ordinary batch (counts, strides); NULL if remote */
+/* Runs every local shard on its GPU (all GPUs concurrently, nothing blocks in between).  gather != 0: the VAD kernel
+ * of each shard writes its states straight into the rank's slot of a double-buffered gather buffer and ONE in-place
+ * ncclAllGather per GPU follows on the side stream; shard[r].vad is then ignored.  async == 0: returns when every GPU
+ * (and the gather) is done; else af_sharded_batch_wait does that. */
+AF_API int af_sharded_batch_run(af_sharded_batch *b, const af_sharded_outputs *out, int gather, int async);
+AF_API int af_sharded_batch_wait(af_sharded_batch *b);
+/* The gathered states of the LAST run on a local rank's GPU: row (r * rows_per_rank + i) holds stream i of rank r,
+ * n_vad_frames[global stream] of them valid (host array of n_streams, may be NULL).  The buffer is reused by the run
+ * after the next one. */
+AF_API int af_sharded_batch_gathered(af_sharded_batch *b, int rank, const uint8_t **states, uint64_t *row_stride,
+                                     uint64_t *rows_per_rank, uint32_t *n_vad_frames);
+/* The same result on the host, in GLOBAL stream order: states[n_streams][stride] (stride >= the longest stream's
+ * frame count).  Waits for the gather. */
+AF_API int af_sharded_batch_gathered_host(af_sharded_batch *b, int rank, uint8_t *states, uint64_t stride);
+/* Device time of the last gather on a local rank (side stream, event to event), milliseconds. */
+AF_API int af_sharded_batch_gather_ms(af_sharded_batch *b, int rank, float *ms);
+/* Host-buffer form (mem == AF_MEM_HOST): `out` holds rows for ALL n_streams streams in host memory; every local shard
+ * runs af_batch_run_host on its GPU from its own host thread, writing its rows.  Blocking. */
+AF_API int af_sharded_batch_run_host(af_sharded_batch *b, const af_outputs *out);
 
 /* ---- host-side planning diagnostics (no GPU needed; used by the CPU test-suite) ---------- */
 /* smallest f32 energy e with 20*log10f(e) > threshold_db under the host libm (NaN if none):

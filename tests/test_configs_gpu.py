@@ -373,3 +373,37 @@ def test_many_cta_scan_timeout_zero(af, orc, timeout, min_speech):
     assert_bit_equal(got["vad"], ref["vad"], f"timeout {timeout}")
     assert got["vad_final"]["state"] == ref["vad_final"]["state"]
     assert got["vad_final"]["speech_frames"] == ref["vad_final"]["speech_frames"]
+
+
+def test_pcm16_wire_output_host_and_device(af, orc):
+    """af_pipeline_config.pcm16: the batch delivers (x.clamp(-1,1) * 32767) as i16 (websocket.rs:246-251) instead of f32 --
+    host-buffer and device-buffer runs, mixed rates / formats / ragged lengths, against the oracle's encode of the oracle's PCM."""
+    import torch
+    from audioflow import synth
+    specs = [(610, 2.3, 48000, 1, "f32"), (611, 1.9, 44100, 2, "f32"), (612, 1.1, 48000, 1, "i16"), (613, 0.0, 48000, 1, "f32"), (614, 3.7, 32000, 1, "f32")]
+    streams = [(synth.stream(i, sec, rate, ch, fmt), rate, ch) for (i, sec, rate, ch, fmt) in specs]
+    streams[0][0][100:140] = np.array([1.5, -1.5, np.nan, 1.0, -1.0] * 8, np.float32)        # clamp / NaN / full scale
+    pipe = af.Pipeline(af.pipeline_config(n_mels=80, pcm16=True))
+    got = pipe.run_host(streams)
+    refs = []
+    for (x, rate, ch), g in zip(streams, got):
+        fmt = "i16" if x.dtype == np.int16 else "f32"
+        ref = orc.pipeline_stream(x, ch, rate, orc.default_feat_config(80), orc.default_vad_config(), 400, 160, fmt)
+        refs.append(ref)
+        assert g["pcm"].dtype == np.int16
+        assert np.array_equal(g["pcm"], orc.pcm16_encode(ref["pcm"])), "host pcm16"
+        assert_bit_equal(g["vad"], ref["vad"], "vad with pcm16")
+        assert_logmel_close(g["logmel"], ref["logmel"], "logmel with pcm16")
+    # device buffers
+    dev = torch.device("cuda")
+    keep = [torch.tensor(x.astype(np.float32) if x.dtype != np.int16 else x, device=dev) if len(x) else torch.zeros(4, device=dev) for (x, _, _) in streams]
+    descs = [(t.data_ptr(), len(x), rate, ch, af.AF_FMT_I16 if x.dtype == np.int16 else af.AF_FMT_F32) for t, (x, rate, ch) in zip(keep, streams)]
+    b = pipe.batch(descs, af.AF_MEM_DEVICE)
+    S = len(streams)
+    pcm = torch.full((S, b.pcm_stride), -7, device=dev, dtype=torch.int16)
+    torch.cuda.synchronize()
+    b.run_device(b.outputs_struct(pcm.data_ptr(), b.pcm_stride))
+    torch.cuda.synchronize()
+    for i, ref in enumerate(refs):
+        n = int(b.n_out[i])
+        assert np.array_equal(pcm[i, :n].cpu().numpy(), orc.pcm16_encode(ref["pcm"])), f"device pcm16 {i}"

@@ -68,3 +68,22 @@ def test_gather_world2_gloo():
             assert (st[i, : i + 1] == i % 3).all() and (st[i, i + 1:] == 0).all()
     parts = sorted(r[1] for r in res)
     assert parts[0][0] == 0 and parts[0][1] == parts[1][0] and parts[1][1] == 7
+
+
+def test_c_abi_partition_matches_helper_and_balances():
+    """af_shard_partition (pure host code behind the C ABI: what af_sharded_batch_create uses) against the Python helper:
+    contiguous, covering, byte-balanced (44.1 kHz and 48 kHz streams differ by 8 %), i16 streams cost half."""
+    import audioflow as af
+    from audioflow import shard
+    descs = [(0, 1440000 if i % 2 == 0 else 1323000, 48000 if i % 2 == 0 else 44100, 1, af.AF_FMT_F32) for i in range(4096)]
+    costs = [d[1] * 4 for d in descs]
+    for world in (1, 2, 3, 4, 8, 16):
+        parts = af.shard_partition(descs, world)
+        assert parts == shard.partition(costs, world)
+        assert parts[0][0] == 0 and parts[-1][1] == 4096 and all(parts[r][1] == parts[r + 1][0] for r in range(world - 1))
+        loads = [sum(costs[a:b]) for a, b in parts]
+        assert max(loads) / (sum(costs) / world) < 1.002
+    mixed = [(0, 1000, 48000, 1, af.AF_FMT_I16)] * 4 + [(0, 1000, 48000, 1, af.AF_FMT_F32)] * 2      # 4 x 2000 B, 2 x 4000 B
+    assert af.shard_partition(mixed, 2) == [(0, 4), (4, 6)]
+    assert af.shard_partition([(0, 100, 1, 1, 0)] + [(0, 1, 1, 1, 0)] * 5, 2) == [(0, 1), (1, 6)]
+    assert af.shard_partition([], 2) == [(0, 0), (0, 0)]
