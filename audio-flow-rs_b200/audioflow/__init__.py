@@ -142,7 +142,7 @@ def load_library():
         "af_sharded_batch_shard": (C.c_int, [vp, C.c_int, szp, szp, C.POINTER(C.c_int)]),
         "af_sharded_batch_local": (vp, [vp, C.c_int]),
         "af_sharded_batch_run": (C.c_int, [vp, C.POINTER(ShardedOutputsC), C.c_int, C.c_int]),
-        "af_sharded_batch_wait": (C.c_int, [vp]),
+        "af_sharded_batch_wait": (C.c_int, [vp]), "af_sharded_batch_join": (C.c_int, [vp]),
         "af_sharded_batch_gathered": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                                 C.POINTER(C.c_uint32)]),
         "af_sharded_batch_gathered_host": (C.c_int, [vp, C.c_int, u8p, C.c_uint64]),
@@ -592,6 +592,9 @@ class ShardedBatch:
 
     def wait(self):
         _check(load_library().af_sharded_batch_wait(self._h))
+
+    def join(self):
+        _check(load_library().af_sharded_batch_join(self._h))
 
     def gathered(self, rank: int):
         """(device pointer, row stride, rows per rank, n_vad_frames[n]) of the last gather on a local rank's GPU."""

@@ -39,10 +39,13 @@ std::mutex g_comm_mu;
 int load_nccl()
 {
     if (g_nccl.handle) return AF_OK;
+    // A copy the process already carries wins (PyTorch bundles its own libnccl.so.2: a process that uses both must
+    // import torch BEFORE the first multi-GPU call, or torch would be handed the system library instead of its own).
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     void *h = nullptr;
     for (const char *n : names) {
-        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        h = dlopen(n, RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
         if (h) break;
     }
     if (!h) return fail(AF_ERR_NO_DEVICE, "NCCL is not available (%s): the multi-GPU entry points need libnccl.so.2", dlerror());
@@ -335,6 +338,18 @@ AF_API int af_sharded_batch_wait(af_sharded_batch *b)
         AF_SCOPE(b->devices[li]);
         AF_CUDA(cudaStreamSynchronize(cur_ctx().stream));
         AF_CUDA(cudaStreamSynchronize(cur_ctx().side));
+    }
+    return AF_OK;
+}
+
+AF_API int af_sharded_batch_join(af_sharded_batch *b)
+{
+    if (!b) return fail(AF_ERR_INVALID, "null batch");
+    if (b->last_parity < 0) return AF_OK;
+    for (size_t li = 0; li < b->local.size(); ++li) {
+        if (!b->gathered_once[b->last_parity][li]) continue;
+        AF_SCOPE(b->devices[li]);
+        AF_CUDA(cudaStreamWaitEvent(cur_ctx().stream, b->ev_gather_end[b->last_parity][li], 0));
     }
     return AF_OK;
 }

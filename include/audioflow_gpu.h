@@ -295,6 +295,9 @@ AF_API af_batch *af_sharded_batch_local(af_sharded_batch *b, int rank);   /* the
  * (and the gather) is done; else af_sharded_batch_wait does that. */
 AF_API int af_sharded_batch_run(af_sharded_batch *b, const af_sharded_outputs *out, int gather, int async);
 AF_API int af_sharded_batch_wait(af_sharded_batch *b);
+/* Orders the compute stream of every local GPU after the last gather WITHOUT blocking the host: work (or an event)
+ * enqueued afterwards sees the gathered states. */
+AF_API int af_sharded_batch_join(af_sharded_batch *b);
 /* The gathered states of the LAST run on a local rank's GPU: row (r * rows_per_rank + i) holds stream i of rank r,
  * n_vad_frames[global stream] of them valid (host array of n_streams, may be NULL).  The buffer is reused by the run
  * after the next one. */

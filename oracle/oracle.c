@@ -752,3 +752,73 @@ ORC_API size_t orc_pipeline_stream(const float *in, size_t n_samples, unsigned c
     if (n_frames_out) *n_frames_out = T;
     return ny;
 }
+
+/* ------------------------------------------------------------------------- */
+/* The same stages driven the way the reference's processing loop would drive   */
+/* them (specs/0002-design.md:1113-1118: every ~100 ms read what the ring holds, */
+/* to_mono, BatchResampler::process, detect per 20 ms frame), INCLUDING the      */
+/* allocations and copies the Rust code performs: `samples.to_vec()` per read    */
+/* (capture.rs:134-141), a fresh mono Vec (capture.rs:34-40), `buffer.extend`,   */
+/* per 128-frame chunk `buffer[..128].to_vec()`, rubato's Vec<Vec<f32>> result,   */
+/* `output.extend` and `buffer.drain(..128)` -- a memmove of the whole residual   */
+/* (resampler.rs:132-147).  Timing row "reference-shaped" of bench.py; the        */
+/* numbers it produces are identical to orc_pipeline_stream's.                    */
+/* ------------------------------------------------------------------------- */
+ORC_API size_t orc_pipeline_stream_shaped(const float *in, size_t n_samples, unsigned channels, uint32_t in_rate,
+                                          size_t read_frames, const orc_vad_config *vc, uint32_t vad_len,
+                                          float *pcm_out, size_t pcm_cap, uint8_t *vad_out, size_t *n_frames_out)
+{
+    orc_resampler *rs = orc_resampler_new(in_rate, 16000);
+    orc_vad v;
+    memset(&v, 0, sizeof(v));
+    if (vc) v.cfg = *vc;
+    float *buffer = NULL; size_t blen = 0, bcap = 0;          /* BatchResampler::buffer */
+    float *pending = NULL; size_t plen = 0, pcap = 0;         /* 16 kHz samples waiting for a full VAD frame */
+    size_t ny = 0, T = 0;
+    const size_t per_read = read_frames * channels;
+    for (size_t pos = 0; pos < n_samples; pos += per_read) {
+        const size_t n = n_samples - pos < per_read ? n_samples - pos : per_read;
+        float *frame = (float *)malloc((n ? n : 1) * sizeof(float));          /* RingBuffer::read -> Vec */
+        memcpy(frame, in + pos, n * sizeof(float));
+        float *mono = (float *)malloc((n / channels + 1) * sizeof(float));    /* to_mono -> new Vec */
+        const size_t nm = orc_to_mono(frame, n, channels, mono);
+        if (blen + nm > bcap) { bcap = (blen + nm) * 2 + CHUNK; buffer = (float *)realloc(buffer, bcap * sizeof(float)); }
+        memcpy(buffer + blen, mono, nm * sizeof(float));                      /* buffer.extend_from_slice */
+        blen += nm;
+        float *output = NULL; size_t olen = 0, ocap = 0;                      /* let mut output = Vec::new() */
+        while (!rs->passthrough && blen >= CHUNK) {
+            float *chunk = (float *)malloc(CHUNK * sizeof(float));            /* buffer[..128].to_vec() */
+            memcpy(chunk, buffer, CHUNK * sizeof(float));
+            float *res = (float *)malloc(max_out_per_chunk(rs) * sizeof(float));   /* rubato's Vec<Vec<f32>> */
+            const size_t m = fastfixedin_step(rs, chunk, res, NULL);
+            if (olen + m > ocap) { ocap = (olen + m) * 2 + 64; output = (float *)realloc(output, ocap * sizeof(float)); }
+            memcpy(output + olen, res, m * sizeof(float));                    /* output.extend(processed) */
+            olen += m;
+            free(res); free(chunk);
+            memmove(buffer, buffer + CHUNK, (blen - CHUNK) * sizeof(float));  /* buffer.drain(..128) */
+            blen -= CHUNK;
+        }
+        if (rs->passthrough) { output = (float *)malloc((blen ? blen : 1) * sizeof(float)); memcpy(output, buffer, blen * sizeof(float)); olen = blen; blen = 0; }
+        if (ny + olen <= pcm_cap) memcpy(pcm_out + ny, output, olen * sizeof(float));
+        ny += olen;
+        if (vc && vad_len) {
+            if (plen + olen > pcap) { pcap = (plen + olen) * 2 + vad_len; pending = (float *)realloc(pending, pcap * sizeof(float)); }
+            memcpy(pending + plen, output, olen * sizeof(float));
+            plen += olen;
+            size_t used = 0;
+            while (plen - used >= vad_len) {
+                const int st = orc_vad_detect(&v, pending + used, vad_len);
+                if (vad_out) vad_out[T] = (uint8_t)st;
+                ++T;
+                used += vad_len;
+            }
+            memmove(pending, pending + used, (plen - used) * sizeof(float));
+            plen -= used;
+        }
+        free(output); free(mono); free(frame);
+    }
+    free(buffer); free(pending);
+    orc_resampler_free(rs);
+    if (n_frames_out) *n_frames_out = T;
+    return ny;
+}

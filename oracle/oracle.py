@@ -112,6 +112,9 @@ def lib():
     L.orc_pipeline_stream.restype = sz
     L.orc_pipeline_stream.argtypes = [fp, sz, C.c_uint, C.c_uint32, C.c_void_p, C.POINTER(VadConfig),
                                       C.c_uint32, C.c_uint32, fp, fp, sz, fp, u8p, C.POINTER(sz)]
+    L.orc_pipeline_stream_shaped.restype = sz
+    L.orc_pipeline_stream_shaped.argtypes = [fp, sz, C.c_uint, C.c_uint32, sz, C.POINTER(VadConfig), C.c_uint32, fp, sz, u8p,
+                                             C.POINTER(sz)]
     _lib = L
     return L
 

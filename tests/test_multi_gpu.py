@@ -106,6 +106,7 @@ def test_single_process_two_gpus_sharded_batch_with_gather(af, orc):
 
 def _rank_worker(rank, world, uid_q, res_q):
     sys.path[:0] = [os.path.join(ROOT, "audio-flow-rs_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    import torch          # (used for device memory only) BEFORE the library binds NCCL: torch must find its own bundled libnccl.so.2
     import audioflow as af
     try:
         af.init(rank)                                  # one process per GPU
@@ -120,9 +121,7 @@ def _rank_worker(rank, world, uid_q, res_q):
         geo = [(0, len(x), rate, 1, af.AF_FMT_F32) for (x, rate) in xs]
         lo, hi = af.shard_partition(geo, world)[rank]
         L = af.load_library()
-        # device copies of this rank's streams only (cudaMalloc through the runtime the library links: ctypes on cudart via torch is not needed)
-        import torch
-        d = torch.device("cuda", rank)
+        d = torch.device("cuda", rank)                 # device copies of this rank's streams only
         dx = {i: torch.tensor(xs[i][0], device=d) for i in range(lo, hi)}
         descs = [(dx[i].data_ptr() if lo <= i < hi else 0, len(x), rate, 1, af.AF_FMT_F32) for i, (x, rate) in enumerate(xs)]
         pipe = af.Pipeline(af.pipeline_config(n_mels=0))
