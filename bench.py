@@ -289,8 +289,12 @@ class Env:
         af.init(self.local_rank)
         af.set_kernel_variant(args.variant)
         self.L = af.load_library()
-        self.stream = torch.cuda.current_stream()
-        af._check(self.L.af_set_stream(self.stream.cuda_stream))      # the library enqueues on torch's stream: torch events time it
+        # a stream of our own (torch's default is the legacy NULL stream, which the C ABI reads as "the library's own"): torch
+        # ops, the events of the timed regions and -- through af_set_stream -- everything the library enqueues share it
+        self.stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.stream)
+        assert self.stream.cuda_stream != 0
+        af._check(self.L.af_set_stream(self.stream.cuda_stream))
         if self.world > 1:
             # the library's own communicator (ncclCommInitRank inside libaudioflow_gpu); torch.distributed only ships the id
             uid = torch.zeros(128, dtype=torch.uint8, device=self.dev)
@@ -326,8 +330,8 @@ class Env:
             step()
         w1.record(self.stream)
         torch.cuda.synchronize()
-        est = max(w0.elapsed_time(w1) / max(warmup, 1), 1e-3)
-        n_pre = int(min(max(math.ceil(PRE_MS / est), 1), 5000))
+        est, _ = self.max_over_ranks(max(w0.elapsed_time(w1) / max(warmup, 1), 1e-3))   # (every rank must run the SAME number of steps:
+        n_pre = int(min(max(math.ceil(PRE_MS / est), 1), 5000))                          #  a step may hold a collective)
         self.barrier()
         sampler = ClockSampler(self.local_rank) if clocks else None
         for _ in range(n_pre):
