@@ -131,29 +131,6 @@ __host__ __device__ inline void plan_tile(const StreamDev &s, uint32_t stream, u
     }
 }
 
-// One resampled sample, given the exact integer position (k, rem) and the stream tables.
-//   RS_EXACT: q is a power of two (or 1) -> the f64 recurrence of the reference is exact and
-//             frac = rem / q.
-//   RS_TABLE: frac comes from the host-run f64 recurrence; when the exact position is an integer
-//             the recurrence may sit one ulp below it, which shows as frac ~ 1 and k - 1.
-__device__ __forceinline__ float resample_one(const void *__restrict__ data, uint64_t n_samples, uint32_t n_in,
-                                              uint32_t channels, uint32_t format, uint32_t mode, float inv_q,
-                                              const float *__restrict__ frac_tab, uint32_t n, int k, uint32_t rem)
-{
-    float frac;
-    if (mode == RS_TABLE) {
-        frac = __ldg(frac_tab + n);
-        if (rem == 0 && frac >= 0.5f) k -= 1;
-    } else {
-        frac = (float)rem * inv_q;
-    }
-    const float y0 = load_mono(data, n_samples, n_in, channels, format, k - 1);
-    const float y1 = load_mono(data, n_samples, n_in, channels, format, k);
-    const float y2 = load_mono(data, n_samples, n_in, channels, format, k + 1);
-    const float y3 = load_mono(data, n_samples, n_in, channels, format, k + 2);
-    return interp_cubic(frac, y0, y1, y2, y3);
-}
-
 // ------------------------------------------------------------------------------------------
 // VAD arithmetic (vad.rs:101-153), one frame step on a precomputed mean-square energy.
 // The dB comparison `20*log10(e) > threshold_db` is replaced by `e >= e_min` where e_min is the

@@ -395,6 +395,72 @@ __device__ __forceinline__ void resample_quads_48k(const float *__restrict__ x0,
         if (i4 < i_hi) quad(px, yq, pq, i4);
 }
 
+// ---- general rational step, interior part (44.1 kHz -> 16 kHz: 441/160 with table fractions; 8 / 24 / 32 kHz: exact) ----
+// Four consecutive outputs per thread and quad: exact integer positions advanced by p / q per output, 16 unchecked taps,
+// four unfused cubics (the reference's operation order), one 16-byte store to the step buffer and one to HBM.  The table
+// fractions of a quad (one 16-byte load from L2) are requested one quad AHEAD, so that the round trip overlaps the
+// arithmetic of the quad before it; their sign bit says "one tap earlier" (plan_rate), which saves the float round trip
+// the position correction used to take.  srcp: the stage (first staged mono frame f_lo) or the stream itself (f_lo = 0).
+template <int KIND>
+__device__ __forceinline__ void resample_part_rational(const unsigned char *__restrict__ srcp, int tile_k, uint32_t tile_rem,
+                                                       const StreamDev *__restrict__ sp, const YSink &out, uint32_t tile_off, int i_lo,
+                                                       int i_hi, int rtid, int f_lo)
+{
+    constexpr int QS = 4 * RS_THREADS;
+    const uint32_t p = sp->p, q = sp->q;
+    const bool table = sp->mode == RS_TABLE;
+    int i4 = (i_lo & ~31) + 4 * rtid;
+    if (i4 < i_lo) i4 += QS;
+    if (i4 >= i_hi) return;
+    const float4 *__restrict__ frac4 = reinterpret_cast<const float4 *>(sp->frac + out.base + i4);
+    float4 ft = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (table) ft = __ldg(frac4);
+    const uint32_t a0 = tile_rem + (tile_off + (uint32_t)i4) * p;
+    uint32_t dk = a0 / q, rem = a0 - dk * q;
+    int k = tile_k + (int)dk - 1 - f_lo;                     // tap y0 of output i4, relative to the staged frames
+    const uint32_t pk = p / q, pr = p - pk * q;              // per output
+    const uint32_t sweep = (uint32_t)(QS - 3) * p;           // from the quad's last output to the next sweep's first
+    const uint32_t sk = sweep / q, sr = sweep - sk * q;
+    const float inv_q = 1.0f / (float)q;
+    const int lim4 = out.pcm ? (int)min((uint32_t)YLEN, out.wr_end - min(out.wr_end, out.base)) - 4 : -(1 << 30);
+    float *yq = out.yb + ypad(i4);
+    float *pq = out.pcm + out.base + i4;
+    for (; i4 < i_hi; i4 += QS) {
+        frac4 += QS / 4;
+        float4 ft_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (table && i4 + QS < i_hi) ft_next = __ldg(frac4);
+        const float fq[4] = {ft.x, ft.y, ft.z, ft.w};
+        float y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int o = k;
+            float frac;
+            if (table) { o -= (int)(__float_as_uint(fq[u]) >> 31); frac = fabsf(fq[u]); }
+            else frac = (float)rem * inv_q;                  // RS_EXACT: q is a power of two, exact
+            const float y0 = tap_fast<KIND>(srcp, o), y1 = tap_fast<KIND>(srcp, o + 1);
+            const float y2 = tap_fast<KIND>(srcp, o + 2), y3 = tap_fast<KIND>(srcp, o + 3);
+            y[u] = interp_cubic(frac, y0, y1, y2, y3);
+            if (u < 3) {
+                k += (int)pk; rem += pr;
+                if (rem >= q) { rem -= q; k += 1; }
+            }
+        }
+        const float4 yv = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4 *>(yq) = yv;
+        if (i4 <= lim4) __stcs(reinterpret_cast<float4 *>(pq), yv);
+        else {
+            const int left = lim4 + 4 - i4;
+            if (left > 0) __stcs(pq, yv.x);
+            if (left > 1) __stcs(pq + 1, yv.y);
+            if (left > 2) __stcs(pq + 2, yv.z);
+        }
+        k += (int)sk; rem += sr;
+        if (rem >= q) { rem -= q; k += 1; }
+        yq += ypad(QS); pq += QS;
+        ft = ft_next;
+    }
+}
+
 // ---- resampling, interior half steps: every tap comes unchecked from the stage (or the stream) ----
 template <int KIND, bool STAGED>
 __device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, const RsTile &rt, int h, const StreamDev &s, const YSink &out,
@@ -438,62 +504,7 @@ __device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, const Rs
         }
         return;
     }
-    // general rational step (44.1 kHz -> 16 kHz: 441/160 with table fractions; 8 / 24 / 32 kHz: exact fractions):
-    // four CONSECUTIVE outputs per thread -- one 16-byte load of the table fractions, exact integer positions
-    // advanced by p/q per output, 16 taps, four cubics, one 16-byte store to the step buffer and to HBM
-    {
-        constexpr int QS = 4 * RS_THREADS;
-        int i4 = (i_lo & ~31) + 4 * rtid;
-        if (i4 < i_lo) i4 += QS;
-        const uint32_t p = s.p;
-        const uint32_t a0 = rt.tile_rem + (tile_off + (uint32_t)i4) * p;
-        uint32_t dk = a0 / q, rem = a0 - dk * q;
-        int k = rt.tile_k + (int)dk - 1 - f_lo;                  // tap y0 of output i4, relative to the staged frames
-        const uint32_t pk = p / q, pr = p - pk * q;              // per output
-        const uint32_t sweep = (uint32_t)(QS - 3) * p;           // from the quad's last output to the next sweep's first
-        const uint32_t sk = sweep / q, sr = sweep - sk * q;
-        const float inv_q = 1.0f / (float)q;
-        const float4 *__restrict__ frac4 = reinterpret_cast<const float4 *>(s.frac + out.base + i4);
-        const int lim4 = out.pcm ? (int)min((uint32_t)YLEN, out.wr_end - min(out.wr_end, out.base)) - 4 : -(1 << 30);
-        float *yq = out.yb + ypad(i4);
-        float *pq = out.pcm + out.base + i4;
-        for (; i4 < i_hi; i4 += QS) {
-            float ft[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (mode == RS_TABLE) {
-                const float4 t = __ldg(frac4);
-                ft[0] = t.x; ft[1] = t.y; ft[2] = t.z; ft[3] = t.w;
-            }
-            float y[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                int o = k;
-                float frac = (float)rem * inv_q;                 // RS_EXACT: q is a power of two, exact
-                if (mode == RS_TABLE) {
-                    o += __float2int_rn(frac - ft[u]);           // -1 when the f64 recurrence sits just below an integer
-                    frac = ft[u];
-                }
-                const float y0 = tap_fast<KIND>(srcp, o), y1 = tap_fast<KIND>(srcp, o + 1);
-                const float y2 = tap_fast<KIND>(srcp, o + 2), y3 = tap_fast<KIND>(srcp, o + 3);
-                y[u] = interp_cubic(frac, y0, y1, y2, y3);
-                if (u < 3) {
-                    k += (int)pk; rem += pr;
-                    if (rem >= q) { rem -= q; k += 1; }
-                }
-            }
-            const float4 yv = make_float4(y[0], y[1], y[2], y[3]);
-            *reinterpret_cast<float4 *>(yq) = yv;
-            if (i4 <= lim4) __stcs(reinterpret_cast<float4 *>(pq), yv);
-            else {
-                const int left = lim4 + 4 - i4;
-                if (left > 0) __stcs(pq, yv.x);
-                if (left > 1) __stcs(pq + 1, yv.y);
-                if (left > 2) __stcs(pq + 2, yv.z);
-            }
-            k += (int)sk; rem += sr;
-            if (rem >= q) { rem -= q; k += 1; }
-            frac4 += QS / 4; yq += ypad(QS); pq += QS;
-        }
-    }
+    resample_part_rational<KIND>(srcp, rt.tile_k, rt.tile_rem, &s, out, tile_off, i_lo, i_hi, rtid, f_lo);
 }
 
 // ---- resampling, checked: samples [base + i_lo, base + i_hi) of the stream, zero beyond n_out ----
@@ -529,8 +540,9 @@ __device__ __noinline__ void resample_half(const FusedSmem &sm, const RsTile &rt
             int kk = k;
             float frac;
             if (mode == RS_TABLE) {
-                frac = __ldg(frac_tab + n);
-                kk += __float2int_rn((float)rem * inv_q - frac);      // -1 when the f64 recurrence sits just below an integer
+                const float fe = __ldg(frac_tab + n);                 // sign bit: the f64 recurrence sits just below an integer (plan_rate)
+                kk -= (int)(__float_as_uint(fe) >> 31);
+                frac = fabsf(fe);
             } else {
                 frac = (float)rem * inv_q;                            // q is a power of two: exact
             }

@@ -165,8 +165,20 @@ int plan_rate(uint32_t in_rate, uint32_t out_rate, uint64_t n_in, uint64_t *n_ou
             auto t = std::make_shared<FracTable>();
             t->n = pl.frac.size();
             if (t->n) {
-                AF_CUDA(cudaMalloc(&t->d, t->n * sizeof(float)));
-                AF_CUDA(cudaMemcpy(t->d, pl.frac.data(), t->n * sizeof(float), cudaMemcpyHostToDevice));
+                // Device form of the table: the fraction the reference's f64 recurrence produces, with the SIGN BIT set where
+                // the recurrence sits just below an exactly integer position (frac ~ 1 and floor one less than the exact
+                // integer arithmetic of the kernel gives): the kernel then needs no float round trip to find the tap --
+                // k -= sign, frac = |entry|.  (Fractions are never negative, and a flagged one is never 0.)
+                std::vector<float> enc(pl.frac);
+                for (size_t n = 0; n < enc.size(); ++n) {
+                    long long k; uint32_t rem;
+                    resample_pos(n, pl.rec.p, pl.rec.q, &k, &rem);
+                    if (rem == 0 && enc[n] >= 0.5f) enc[n] = -enc[n];
+                }
+                // (16 floats of slack: the kernel fetches whole quads)
+                AF_CUDA(cudaMalloc(&t->d, (t->n + 16) * sizeof(float)));
+                AF_CUDA(cudaMemset(t->d, 0, (t->n + 16) * sizeof(float)));
+                AF_CUDA(cudaMemcpy(t->d, enc.data(), t->n * sizeof(float), cudaMemcpyHostToDevice));
             }
             pl.dev = t;
         }

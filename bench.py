@@ -510,13 +510,14 @@ def measure_cfg3(env: Env, steps: int, warmup: int):
     """BASELINE config 3: 4096 x 30 s mixed 44.1/48 kHz mono f32, full pipeline (PCM + 80 mel + VAD), sharded over the N GPUs by
     input bytes inside the library (strong scaling), with and without the gather of the VAD states."""
     af, torch = env.af, env.torch
-    S_total = 4096
-    rates = [44100 if i % 2 else 48000 for i in range(S_total)]
+    S_total = int(os.environ.get("AF_CFG3_STREAMS", "4096"))                # (experiments: fewer streams / a single rate)
+    only = os.environ.get("AF_CFG3_RATE")
+    rates = [int(only) if only else (44100 if i % 2 else 48000) for i in range(S_total)]
     geo = [(0, int(SECONDS * r), r, 1, af.AF_FMT_F32) for r in rates]
     lo, hi = af.shard_partition(geo, env.world)[env.rank]
     mine = list(range(lo, hi))
-    x48 = env.synth.torch_batch(sum(1 for i in mine if rates[i] == 48000), SECONDS, 48000, 1, env.dev, seed=2 * env.rank)
-    x44 = env.synth.torch_batch(sum(1 for i in mine if rates[i] == 44100), SECONDS, 44100, 1, env.dev, seed=2 * env.rank + 1)
+    x48 = env.synth.torch_batch(max(sum(1 for i in mine if rates[i] == 48000), 1), SECONDS, 48000, 1, env.dev, seed=2 * env.rank)
+    x44 = env.synth.torch_batch(max(sum(1 for i in mine if rates[i] == 44100), 1), SECONDS, 44100, 1, env.dev, seed=2 * env.rank + 1)
     descs, i48, i44 = list(geo), 0, 0
     for i in mine:
         if rates[i] == 48000:
