@@ -756,6 +756,7 @@ struct SubBatch {                     // a group of streams resident on the devi
     size_t in_bytes = 0;
     uint32_t *d_scan = nullptr;       // long streams: scratch of the many-CTA VAD scan (launch_vad_scan)
     bool quarters = false;            // some stream stages its input in quarter steps (f32 stereo)
+    bool no_merge = false;            // host mode: a merged copy was refused (rows adjacent in memory but separately allocated)
 };
 
 }  // namespace
@@ -1206,14 +1207,26 @@ AF_API int af_batch_run_host(af_batch *b, const af_outputs *o)
         for (size_t i = 0; i < sb.count;) {
             const af_stream_desc &d0 = b->streams[sb.first + i].desc;
             size_t bytes = d0.n_samples * (d0.format == AF_FMT_I16 ? 2 : 4);
+            const size_t bytes0 = bytes;
             size_t j = i + 1;
-            while (j < sb.count) {
+            while (!sb.no_merge && j < sb.count) {
                 const af_stream_desc &dj = b->streams[sb.first + j].desc;
                 if ((const char *)dj.data != (const char *)d0.data + bytes || sb.in_off[j] != sb.in_off[i] + bytes) break;
                 bytes += dj.n_samples * (dj.format == AF_FMT_I16 ? 2 : 4);
                 ++j;
             }
-            if (bytes) AF_CUDA(cudaMemcpyAsync((char *)sl.d_in + sb.in_off[i], d0.data, bytes, cudaMemcpyHostToDevice, st));
+            if (bytes) {
+                cudaError_t ce = cudaMemcpyAsync((char *)sl.d_in + sb.in_off[i], d0.data, bytes, cudaMemcpyHostToDevice, st);
+                if (ce == cudaErrorInvalidValue && j > i + 1) {
+                    // rows that happen to be adjacent in host memory but belong to separate pinned allocations: CUDA refuses a
+                    // copy that spans two of them.  Not sticky: copy this sub-batch stream by stream from now on.
+                    (void)cudaGetLastError();
+                    sb.no_merge = true;
+                    j = i + 1;
+                    ce = bytes0 ? cudaMemcpyAsync((char *)sl.d_in + sb.in_off[i], d0.data, bytes0, cudaMemcpyHostToDevice, st) : cudaSuccess;
+                }
+                AF_CUDA(ce);
+            }
             i = j;
         }
         const bool need_pcm = (cfg.write_pcm && o->pcm) || (cfg.vad_enable && cfg.vad_frame_len != 0);

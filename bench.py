@@ -42,7 +42,7 @@ N_MELS = 80
 BYTES_PER_AUDIO_S = RATE * 1 * 4 + 16000 * 4 + 100 * N_MELS * 4          # 288000 (VAD off)
 BYTES_PER_AUDIO_S_VAD = BYTES_PER_AUDIO_S + 100                          # + u8 VAD state per frame
 WORKLOAD = "cfg2: 256 x 30 s 48 kHz mono f32 streams per GPU -> 16 kHz PCM + 25/10 ms STFT + 80-bin log-mel"
-PRE_MS = 50.0        # untimed load right after the barrier: the timed window starts on a GPU that is already busy
+PRE_MS = float(os.environ.get("AF_BENCH_PRE_MS", "50"))   # untimed load in front of a timed window (0 under ncu: fixed launch counts)
 
 
 def config_dict(world: int, variant: str = "auto") -> dict:
