@@ -27,12 +27,21 @@ namespace af {
 
 constexpr int AF_MAX_GPUS_INTERNAL = 16;
 
-struct RsTile {
-    StreamDev stream;
-    int tile_k;                                      // floor(position) of the tile's first output
+// What the resampler warps need of a TileDev, copied as it lies in global memory: the 32-byte header and the 80 bytes
+// behind the fill descriptors (stream descriptor + position increments).  cp.async puts the NEXT tile's copy into the
+// warp's other slot while the current tile is worked on: no registers are held across the tile and nothing waits for
+// the global loads (held in registers, the prefetched words were spilled at once -- a store that waits for the load).
+struct alignas(16) RsTile {
+    uint32_t stream_idx, tile;
+    int tile_k;                                      // floor(position) of the tile's first output (TileDev::k0)
     uint32_t tile_rem;                               // and its remainder (numerator units)
+    uint32_t n_steps, tile_end, n_frames, parts;
+    StreamDev stream;
     uint32_t inc_k, inc_rem;                         // position increment for RS_THREADS outputs
 };
+static_assert(sizeof(RsTile) == 112 && offsetof(RsTile, stream) == 32, "RsTile mirrors the head and the tail of TileDev");
+static_assert(offsetof(TileDev, sdesc) % 16 == 0 && sizeof(TileDev) - offsetof(TileDev, sdesc) == 80 && offsetof(TileDev, parts) == 28 &&
+              offsetof(TileDev, inc_k) == offsetof(TileDev, sdesc) + sizeof(StreamDev), "TileDev layout the cp.async prefetch relies on");
 
 struct __align__(128) FusedSmem {
     unsigned char stage[N_STAGE][STAGE_BYTES];       // raw interleaved input of a part of a step (bulk-copy targets)
@@ -56,7 +65,7 @@ struct __align__(128) FusedSmem {
                                                      // 2: inside the stream but not staged (unchecked global loads)
     // resampler role: every warp keeps its own copy of the tile's stream descriptor and first-output position, so that
     // a new tile needs no synchronisation among the resampler warps
-    RsTile rs[RS_WARPS];
+    RsTile rs[2][RS_WARPS];
 };
 static_assert(sizeof(FusedSmem) <= 232448, "FusedSmem exceeds the 227 KB a CTA may use");
 
@@ -109,6 +118,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // warp-level arrive: every lane's earlier shared-memory accesses are ordered before lane 0's arrive
 __device__ __forceinline__ void warp_arrive(unsigned long long *bar, int lane)
 {
@@ -966,34 +980,25 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
     uint32_t it = 0;
     uint32_t uses0 = 0;                                     // uses of EACH stage buffer before the current step (see role_vad: fills0)
     AF_STATS_DECL
-    // the descriptor of a tile's stream is fetched one tile ahead into registers: lanes 0..15 of every warp hold one
-    // word of the StreamDev each, lane 16 the planned position of the tile's first output
-    RsTile &rt = sm.rs[rtid >> 5];
-    uint32_t nx_word = 0, nx_rem = 0, nx_inck = 0, nx_incr = 0;
-    int nx_k = 0;
-    TileGeo nx_t{};
-    auto prefetch = [&](uint32_t tile) {
-        if (tile >= P.n_tiles) return;
-        const TileDev *td = P.tiles + tile;
-        const StreamDev *sp = &td->sdesc;
-        nx_t.stream = td->stream;
-        nx_t.n_tile0 = td->tile * TILE_SAMPLES;
-        nx_t.tile_end = td->tile_end;
-        nx_t.n_steps = td->n_steps;
-        nx_t.n_frames = td->n_frames;
-        nx_t.parts = td->parts;
-        if (lane < (int)(sizeof(StreamDev) / 4)) nx_word = reinterpret_cast<const uint32_t *>(sp)[lane];
-        if (lane == 16) { nx_k = td->k0; nx_rem = td->rem0; nx_inck = td->inc_k; nx_incr = td->inc_rem; }   // planned on the host
+    // the descriptor of a tile is fetched one tile ahead with cp.async into the warp's other slot (RsTile)
+    const int w = rtid >> 5;
+    auto prefetch = [&](uint32_t tile, int slot) {
+        if (tile < P.n_tiles && lane < 7) {
+            const char *src = reinterpret_cast<const char *>(P.tiles + tile) + (lane < 2 ? 16 * lane : (int)offsetof(TileDev, sdesc) + 16 * (lane - 2));
+            cp_async16(reinterpret_cast<char *>(&sm.rs[slot][w]) + 16 * lane, src);
+        }
     };
-    prefetch(blockIdx.x);
-    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    int slot = 0;
+    prefetch(blockIdx.x, 0);
+    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, slot ^= 1) {
         AF_TIC
-        const TileGeo t = nx_t;
-        __syncwarp();                                   // this warp is done with the previous tile's descriptor
-        if (lane < (int)(sizeof(StreamDev) / 4)) reinterpret_cast<uint32_t *>(&rt.stream)[lane] = nx_word;
-        if (lane == 16) { rt.tile_k = nx_k; rt.tile_rem = nx_rem; rt.inc_k = nx_inck; rt.inc_rem = nx_incr; }
-        __syncwarp();
-        prefetch(tile + gridDim.x);
+        cp_async_wait_all();
+        __syncwarp();                                   // the copy is visible to the warp; every lane is done with the other slot
+        const RsTile &rt = sm.rs[slot][w];
+        prefetch(tile + gridDim.x, slot ^ 1);
+        TileGeo t;
+        t.stream = rt.stream_idx; t.n_tile0 = rt.tile * TILE_SAMPLES; t.tile_end = rt.tile_end; t.n_steps = rt.n_steps;
+        t.n_frames = rt.n_frames; t.parts = rt.parts;
         AF_TOC(2)
         const StreamDev &s = rt.stream;
         int kind = K_GENERIC;
