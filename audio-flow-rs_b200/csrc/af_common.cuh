@@ -250,6 +250,7 @@ struct FusedParams {
     uint32_t use_stage;      // 0: plain global loads everywhere ("sync" variant)
     uint32_t layout;         // warp-to-role layout (warp_role)
     uint32_t quarters;       // 1: some tile stages its input in quarter steps (TileDev::parts == 4): general kernel instance
+    float neg_zero;          // -0.0f, unknown to the compiler: the addend of the packed cubic's products (interp_cubic2)
 };
 
 }  // namespace af

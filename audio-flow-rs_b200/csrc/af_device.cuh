@@ -271,6 +271,27 @@ __device__ __forceinline__ void cmul2(f2 &r, f2 &i, f2 c, f2 s)
     const f2 ti = fma2(r, s, mul2(i, c));
     r = tr; i = ti;
 }
+// ------------------------------------------------------------------------------------------
+// rubato's interp_cubic on TWO outputs at once in packed f32x2 arithmetic, bit for bit the scalar interp_cubic above.
+// ptxas contracts a packed multiply with the packed addition that follows it into FFMA2 even when both carry .rn (and
+// also when the product is written fma(a, b, -0) with a literal zero, and with -fmad=false: tools/ubench/cubic2_check.cu),
+// which changes the rounding.  So every product here is fma(a, b, nz) with nz = -0.0f that only the host knows (a kernel
+// argument): ptxas cannot fold the addend away, there is nothing left to contract, and a * b + (-0) is RN(a * b) for every
+// a, b -- zero products of either sign, subnormals, Inf and NaN included.  11 FFMA2 + 11 FADD2 for two outputs instead
+// of 22 FMUL + 22 FADD.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ f2 interp_cubic2(f2 x, f2 y0, f2 y1, f2 y2, f2 y3, float nz)
+{
+    const float c13 = 1.0f / 3.0f, c16 = 1.0f / 6.0f;
+    const f2 z = mk2(nz, nz), h = mk2(0.5f, 0.5f), s6 = mk2(c16, c16);
+    const f2 a1 = sub2(add2(sub2(fma2(mk2(-c13, -c13), y0, z), fma2(h, y1, z)), y2), fma2(s6, y3, z));
+    const f2 a2 = sub2(fma2(h, add2(y0, y2), z), y1);
+    const f2 a3 = add2(fma2(h, sub2(y1, y2), z), fma2(s6, sub2(y3, y0), z));
+    const f2 x2 = fma2(x, x, z);
+    const f2 x3 = fma2(x2, x, z);
+    return add2(add2(add2(y1, fma2(a1, x, z)), fma2(a2, x2, z)), fma2(a3, x3, z));
+}
+
 // radix-4 butterfly on two transforms at once (the halves of the packs), in place; output c lands where input c was
 __device__ __forceinline__ void fft4p(f2 &r0, f2 &i0, f2 &r1, f2 &i1, f2 &r2, f2 &i2, f2 &r3, f2 &i3)
 {

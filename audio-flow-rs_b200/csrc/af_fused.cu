@@ -340,6 +340,7 @@ struct YSink {
     float *__restrict__ pcm;      // stream's PCM row or nullptr
     uint32_t base;                // stream index of step-buffer sample 0
     uint32_t wr_end;              // the tile owns stream samples < wr_end
+    float nz;                     // FusedParams::neg_zero (interp_cubic2)
     __device__ __forceinline__ void put(int i, float v) const
     {
         yb[ypad(i)] = v;
@@ -418,7 +419,7 @@ __device__ __forceinline__ void resample_quads_48k(const float *__restrict__ x0,
 template <int KIND>
 __device__ __forceinline__ void resample_part_rational(const unsigned char *__restrict__ srcp, int tile_k, uint32_t tile_rem,
                                                        const StreamDev *__restrict__ sp, const YSink &out, uint32_t tile_off, int i_lo,
-                                                       int i_hi, int rtid, int f_lo)
+                                                       int i_hi, int rtid, int f_lo, float nz)
 {
     constexpr int QS = 4 * RS_THREADS;
     const uint32_t p = sp->p, q = sp->q;
@@ -444,22 +445,23 @@ __device__ __forceinline__ void resample_part_rational(const unsigned char *__re
         float4 ft_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (table && i4 + QS < i_hi) ft_next = __ldg(frac4);
         const float fq[4] = {ft.x, ft.y, ft.z, ft.w};
-        float y[4];
+        float fr[4], t0[4], t1[4], t2[4], t3[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             int o = k;
-            float frac;
-            if (table) { o -= (int)(__float_as_uint(fq[u]) >> 31); frac = fabsf(fq[u]); }
-            else frac = (float)rem * inv_q;                  // RS_EXACT: q is a power of two, exact
-            const float y0 = tap_fast<KIND>(srcp, o), y1 = tap_fast<KIND>(srcp, o + 1);
-            const float y2 = tap_fast<KIND>(srcp, o + 2), y3 = tap_fast<KIND>(srcp, o + 3);
-            y[u] = interp_cubic(frac, y0, y1, y2, y3);
+            if (table) { o -= (int)(__float_as_uint(fq[u]) >> 31); fr[u] = fabsf(fq[u]); }
+            else fr[u] = (float)rem * inv_q;                 // RS_EXACT: q is a power of two, exact
+            t0[u] = tap_fast<KIND>(srcp, o); t1[u] = tap_fast<KIND>(srcp, o + 1);
+            t2[u] = tap_fast<KIND>(srcp, o + 2); t3[u] = tap_fast<KIND>(srcp, o + 3);
             if (u < 3) {
                 k += (int)pk; rem += pr;
                 if (rem >= q) { rem -= q; k += 1; }
             }
         }
-        const float4 yv = make_float4(y[0], y[1], y[2], y[3]);
+        // two outputs per packed cubic (bit for bit the scalar interp_cubic: see interp_cubic2)
+        const f2 ya = interp_cubic2(mk2(fr[0], fr[1]), mk2(t0[0], t0[1]), mk2(t1[0], t1[1]), mk2(t2[0], t2[1]), mk2(t3[0], t3[1]), nz);
+        const f2 yb2 = interp_cubic2(mk2(fr[2], fr[3]), mk2(t0[2], t0[3]), mk2(t1[2], t1[3]), mk2(t2[2], t2[3]), mk2(t3[2], t3[3]), nz);
+        const float4 yv = make_float4(ya.x, ya.y, yb2.x, yb2.y);
         *reinterpret_cast<float4 *>(yq) = yv;
         if (i4 <= lim4) __stcs(reinterpret_cast<float4 *>(pq), yv);
         else {
@@ -518,7 +520,7 @@ __device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, const Rs
         }
         return;
     }
-    resample_part_rational<KIND>(srcp, rt.tile_k, rt.tile_rem, &s, out, tile_off, i_lo, i_hi, rtid, f_lo);
+    resample_part_rational<KIND>(srcp, rt.tile_k, rt.tile_rem, &s, out, tile_off, i_lo, i_hi, rtid, f_lo, out.nz);
 }
 
 // ---- resampling, checked: samples [base + i_lo, base + i_hi) of the stream, zero beyond n_out ----
@@ -1017,7 +1019,7 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
         for (uint32_t g = 0; g < t.n_steps; ++g, ++it) {
             const int b = (int)(it & 1u);
             const uint32_t toff = g * STEP_SAMPLES;
-            YSink out{sm.ybuf[b], pcm_row, t.n_tile0 + toff, t.tile_end};
+            YSink out{sm.ybuf[b], pcm_row, t.n_tile0 + toff, t.tile_end, P.neg_zero};
             const int lim4 = pcm_row ? (int)min((uint32_t)YLEN, out.wr_end - min(out.wr_end, out.base)) - 4 : -(1 << 30);
             AF_WAIT(&sm.y_empty[b], ((it >> 1) & 1u) ^ 1u, 0);   // FFT and VAD warps are done with this buffer
             AF_TIC2

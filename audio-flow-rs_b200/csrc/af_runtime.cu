@@ -858,6 +858,7 @@ int run_sub(af_batch *b, SubBatch &sb, float *pcm, uint64_t pcm_stride, float *l
         P.use_stage = kernel_variant() == "sync" ? 0u : 1u;
         P.layout = fused_layout(stft_vad);
         P.quarters = sb.quarters ? 1u : 0u;
+        P.neg_zero = -0.0f;
         const int n_ctas = (int)std::min<size_t>(sb.h_tiles.size(), (size_t)cur_ctx().sm_count);   // one persistent CTA per SM
         AF_CUDA(launch_fused(P, n_ctas, st));
         count_launch();
@@ -1619,6 +1620,7 @@ AF_API int af_session_push(af_session *s, const void *data, uint64_t in_stride, 
             P.log_scale = cfg.log10 ? 0.30102999566398120f : 0.69314718055994531f;
             P.use_stage = kernel_variant() == "sync" ? 0u : 1u;
             P.layout = fused_layout(P.do_energy != 0);
+            P.neg_zero = -0.0f;
             if (P.n_mels || P.do_energy) {
                 AF_CUDA(launch_fused(P, (int)std::min<size_t>(P.n_tiles, (size_t)cur_ctx().sm_count), st));
                 count_launch(2);
