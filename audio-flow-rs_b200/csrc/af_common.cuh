@@ -119,6 +119,7 @@ constexpr int PB_COLS = PB_ROW;              // bins a padded weight quadruple m
 constexpr int PBUF_FLOATS = SF * PB_ROW;
 __host__ __device__ constexpr int pb_row(int q) { return ((q >> 1) & 3) + 8 * (q >> 3) + 4 * (q & 1); }
 __host__ __device__ constexpr int pb_frame(int row) { return 2 * ((row & 3) + 4 * (row >> 3)) + ((row >> 2) & 1); }
+constexpr int KOFF_MAX = 640;                // longest output period (q) the periodic-position path of the resampler serves
 constexpr int STAGE_BYTES = 32384;           // one TMA-staged part of raw input (2688 outputs x 3 x 4 B + halo), two of them
 
 // formats / flags (mirror include/audioflow_gpu.h)
@@ -251,6 +252,7 @@ struct FusedParams {
     uint32_t layout;         // warp-to-role layout (warp_role)
     uint32_t quarters;       // 1: some tile stages its input in quarter steps (TileDev::parts == 4): general kernel instance
     float neg_zero;          // -0.0f, unknown to the compiler: the addend of the packed cubic's products (interp_cubic2)
+    uint32_t per_p, per_q;   // RS_TABLE streams with this p / q take the periodic-position path (resample_part_periodic); 0: none
 };
 
 }  // namespace af

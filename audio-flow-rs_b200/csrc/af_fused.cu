@@ -66,6 +66,10 @@ struct __align__(128) FusedSmem {
     // resampler role: every warp keeps its own copy of the tile's stream descriptor and first-output position, so that
     // a new tile needs no synchronisation among the resampler warps
     RsTile rs[2][RS_WARPS];
+    // periodic positions of the batch's table-mode rate (FusedParams::per_p / per_q): output r of a period of q outputs sits
+    // floor((r + 1) p / q) input frames behind the period's base; sw_*: what a sweep of 4 * RS_THREADS outputs adds
+    uint32_t per_p, per_q, sw_r, sw_kp;
+    alignas(8) uint16_t koff[KOFF_MAX];
 };
 static_assert(sizeof(FusedSmem) <= 232448, "FusedSmem exceeds the 227 KB a CTA may use");
 
@@ -477,6 +481,62 @@ __device__ __forceinline__ void resample_part_rational(const unsigned char *__re
     }
 }
 
+// ---- table-mode rate whose positions repeat every q outputs (44.1 kHz -> 16 kHz: q = 160, p = 441), interior part ----
+// Output i of the step buffer (the step starts on a period boundary: q divides STEP_SAMPLES) reads the taps
+// kb + (i div q) p + koff[i mod q] - 1 ...: one LDS.64 of four 16-bit offsets replaces the quad's position arithmetic, the
+// period counter advances by constants per sweep.  Fractions as in resample_part_rational (table in L2, one quad ahead).
+template <int KIND>
+__device__ __forceinline__ void resample_part_periodic(const FusedSmem &sm, const unsigned char *__restrict__ srcp, int kb, uint32_t p,
+                                                       uint32_t q, const float *__restrict__ frac_row, const YSink &out, int i_lo, int i_hi,
+                                                       int rtid)
+{
+    constexpr int QS = 4 * RS_THREADS;
+    int i4 = (i_lo & ~31) + 4 * rtid;
+    if (i4 < i_lo) i4 += QS;
+    if (i4 >= i_hi) return;
+    const float4 *__restrict__ frac4 = reinterpret_cast<const float4 *>(frac_row + i4);
+    float4 ft = __ldg(frac4);
+    const uint32_t per = (uint32_t)i4 / q;
+    uint32_t r4 = (uint32_t)i4 - per * q;                    // position of the quad inside its period (a multiple of 4)
+    kb += (int)(per * p);
+    const uint32_t sw_r = sm.sw_r;
+    const int sw_kp = (int)sm.sw_kp;
+    const int lim4 = out.pcm ? (int)min((uint32_t)YLEN, out.wr_end - min(out.wr_end, out.base)) - 4 : -(1 << 30);
+    float *yq = out.yb + ypad(i4);
+    float *pq = out.pcm + out.base + i4;
+    for (; i4 < i_hi; i4 += QS) {
+        frac4 += QS / 4;
+        float4 ft_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (i4 + QS < i_hi) ft_next = __ldg(frac4);
+        const uint2 kk = *reinterpret_cast<const uint2 *>(sm.koff + r4);
+        const uint32_t fb[4] = {__float_as_uint(ft.x), __float_as_uint(ft.y), __float_as_uint(ft.z), __float_as_uint(ft.w)};
+        const uint32_t ko[4] = {kk.x & 0xffffu, kk.x >> 16, kk.y & 0xffffu, kk.y >> 16};
+        float fr[4], t0[4], t1[4], t2[4], t3[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int o = kb + (int)ko[u] - (int)(fb[u] >> 31);      // sign bit: "one tap earlier" (plan_rate)
+            fr[u] = __uint_as_float(fb[u] & 0x7fffffffu);
+            t0[u] = tap_fast<KIND>(srcp, o); t1[u] = tap_fast<KIND>(srcp, o + 1);
+            t2[u] = tap_fast<KIND>(srcp, o + 2); t3[u] = tap_fast<KIND>(srcp, o + 3);
+        }
+        const f2 ya = interp_cubic2(mk2(fr[0], fr[1]), mk2(t0[0], t0[1]), mk2(t1[0], t1[1]), mk2(t2[0], t2[1]), mk2(t3[0], t3[1]), out.nz);
+        const f2 yb2 = interp_cubic2(mk2(fr[2], fr[3]), mk2(t0[2], t0[3]), mk2(t1[2], t1[3]), mk2(t2[2], t2[3]), mk2(t3[2], t3[3]), out.nz);
+        const float4 yv = make_float4(ya.x, ya.y, yb2.x, yb2.y);
+        *reinterpret_cast<float4 *>(yq) = yv;
+        if (i4 <= lim4) __stcs(reinterpret_cast<float4 *>(pq), yv);
+        else {
+            const int left = lim4 + 4 - i4;
+            if (left > 0) __stcs(pq, yv.x);
+            if (left > 1) __stcs(pq + 1, yv.y);
+            if (left > 2) __stcs(pq + 2, yv.z);
+        }
+        r4 += sw_r; kb += sw_kp;
+        if (r4 >= q) { r4 -= q; kb += (int)p; }
+        yq += ypad(QS); pq += QS;
+        ft = ft_next;
+    }
+}
+
 // ---- resampling, interior half steps: every tap comes unchecked from the stage (or the stream) ----
 template <int KIND, bool STAGED>
 __device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, const RsTile &rt, int h, const StreamDev &s, const YSink &out,
@@ -518,6 +578,13 @@ __device__ __forceinline__ void resample_half_fast(const FusedSmem &sm, const Rs
             if (!(y1 != 0.0f && (orx & 0x40000000u) == 0u)) v = interp_cubic(0.0f, y0, y1, y2, y3);
             out.put(i, v);
         }
+        return;
+    }
+    if (s.mode == RS_TABLE && q == sm.per_q && s.p == sm.per_p) {
+        // k of step-buffer output i = kb0 + (i div q) p + koff[i mod q]; tile_k is the k of the tile's first output (koff[0] past its
+        // period base), the step starts tile_off / q periods later; "- 1 - f_lo": tap y0, relative to the staged frames
+        const int kb0 = rt.tile_k - (int)sm.koff[0] + (int)((tile_off / q) * s.p) - 1 - f_lo;
+        resample_part_periodic<KIND>(sm, srcp, kb0, s.p, q, s.frac + out.base, out, i_lo, i_hi, rtid);
         return;
     }
     resample_part_rational<KIND>(srcp, rt.tile_k, rt.tile_rem, &s, out, tile_off, i_lo, i_hi, rtid, f_lo, out.nz);
@@ -1096,6 +1163,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
             for (int i = tid; i < (int)(sizeof(MelTables) / 4); i += FUSED_THREADS) md[i] = ms[i];
         }
         for (int i = tid; i < 2 * PBUF_FLOATS; i += FUSED_THREADS) sm.pbuf[0][i] = 0.0f;
+        if (P.per_q) {
+            for (uint32_t r = tid; r < P.per_q; r += FUSED_THREADS) sm.koff[r] = (uint16_t)(((r + 1u) * P.per_p) / P.per_q);
+        }
+        if (tid == 0) {
+            constexpr uint32_t QS = 4u * RS_THREADS;
+            sm.per_p = P.per_p; sm.per_q = P.per_q;
+            sm.sw_r = P.per_q ? QS % P.per_q : 0u;
+            sm.sw_kp = P.per_q ? (QS / P.per_q) * P.per_p : 0u;
+        }
     }
     if (tid == 0) {
         for (int h = 0; h < N_STAGE; ++h) {
