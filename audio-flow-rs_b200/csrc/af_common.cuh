@@ -41,10 +41,17 @@ constexpr int TILE_FRAMES = 128;             // frames per tile (work unit of on
 constexpr int TILE_SAMPLES = TILE_FRAMES * HOP;   // 20480
 constexpr int FFT_WARPS = 16;                // "F": window + FFT + power, one frame per half-warp
 constexpr int MEL_WARPS = 4;                 // "M": mel projection + log, lane = frame
-constexpr int RS_WARPS = 7;                  // "R": downmix + resample + PCM write-out.  224 threads: a half step (2688
+#ifdef AF_V2
+constexpr int VAD_WARPS = 2;
+constexpr int RS_WARPS = 6;
+#else
+constexpr int VAD_WARPS = 1;
+constexpr int RS_WARPS = 7;
+#endif
+constexpr int RS_WARPS_DOC = 7;                  // "R": downmix + resample + PCM write-out.  224 threads: a half step (2688
                                              // outputs) is exactly three quads per thread
 constexpr int RS_THREADS = RS_WARPS * 32;
-constexpr int FUSED_WARPS = FFT_WARPS + MEL_WARPS + 1 + RS_WARPS;   // 28 (one "V" warp: stage fills + sequential frame energies)
+constexpr int FUSED_WARPS = FFT_WARPS + MEL_WARPS + VAD_WARPS + RS_WARPS;   // 28 (one "V" warp: stage fills + sequential frame energies)
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;   // 896
 // Which role a hardware warp plays.  Warp w issues from scheduler (SM sub-partition) w % 4, seven warps each, and
 // addresses TMEM lane quarter w % 4.  Three layouts, chosen per launch (FusedParams::layout):
@@ -61,11 +68,19 @@ constexpr unsigned long long pack_layout(int layout)
 {
     constexpr int F = ROLE_F, M = ROLE_M, V = ROLE_V, R = ROLE_R;
     // rows = w / 4, columns = scheduler
+#ifdef AF_V2
+    constexpr int tab[N_LAYOUTS][FUSED_WARPS] = {
+        {V, V, F, F,  M, M, M, M,  R, R, R, R,  R, R, F, F,  F, F, F, F,  F, F, F, F,  F, F, F, F},
+        {V, V, F, F,  M, M, M, M,  R, R, R, R,  R, R, F, F,  F, F, F, F,  F, F, F, F,  F, F, F, F},
+        {V, V, F, F,  M, M, M, M,  R, R, R, R,  R, R, F, F,  F, F, F, F,  F, F, F, F,  F, F, F, F},
+        {V, V, F, F,  M, M, M, M,  R, R, R, R,  R, R, F, F,  F, F, F, F,  F, F, F, F,  F, F, F, F}};
+#else
     constexpr int tab[N_LAYOUTS][FUSED_WARPS] = {
         {F, F, F, F,  F, F, F, F,  F, F, F, F,  F, F, F, F,  M, M, M, M,  V, R, R, R,  R, R, R, R},
         {V, F, F, F,  F, F, F, F,  F, F, F, F,  M, F, F, F,  R, M, M, M,  R, F, F, R,  R, R, R, R},
         {V, F, F, F,  F, F, F, F,  M, F, F, F,  R, M, M, M,  R, F, F, F,  R, F, F, F,  R, R, R, R},
         {V, F, F, F,  M, F, F, F,  R, F, F, F,  R, F, F, F,  R, F, F, F,  R, F, R, R,  R, M, M, M}};
+#endif
     unsigned long long m = 0;
     for (int w = 0; w < FUSED_WARPS; ++w) m |= (unsigned long long)tab[layout][w] << (2 * w);
     return m;
@@ -94,7 +109,7 @@ constexpr bool layouts_ok()
             ++n[r.role];
             if (r.role == ROLE_M && (w & 3) != r.index) return false;      // mel warp j on scheduler / TMEM quarter j
         }
-        if (n[ROLE_F] != FFT_WARPS || n[ROLE_M] != MEL_WARPS || n[ROLE_V] != 1 || n[ROLE_R] != RS_WARPS) return false;
+        if (n[ROLE_F] != FFT_WARPS || n[ROLE_M] != MEL_WARPS || n[ROLE_V] != VAD_WARPS || n[ROLE_R] != RS_WARPS) return false;
     }
     return true;
 }

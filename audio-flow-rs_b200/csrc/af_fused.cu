@@ -81,7 +81,11 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t coun
 }
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 {
+#ifdef AF_ARRIVE_RELAXED
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.relaxed.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+#else
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes)
 {
@@ -786,8 +790,9 @@ __device__ __forceinline__ float frame_energy_smem(const float *__restrict__ ybu
         for (int s8 = 4 * seg; s8 < 4 * seg + 4; ++s8) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) sum = energy_acc4(sum, yp[9 * s8 + j]);   // 8 float4 of data + 1 of padding per 32 samples
+            if (VAD_WARPS == 2 && (s8 & 1)) between();                            // (a chain that may take two steps must serve fills more often)
         }
-        between();
+        if (VAD_WARPS == 1) between();
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) sum = energy_acc4(sum, yp[9 * 12 + j]);           // samples 384..399
@@ -954,13 +959,14 @@ __device__ __forceinline__ void role_mel(FusedSmem &sm, const FusedParams &P, in
 }
 
 template <bool QUARTERS>
-__device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, int lane)
+__device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, int lane, int vidx)
 {
     // Two cursors.  FILLS (lane 0): the bulk copy of a half step is issued as soon as the resampler warps have
     // released its stage buffer -- blocking for the step the resamplers need next, and opportunistically (one
     // non-blocking test between the 128-sample segments of the energy chains) for the steps after it, so that a
     // long chain never delays a fill.  ENERGIES: the 32 frames of the previous step once its buffer is full.
     const bool chains = P.do_energy && P.energy;
+    if (vidx != 0 && !chains) return;                       // a second V warp only takes energy chains (of the odd steps)
     AF_STATS_DECL
     // fill cursor (lane 0): tile, step, half.  The descriptors (source pointer, byte count, staged range) were planned
     // per tile on the host; the next one is fetched right after a fill is issued, so that issuing a fill is a
@@ -969,7 +975,7 @@ __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, in
     // quarters (fill[parts * step + part] = fill[2 * pair + half]), so a pair index works like the step index did.
     uint32_t tile_f = blockIdx.x, g_f = 0, it_f = 0, steps_f = 0;   // pair inside the tile, pairs issued so far, pairs of the tile
     int h_f = 0;
-    bool fill_live = tile_f < P.n_tiles;
+    bool fill_live = vidx == 0 && tile_f < P.n_tiles;
     FillDesc d_next{};
     auto fetch_desc = [&]() {
         const uint4 *src = reinterpret_cast<const uint4 *>(&P.tiles[tile_f].fill[2 * g_f + h_f]);
@@ -1010,16 +1016,18 @@ __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, in
         if (live) t = tile_geo(P, tile, &n_frames);
         const uint32_t n_steps = live ? t.n_steps : 1u;        // one drain iteration after the last tile
         for (uint32_t g = 0; g < n_steps; ++g) {
-            if (live) {
-                // the fills of the earlier steps and the first pair of step `it` are out (a second pair, if any, needs the
-                // resampler warps to release the buffers first: it goes out through service() or the next trip here)
-                if (lane == 0) while (fill_live && it_f <= pairs_before) issue_next(true);
-                __syncwarp();
-            } else {
-                if (lane == 0) while (fill_live) issue_next(true);      // drain trip: the last step's later parts, if any
+            if (vidx == 0) {
+                if (live) {
+                    // the fills of the earlier steps and the first pair of step `it` are out (a second pair, if any, needs the
+                    // resampler warps to release the buffers first: it goes out through service() or the next trip here)
+                    if (lane == 0) while (fill_live && it_f <= pairs_before) issue_next(true);
+                } else {
+                    if (lane == 0) while (fill_live) issue_next(true);      // drain trip: the last step's later parts, if any
+                }
                 __syncwarp();
             }
-            if (have_prev) {
+            // with two V warps, V0 takes the even steps (ybuf[0]) and V1 the odd ones: a chain then has two steps of time
+            if (have_prev && (VAD_WARPS == 1 || !chains || (prev_it & 1u) == (uint32_t)vidx)) {
                 const int b = (int)(prev_it & 1u);
                 AF_WAIT(&sm.y_full[b], (prev_it >> 1) & 1u, 1);
                 if (chains) {
@@ -1224,7 +1232,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
     const WarpRole wr = warp_role(P.layout, warp);
     if (wr.role == ROLE_F) role_fft(sm, P, wr.index, lane);
     else if (wr.role == ROLE_M) role_mel(sm, P, wr.index, lane);
-    else if (wr.role == ROLE_V) role_vad<QUARTERS>(sm, P, lane);
+    else if (wr.role == ROLE_V) role_vad<QUARTERS>(sm, P, lane, wr.index);
     else role_resample<QUARTERS>(sm, P, wr.index * 32 + lane, lane);
 
     // every role has drained its pipeline: release the tensor memory
