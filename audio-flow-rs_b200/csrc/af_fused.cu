@@ -95,6 +95,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, u
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
 {
+#ifdef AF_WAIT_SLEEP
+    // poll with an explicit back-off: the "suspended" try_wait below comes back after a few cycles, so a waiting warp
+    // spins at ~5 instructions + 2 barrier reads per 8 cycles (ncu: 50+ trips per wait) and takes issue slots and
+    // shared-memory requests from the working warps
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "WAIT_%=:\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity), "n"(AF_WAIT_SLEEP)
+        : "memory");
+#else
     // try_wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint
     // expires), so waiting warps do not take issue slots from the working ones
     asm volatile(
@@ -105,6 +122,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         "}" ::"r"(smem_u32(bar)),
         "r"(parity), "r"(1000000u)
         : "memory");
+#endif
 }
 // non-blocking phase test
 __device__ __forceinline__ bool mbar_test(unsigned long long *bar, uint32_t parity)
@@ -167,8 +185,6 @@ __device__ unsigned long long g_pipe_stats[32];
 #define AF_STATS_FLUSH(role, lane)
 #endif
 
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---- tensor memory (TMEM) as a per-lane constant store -------------------------------------------------------
 // The FFT warps need 74 per-lane constants per frame pair (window samples, pass-1 and Hermitian-split twiddles).
