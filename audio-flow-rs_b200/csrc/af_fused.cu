@@ -19,6 +19,7 @@
 // vad.rs:157-168; the STFT/mel stages are spec-defined.  The sequential EMA/state
 // machine of vad.rs:101-153 runs in the scan kernels (af_kernels.cu).
 #include <atomic>
+#include <type_traits>
 
 #include "af_device.cuh"
 #include "af_launch.h"
@@ -1107,6 +1108,11 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
         // parts per step: a compile-time 2 in the kernel instance for batches without quarter-staged streams
         const uint32_t parts = QUARTERS ? t.parts : 2u;
 
+        // The steps of the tile, instantiated twice: HOT = 48 kHz mono f32 (its interior parts go straight to the quad loop and
+        // nothing of the other formats is in the loop), and everything else.  One loop for both made the 48 kHz path pay
+        // (register allocation) for every addition to the general one.
+        auto run_steps = [&](auto hot_tag) {
+        constexpr bool HOT = decltype(hot_tag)::value;
         for (uint32_t g = 0; g < t.n_steps; ++g, ++it) {
             const int b = (int)(it & 1u);
             const uint32_t toff = g * STEP_SAMPLES;
@@ -1134,12 +1140,14 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
 #pragma unroll 1
             for (int k = 0; k < (int)parts; ++k) {
                 const int h = k & 1;                            // parts alternate between the two stage buffers
-                AF_WAIT(&sm.stage_full[h], (uses0 + ((uint32_t)k >> 1)) & 1u, 1);
                 const int i_lo = part_lo(g, (int)parts, k), i_hi = part_end((int)parts, k);
+                AF_WAIT(&sm.stage_full[h], (uses0 + ((uint32_t)k >> 1)) & 1u, 1);
                 AF_TIC2
-                if (hot && sm.st_interior[h] == 1u) {
+                if (HOT && sm.st_interior[h] == 1u) {
                     resample_quads_48k(reinterpret_cast<const float *>(sm.stage[h]) + (tile_k + 3 * (int)toff - 1 - (int)(uint32_t)sm.st_lo[h]),
                                        out.yb, out.pcm + out.base, lim4, i_lo, i_hi, rtid);
+                } else if (HOT) {
+                    resample_dispatch<K_F32_1>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid);
                 } else {
                     switch (kind) {
                     case K_F32_1: resample_dispatch<K_F32_1>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
@@ -1166,6 +1174,9 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
             warp_arrive(&sm.y_full[b], lane);
             uses0 += parts >> 1;
         }
+        };
+        if (hot) run_steps(std::true_type{});
+        else run_steps(std::false_type{});
     }
     AF_STATS_FLUSH(3, lane);
 }
