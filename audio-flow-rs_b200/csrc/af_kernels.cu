@@ -1,6 +1,7 @@
 // af_kernels.cu -- the small kernels around the fused path: compat objects (to_mono, chunked
 // resampling, single-detector VAD), generic frame energies, the sequential VAD scan, PCM16
 // encode and VAD segmentation.
+#include <cstdio>
 #include "af_device.cuh"
 #include "af_launch.h"
 
@@ -334,6 +335,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
     VadMachine carry_m{(uint32_t)v.state, (uint32_t)v.silence_frames, (uint32_t)v.speech_frames};
     const bool aligned_out = out && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 
+#ifdef AF_SCAN_PROFILE
+    long long tp[6]; tp[0] = clock64();
+#define AF_SCAN_T(i) tp[i] = clock64();
+#else
+#define AF_SCAN_T(i)
+#endif
     for (uint32_t b0 = 0; b0 < T; b0 += SCAN_BLOCK) {
         const uint32_t n = min(SCAN_BLOCK, T - b0);
         const uint32_t n_chunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK, n_words = (n + 31) / 32;
@@ -343,6 +350,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
         const float *eb = s_e + lead;                        // eb[f - b0] = e[f] for f in [b0 - lead, b0 + n)
         for (uint32_t i = tid; i < lead + n; i += SCAN_THREADS) s_e[i] = e[b0 - lead + i];
         __syncthreads();
+        AF_SCAN_T(1)
         // ---- phase 1: EMA chunks (speculative start) -> decision bits ----
         for (uint32_t c = tid; c < n_chunks; c += SCAN_THREADS) {
             const uint32_t f_begin = b0 + c * SCAN_CHUNK, f_end = min(f_begin + SCAN_CHUNK, b0 + n);
@@ -369,6 +377,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
             s_end[c] = sm;
         }
         __syncthreads();
+        AF_SCAN_T(2)
         // ---- verify every boundary bit for bit ----
         for (uint32_t c = 1 + tid; c < n_chunks; c += SCAN_THREADS)
             if (__float_as_uint(s_spec[c]) != __float_as_uint(s_end[c - 1])) s_bad = 1;
@@ -390,6 +399,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
             }
             __syncthreads();
         }
+        AF_SCAN_T(3)
         // ---- phase 2: one thread walks the words, recording the machine state at every word boundary ----
         if (tid == 0) {
             VadMachine m = carry_m;
@@ -401,6 +411,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
             carry_m = m;
         }
         __syncthreads();
+        AF_SCAN_T(4)
         // ---- phase 3: every thread expands its words into state bytes ----
         if (out) {
             for (uint32_t w = tid; w < n_words; w += SCAN_THREADS) {
@@ -444,6 +455,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
         if (J.state_io) J.state_io[s] = v;
         if (J.final_out) J.final_out[s] = v;
     }
+#ifdef AF_SCAN_PROFILE
+    AF_SCAN_T(5)
+    if (tid == 0 && (s == 0 || s == 200)) printf("[scan-profile] stream %u: load %lld  ema %lld  verify %lld  walk %lld  expand %lld cycles\n", s, tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4]);
+#endif
 }
 
 // ---- long streams: many CTAs per stream ------------------------------------------------------------------------
