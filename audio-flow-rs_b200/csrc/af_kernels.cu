@@ -251,6 +251,13 @@ constexpr uint32_t SCAN_CHUNK = 64;                  // frames per EMA chunk (2 
 constexpr uint32_t SCAN_BLOCK = 8192;                // frames per block of a long stream (128 chunks, 256 words)
 constexpr uint32_t SCAN_THREADS = 128;
 constexpr uint32_t SCAN_WARM_MAX = 512;              // longest warm-up the host selects (scan_warmup)
+// The staged energies are read by one thread per chunk, i.e. SCAN_CHUNK (= two banks' worth of) floats apart: without
+// padding every lane of a warp hits the same bank (measured: 112 cycles per EMA step).  One pad word per SCAN_CHUNK floats
+// puts the lanes on consecutive banks.
+__host__ __device__ constexpr uint32_t epad(uint32_t i) { return i + i / SCAN_CHUNK; }
+constexpr uint32_t SCAN_E_FLOATS = epad(SCAN_WARM_MAX + SCAN_BLOCK) + 1;
+// EB(x) = e[b0 + x] for x in [-lead, n): the block's energies (and the warm-up in front of it) staged in s_e
+#define EB(x) s_e[epad((uint32_t)((int)lead + (int)(x)))]
 
 struct EmitMask {          // collects the states of one word as two bit masks (Speech, Ending)
     uint32_t speech = 0, ending = 0;
@@ -312,12 +319,46 @@ __device__ __forceinline__ void vad_machine_word_t(VadMachine &m, uint32_t bits,
     }
 }
 
+// EMA over frames [f0, f1) of the staged energies (x = f - b0), strictly sequential (vad.rs:101-106); the loads of four
+// steps are issued ahead of their dependent multiply-add chain.  `ema_bits` also collects up to 32 decision bits.
+#define AF_EMA_STEP(sm, ev) __fadd_rn(__fmul_rn(alpha, (ev)), __fmul_rn(beta, (sm)))
+__device__ __forceinline__ float ema_run(const float *s_e, uint32_t lead, int x0, int x1, float sm, float alpha, float beta)
+{
+    int x = x0;
+    for (; x + 4 <= x1; x += 4) {
+        const float e0 = EB(x), e1 = EB(x + 1), e2 = EB(x + 2), e3 = EB(x + 3);
+        sm = AF_EMA_STEP(sm, e0); sm = AF_EMA_STEP(sm, e1); sm = AF_EMA_STEP(sm, e2); sm = AF_EMA_STEP(sm, e3);
+    }
+    for (; x < x1; ++x) sm = AF_EMA_STEP(sm, EB(x));
+    return sm;
+}
+__device__ __forceinline__ uint32_t ema_bits(const float *s_e, uint32_t lead, int x0, uint32_t m, float &sm_io, float alpha, float beta,
+                                             float e_min, bool use_smoothed)
+{
+    float sm = sm_io;
+    uint32_t bits = 0, j = 0;
+    for (; j + 4 <= m; j += 4) {
+        const float e0 = EB(x0 + (int)j), e1 = EB(x0 + (int)j + 1), e2 = EB(x0 + (int)j + 2), e3 = EB(x0 + (int)j + 3);
+        sm = AF_EMA_STEP(sm, e0); bits |= ((use_smoothed ? sm : e0) >= e_min ? 1u : 0u) << j;
+        sm = AF_EMA_STEP(sm, e1); bits |= ((use_smoothed ? sm : e1) >= e_min ? 1u : 0u) << (j + 1);
+        sm = AF_EMA_STEP(sm, e2); bits |= ((use_smoothed ? sm : e2) >= e_min ? 1u : 0u) << (j + 2);
+        sm = AF_EMA_STEP(sm, e3); bits |= ((use_smoothed ? sm : e3) >= e_min ? 1u : 0u) << (j + 3);
+    }
+    for (; j < m; ++j) {
+        const float ev = EB(x0 + (int)j);
+        sm = AF_EMA_STEP(sm, ev);
+        bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
+    }
+    sm_io = sm;
+    return bits;
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const ScanJob J, uint32_t warm)
 {
     __shared__ uint32_t s_bits[SCAN_BLOCK / 32];
     __shared__ uint32_t s_entry[SCAN_BLOCK / 32][3];
     __shared__ float s_spec[SCAN_BLOCK / SCAN_CHUNK], s_end[SCAN_BLOCK / SCAN_CHUNK];
-    __shared__ float s_e[SCAN_WARM_MAX + SCAN_BLOCK];   // energies of [b0 - lead, b0 + n)
+    __shared__ float s_e[SCAN_E_FLOATS];                // energies of [b0 - lead, b0 + n), padded (epad)
     __shared__ int s_bad;
     const uint32_t s = blockIdx.x, tid = threadIdx.x;
     const uint32_t T = J.n_frames ? J.n_frames[s] : J.n_frames_all;
@@ -347,8 +388,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
         if (tid == 0) s_bad = 0;
         // ---- phase 0: the block's energies and the warm-up before it -> shared memory ----
         const uint32_t lead = min(warm, b0);                 // frames staged in front of the block
-        const float *eb = s_e + lead;                        // eb[f - b0] = e[f] for f in [b0 - lead, b0 + n)
-        for (uint32_t i = tid; i < lead + n; i += SCAN_THREADS) s_e[i] = e[b0 - lead + i];
+#pragma unroll 8
+        for (uint32_t i = tid; i < lead + n; i += SCAN_THREADS) s_e[epad(i)] = e[b0 - lead + i];
         __syncthreads();
         AF_SCAN_T(1)
         // ---- phase 1: EMA chunks (speculative start) -> decision bits ----
@@ -361,18 +402,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
                 uint32_t w0;
                 if (f_begin >= warm) { w0 = f_begin - warm; sm = 0.0f; }
                 else { w0 = 0; sm = v.smoothed; }
-                for (uint32_t f = w0; f < f_begin; ++f) sm = __fadd_rn(__fmul_rn(alpha, eb[(int)f - (int)b0]), __fmul_rn(beta, sm));
+                sm = ema_run(s_e, lead, (int)w0 - (int)b0, (int)f_begin - (int)b0, sm, alpha, beta);
                 s_spec[c] = sm;
             }
             for (uint32_t f = f_begin; f < f_end; f += 32) {
                 const uint32_t m = min(32u, f_end - f);
-                uint32_t bits = 0;
-                for (uint32_t j = 0; j < m; ++j) {
-                    const float ev = eb[f - b0 + j];
-                    sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
-                    bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
-                }
-                s_bits[(f - b0) >> 5] = bits;
+                s_bits[(f - b0) >> 5] = ema_bits(s_e, lead, (int)(f - b0), m, sm, alpha, beta, e_min, use_smoothed);
             }
             s_end[c] = sm;
         }
@@ -389,7 +424,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
                     const uint32_t m = min(32u, n - w * 32);
                     uint32_t bits = 0;
                     for (uint32_t j = 0; j < m; ++j) {
-                        const float ev = eb[w * 32 + j];
+                        const float ev = EB(w * 32 + j);
                         sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
                         bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
                     }
@@ -404,9 +439,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
         if (tid == 0) {
             VadMachine m = carry_m;
             EmitNone none;
+            uint32_t next_bits = s_bits[0];
             for (uint32_t w = 0; w < n_words; ++w) {
+                const uint32_t bits = next_bits, m_n = min(32u, n - w * 32);
+                if (w + 1 < n_words) next_bits = s_bits[w + 1];                     // (the load overlaps this word's walk)
                 s_entry[w][0] = m.st; s_entry[w][1] = m.sil; s_entry[w][2] = m.spk;
-                vad_machine_word_t(m, s_bits[w], min(32u, n - w * 32), none, timeout, minsp);
+                // whole words of silence in Silence, or of speech in Speech, leave the machine where it is (up to the count)
+                if (m.st == 0u && bits == 0u) continue;
+                if (m.st == 1u && m_n == 32u && bits == 0xffffffffu) { m.spk += 32u; m.sil = 0u; continue; }
+                vad_machine_word_t(m, bits, m_n, none, timeout, minsp);
             }
             carry_m = m;
         }
@@ -500,7 +541,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_long_a_kernel(const ScanJ
 {
     __shared__ uint32_t s_bits[SCAN_BLOCK / 32];
     __shared__ float s_spec[SCAN_BLOCK / SCAN_CHUNK], s_end[SCAN_BLOCK / SCAN_CHUNK];
-    __shared__ float s_e[SCAN_WARM_MAX + SCAN_BLOCK];
+    __shared__ float s_e[SCAN_E_FLOATS];
     __shared__ int s_bad;
     const uint32_t blk = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
     const uint32_t T = J.n_frames ? J.n_frames[s] : J.n_frames_all;
@@ -516,8 +557,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_long_a_kernel(const ScanJ
     const uint32_t n_chunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK, n_words = (n + 31) / 32;
     if (tid == 0) s_bad = 0;
     const uint32_t lead = min(warm, b0);
-    const float *eb = s_e + lead;
-    for (uint32_t i = tid; i < lead + n; i += SCAN_THREADS) s_e[i] = e[b0 - lead + i];
+#pragma unroll 8
+    for (uint32_t i = tid; i < lead + n; i += SCAN_THREADS) s_e[epad(i)] = e[b0 - lead + i];
     __syncthreads();
     // EMA chunks: every chunk but the stream's very first starts from a warm-up (fresh detector: the stream starts at 0)
     for (uint32_t c = tid; c < n_chunks; c += SCAN_THREADS) {
@@ -525,18 +566,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_long_a_kernel(const ScanJ
         float sm = 0.0f;
         if (f_begin != 0) {
             const uint32_t w0 = f_begin >= warm ? f_begin - warm : 0u;
-            for (uint32_t f = w0; f < f_begin; ++f) sm = __fadd_rn(__fmul_rn(alpha, eb[(int)f - (int)b0]), __fmul_rn(beta, sm));
+            sm = ema_run(s_e, lead, (int)w0 - (int)b0, (int)f_begin - (int)b0, sm, alpha, beta);
         }
         s_spec[c] = sm;
         for (uint32_t f = f_begin; f < f_end; f += 32) {
             const uint32_t m = min(32u, f_end - f);
-            uint32_t bits = 0;
-            for (uint32_t j = 0; j < m; ++j) {
-                const float ev = eb[f - b0 + j];
-                sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
-                bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
-            }
-            s_bits[(f - b0) >> 5] = bits;
+            s_bits[(f - b0) >> 5] = ema_bits(s_e, lead, (int)(f - b0), m, sm, alpha, beta, e_min, use_smoothed);
         }
         s_end[c] = sm;
     }
@@ -550,7 +585,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_long_a_kernel(const ScanJ
             const uint32_t m = min(32u, n - w * 32);
             uint32_t bits = 0;
             for (uint32_t j = 0; j < m; ++j) {
-                const float ev = eb[w * 32 + j];
+                const float ev = EB(w * 32 + j);
                 sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
                 bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
             }
