@@ -21,6 +21,17 @@
 #include <atomic>
 #include <type_traits>
 
+// This file is compiled TWICE (Makefile).  The default translation unit holds the kernel all-48-kHz-mono-f32 batches run
+// (cfg2): its resampler role is one loop over every kind of tile (role_resample_single).  With -DAF_FUSED_SPLIT_TU it
+// holds the kernel of every other batch (cfg3, cfg4, sessions with other formats): the same roles, but the resampler role
+// instantiates the steps of a tile twice -- 48 kHz mono f32 / everything else (role_resample_split).  Two units instead of
+// one template parameter because the hot kernel is sensitive to what else is compiled next to it: as a third instance
+// of one template it came out 3-7 % slower on cfg2 (0.585-0.595 vs 0.555 ms), in a unit of its own it is the kernel it was.
+#ifdef AF_FUSED_SPLIT_TU
+#define af_fused_kernel af_fused_split_kernel
+#define g_pipe_stats g_pipe_stats_split
+#endif
+
 #include "af_device.cuh"
 #include "af_launch.h"
 
@@ -1068,8 +1079,117 @@ __device__ __forceinline__ void role_vad(FusedSmem &sm, const FusedParams &P, in
     AF_STATS_FLUSH(2, lane);
 }
 
+#ifndef AF_FUSED_SPLIT_TU
+// ---- R role, one loop for every kind of tile: the kernel all-48-kHz batches run (default translation unit).  Kept as it was when
+// the two-instantiation loop below was introduced: the same logic wrapped differently compiles to a kernel that is 2-7 %
+// slower on cfg2 (0.555 vs 0.565 / 0.595 ms measured), so the source of the fast one is left alone.
 template <bool QUARTERS>
-__device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &P, int rtid, int lane)
+__device__ __forceinline__ void role_resample_single(FusedSmem &sm, const FusedParams &P, int rtid, int lane)
+{
+    uint32_t it = 0;
+    uint32_t uses0 = 0;                                     // uses of EACH stage buffer before the current step (see role_vad: fills0)
+    AF_STATS_DECL
+    // the descriptor of a tile is fetched one tile ahead with cp.async into the warp's other slot (RsTile)
+    const int w = rtid >> 5;
+    auto prefetch = [&](uint32_t tile, int slot) {
+        if (tile < P.n_tiles && lane < 7) {
+            const char *src = reinterpret_cast<const char *>(P.tiles + tile) + (lane < 2 ? 16 * lane : (int)offsetof(TileDev, sdesc) + 16 * (lane - 2));
+            cp_async16(reinterpret_cast<char *>(&sm.rs[slot][w]) + 16 * lane, src);
+        }
+    };
+    int slot = 0;
+    prefetch(blockIdx.x, 0);
+    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, slot ^= 1) {
+        AF_TIC
+        cp_async_wait_all();
+        __syncwarp();                                   // the copy is visible to the warp; every lane is done with the other slot
+        const RsTile &rt = sm.rs[slot][w];
+        prefetch(tile + gridDim.x, slot ^ 1);
+        TileGeo t;
+        t.stream = rt.stream_idx; t.n_tile0 = rt.tile * TILE_SAMPLES; t.tile_end = rt.tile_end; t.n_steps = rt.n_steps;
+        t.n_frames = rt.n_frames; t.parts = rt.parts;
+        AF_TOC(2)
+        const StreamDev &s = rt.stream;
+        int kind = K_GENERIC;
+        if (s.channels == 1) kind = s.format == FMT_F32 ? K_F32_1 : K_I16_1;
+        else if (s.channels == 2) kind = s.format == FMT_F32 ? K_F32_2 : K_I16_2;
+        float *pcm_row = P.pcm ? P.pcm + (uint64_t)t.stream * P.pcm_stride : nullptr;
+        // does this tile's fast path hand out output quads to fixed owner threads (see resample_half_fast)?
+        const bool quad_tile = s.mode != RS_PASSTHROUGH && ((kind == K_F32_1 && s.q == 1 && s.p == 3) || (kind != K_GENERIC && s.q > 1));
+        bool prev_quads = false;
+        // the hot case -- 48 kHz mono f32 -- bypasses the format dispatch: its interior half steps go straight to the quad loop
+        const bool hot = kind == K_F32_1 && s.mode != RS_PASSTHROUGH && s.q == 1 && s.p == 3;
+        const int tile_k = rt.tile_k;
+        // parts per step: a compile-time 2 in the kernel instance for batches without quarter-staged streams
+        const uint32_t parts = QUARTERS ? t.parts : 2u;
+
+        for (uint32_t g = 0; g < t.n_steps; ++g, ++it) {
+            const int b = (int)(it & 1u);
+            const uint32_t toff = g * STEP_SAMPLES;
+            YSink out{sm.ybuf[b], pcm_row, t.n_tile0 + toff, t.tile_end, P.neg_zero};
+            const int lim4 = pcm_row ? (int)min((uint32_t)YLEN, out.wr_end - min(out.wr_end, out.base)) - 4 : -(1 << 30);
+            AF_WAIT(&sm.y_empty[b], ((it >> 1) & 1u) ^ 1u, 0);   // FFT and VAD warps are done with this buffer
+            AF_TIC2
+            if (g > 0) {
+                // the 240-sample overlap with the previous step
+                const float *prev = sm.ybuf[b ^ 1];
+                if (prev_quads) {
+                    // the quad paths give every output quad a fixed owner thread: each thread carries the quad it wrote
+                    // itself in the previous step -- no synchronisation among the resampler warps
+                    constexpr int QS = 4 * RS_THREADS;
+                    int c4 = LAST_PART_LO2 + 4 * rtid;
+                    c4 += ((STEP_SAMPLES - c4 + QS - 1) / QS) * QS;           // first own quad at or after STEP_SAMPLES
+                    if (c4 < YLEN)
+                        *reinterpret_cast<float4 *>(out.yb + ypad(c4 - STEP_SAMPLES)) = *reinterpret_cast<const float4 *>(prev + ypad(c4));
+                } else {
+                    named_bar_sync(1, RS_THREADS);                            // written by all resampler threads: sync first
+                    for (int i = rtid; i < CARRY; i += RS_THREADS) out.yb[ypad(i)] = prev[ypad(STEP_SAMPLES + i)];
+                }
+            }
+            AF_TOC(3)
+#pragma unroll 1
+            for (int k = 0; k < (int)parts; ++k) {
+                const int h = k & 1;                            // parts alternate between the two stage buffers
+                AF_WAIT(&sm.stage_full[h], (uses0 + ((uint32_t)k >> 1)) & 1u, 1);
+                const int i_lo = part_lo(g, (int)parts, k), i_hi = part_end((int)parts, k);
+                AF_TIC2
+                if (hot && sm.st_interior[h] == 1u) {
+                    resample_quads_48k(reinterpret_cast<const float *>(sm.stage[h]) + (tile_k + 3 * (int)toff - 1 - (int)(uint32_t)sm.st_lo[h]),
+                                       out.yb, out.pcm + out.base, lim4, i_lo, i_hi, rtid);
+                } else {
+                    switch (kind) {
+                    case K_F32_1: resample_dispatch<K_F32_1>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                    case K_I16_1: resample_dispatch<K_I16_1>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                    case K_F32_2: resample_dispatch<K_F32_2>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                    case K_I16_2: resample_dispatch<K_I16_2>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                    default: resample_dispatch<K_GENERIC>(sm, rt, h, s, out, toff, i_lo, i_hi, rtid); break;
+                    }
+                }
+                AF_TOC(4)
+                if (k == (int)parts - 1) prev_quads = quad_tile && parts == 2u && sm.st_interior[1] != 0u;   // (read before the stage is released)
+                warp_arrive(&sm.stage_empty[h], lane);          // this warp no longer reads stage[h] or its metadata
+            }
+            if (rtid == 0) {
+                // what this step buffer holds, for the FFT and mel warps (they keep no tile state)
+                const uint32_t f0 = (t.n_tile0 / HOP) + g * SF, n_frames = t.n_frames;
+                StepInfo info;
+                info.lm_dst = (P.logmel && P.n_mels) ? P.logmel + (uint64_t)t.stream * P.logmel_stride + (uint64_t)f0 * P.n_mels : nullptr;
+                info.n_valid = f0 < n_frames ? (int)min((uint32_t)SF, n_frames - f0) : 0;
+                if (g + 1 == t.n_steps && tile + gridDim.x >= P.n_tiles) info.n_valid |= STEP_LAST;
+                info.pad_ = 0;
+                sm.yinfo[b] = info;
+            }
+            warp_arrive(&sm.y_full[b], lane);
+            uses0 += parts >> 1;
+        }
+    }
+    AF_STATS_FLUSH(3, lane);
+}
+
+#else
+// ---- R role for batches that also hold other tiles than 48 kHz mono f32 (-DAF_FUSED_SPLIT_TU) ----
+template <bool QUARTERS>
+__device__ __forceinline__ void role_resample_split(FusedSmem &sm, const FusedParams &P, int rtid, int lane)
 {
     uint32_t it = 0;
     uint32_t uses0 = 0;                                     // uses of EACH stage buffer before the current step (see role_vad: fills0)
@@ -1109,8 +1229,8 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
         const uint32_t parts = QUARTERS ? t.parts : 2u;
 
         // The steps of the tile, instantiated twice: HOT = 48 kHz mono f32 (its interior parts go straight to the quad loop and
-        // nothing of the other formats is in the loop), and everything else.  One loop for both made the 48 kHz path pay
-        // (register allocation) for every addition to the general one.
+        // nothing of the other formats is in the loop), and everything else.  In one shared loop the general path paid --
+        // through register allocation -- for the hot one and the other way round (cfg3 13.1 -> 12.4 ms).
         auto run_steps = [&](auto hot_tag) {
         constexpr bool HOT = decltype(hot_tag)::value;
         for (uint32_t g = 0; g < t.n_steps; ++g, ++it) {
@@ -1180,6 +1300,8 @@ __device__ __forceinline__ void role_resample(FusedSmem &sm, const FusedParams &
     }
     AF_STATS_FLUSH(3, lane);
 }
+
+#endif
 
 // QUARTERS: some stream of the batch stages its input in quarter steps (f32 stereo); the other instance keeps the
 // two-parts-per-step constants folded in (measured: the general one costs mono batches 1.4 %, 2.8 % with the VAD on)
@@ -1260,7 +1382,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
     if (wr.role == ROLE_F) role_fft(sm, P, wr.index, lane);
     else if (wr.role == ROLE_M) role_mel(sm, P, wr.index, lane);
     else if (wr.role == ROLE_V) role_vad<QUARTERS>(sm, P, lane, wr.index);
-    else role_resample<QUARTERS>(sm, P, wr.index * 32 + lane, lane);
+#ifdef AF_FUSED_SPLIT_TU
+    else role_resample_split<QUARTERS>(sm, P, wr.index * 32 + lane, lane);
+#else
+    else role_resample_single<QUARTERS>(sm, P, wr.index * 32 + lane, lane);
+#endif
 
     // every role has drained its pipeline: release the tensor memory
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1268,10 +1394,16 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) af_fused_kernel(const FusedP
     if (warp == 0) tmem_dealloc(sm.tmem_base);
 }
 
+#ifndef AF_FUSED_SPLIT_TU
 size_t fused_smem_bytes() { return sizeof(FusedSmem); }
+#endif
 
-// debugging aid: copies (and clears) the pipeline statistics; all zero unless built with -DAF_PIPE_STATS
-cudaError_t fused_pipe_stats(unsigned long long out[32])
+// debugging aid: copies (and clears) the pipeline statistics of both kernels; all zero unless built with -DAF_PIPE_STATS
+#ifdef AF_FUSED_SPLIT_TU
+cudaError_t fused_pipe_stats_split(unsigned long long out[32])
+#else
+static cudaError_t fused_pipe_stats_own(unsigned long long out[32])
+#endif
 {
 #ifdef AF_PIPE_STATS
     cudaError_t e = cudaMemcpyFromSymbol(out, g_pipe_stats, sizeof(unsigned long long) * 32);
@@ -1283,18 +1415,35 @@ cudaError_t fused_pipe_stats(unsigned long long out[32])
     return cudaSuccess;
 #endif
 }
-
-cudaError_t launch_fused(const FusedParams &P, int n_ctas, cudaStream_t st)
+#ifndef AF_FUSED_SPLIT_TU
+cudaError_t fused_pipe_stats(unsigned long long out[32])
 {
-    // the attribute is per device: one flag per GPU of the process (af_init_multi drives several from one process)
+    unsigned long long other[32];
+    cudaError_t e = fused_pipe_stats_own(out);
+    if (e == cudaSuccess) e = fused_pipe_stats_split(other);
+    for (int i = 0; i < 32 && e == cudaSuccess; ++i) out[i] += other[i];
+    return e;
+}
+#endif
+
+// the shared-memory attribute is per device: one flag per GPU of the process (af_init_multi drives several from one process)
+template <class K>
+static cudaError_t fused_attr(K kernel)
+{
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+}
+
+#ifdef AF_FUSED_SPLIT_TU
+cudaError_t launch_fused_split(const FusedParams &P, int n_ctas, cudaStream_t st)
+{
     static std::atomic<bool> attr_set[AF_MAX_GPUS_INTERNAL] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= AF_MAX_GPUS_INTERNAL) return cudaErrorInvalidDevice;
     if (!attr_set[dev].load(std::memory_order_acquire)) {
-        e = cudaFuncSetAttribute(af_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(af_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+        e = fused_attr(af_fused_kernel<false>);
+        if (e == cudaSuccess) e = fused_attr(af_fused_kernel<true>);
         if (e != cudaSuccess) return e;
         attr_set[dev].store(true, std::memory_order_release);
     }
@@ -1302,5 +1451,23 @@ cudaError_t launch_fused(const FusedParams &P, int n_ctas, cudaStream_t st)
     else af_fused_kernel<false><<<n_ctas, FUSED_THREADS, sizeof(FusedSmem), st>>>(P);
     return cudaGetLastError();
 }
+#else
+cudaError_t launch_fused(const FusedParams &P, int n_ctas, cudaStream_t st, bool split)
+{
+    if (split || P.quarters) return launch_fused_split(P, n_ctas, st);
+    static std::atomic<bool> attr_set[AF_MAX_GPUS_INTERNAL] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= AF_MAX_GPUS_INTERNAL) return cudaErrorInvalidDevice;
+    if (!attr_set[dev].load(std::memory_order_acquire)) {
+        e = fused_attr(af_fused_kernel<false>);
+        if (e != cudaSuccess) return e;
+        attr_set[dev].store(true, std::memory_order_release);
+    }
+    af_fused_kernel<false><<<n_ctas, FUSED_THREADS, sizeof(FusedSmem), st>>>(P);
+    return cudaGetLastError();
+}
+#endif
 
 }  // namespace af

@@ -77,7 +77,12 @@ cudaError_t fused_pipe_stats(unsigned long long out[32]);
 cudaError_t launch_session_tick(const SessionIngest &I, const SessionResample &R, uint32_t n_streams, cudaStream_t st);
 cudaError_t launch_session_setup(StreamDev *tab, TileDev *tiles, uint32_t n_streams, uint32_t n, uint32_t n_frames, uint32_t n_vad,
                                  cudaStream_t st);
-cudaError_t launch_fused(const FusedParams &P, int n_ctas, cudaStream_t st);
+// split: the batch holds tiles other than 48 kHz mono f32 -> 16 kHz; such batches (and quarter-staged ones) run the
+// kernel of the second translation unit of af_fused.cu (AF_FUSED_SPLIT_TU), whose resampler role keeps the hot and the
+// general tiles in separate loops
+cudaError_t launch_fused(const FusedParams &P, int n_ctas, cudaStream_t st, bool split = false);
+cudaError_t launch_fused_split(const FusedParams &P, int n_ctas, cudaStream_t st);
+cudaError_t fused_pipe_stats_split(unsigned long long out[32]);
 cudaError_t launch_peak(const float *y, uint64_t y_stride, uint32_t n, uint32_t n_streams, float *peak, cudaStream_t st);
 
 cudaError_t launch_to_mono(const float *in, uint64_t n_samples, uint32_t channels, float *out, uint64_t n_frames,

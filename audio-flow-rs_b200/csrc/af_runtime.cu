@@ -756,6 +756,7 @@ struct SubBatch {                     // a group of streams resident on the devi
     size_t in_bytes = 0;
     uint32_t *d_scan = nullptr;       // long streams: scratch of the many-CTA VAD scan (launch_vad_scan)
     bool quarters = false;            // some stream stages its input in quarter steps (f32 stereo)
+    bool split = false;               // some stream is not 48 kHz mono f32 -> 16 kHz (FusedParams::split)
     uint32_t per_p = 0, per_q = 0;    // p / q of the batch's RS_TABLE streams when the output period fits the kernel's position table
     bool no_merge = false;            // host mode: a merged copy was refused (rows adjacent in memory but separately allocated)
 };
@@ -793,6 +794,7 @@ int build_sub(af_batch *b, SubBatch &sb, const void *slot_in_base)
     sb.h_tiles.clear();
     sb.quarters = false;
     sb.per_p = sb.per_q = 0;
+    sb.split = false;
     std::vector<uint32_t> nf(sb.count), nv(sb.count);
     for (size_t i = 0; i < sb.count; ++i) {
         const HostStream &hs = b->streams[sb.first + i];
@@ -815,6 +817,7 @@ int build_sub(af_batch *b, SubBatch &sb, const void *slot_in_base)
             }
         }
         if (d.staged == 4u) sb.quarters = true;
+        if (!(hs.desc.channels == 1 && hs.desc.format == AF_FMT_F32 && hs.mode != RS_PASSTHROUGH && hs.p == 3 && hs.q == 1)) sb.split = true;
         // positions repeat every q outputs (p inputs): the first table-mode rate of the batch gets the kernel's position table
         if (hs.mode == RS_TABLE && sb.per_q == 0 && hs.q <= (uint32_t)KOFF_MAX && hs.q % 4 == 0 && STEP_SAMPLES % hs.q == 0 && hs.p < 65536) {
             sb.per_p = hs.p; sb.per_q = hs.q;
@@ -867,7 +870,7 @@ int run_sub(af_batch *b, SubBatch &sb, float *pcm, uint64_t pcm_stride, float *l
         P.neg_zero = -0.0f;
         P.per_p = sb.per_p; P.per_q = sb.per_q;
         const int n_ctas = (int)std::min<size_t>(sb.h_tiles.size(), (size_t)cur_ctx().sm_count);   // one persistent CTA per SM
-        AF_CUDA(launch_fused(P, n_ctas, st));
+        AF_CUDA(launch_fused(P, n_ctas, st, sb.split));
         count_launch();
     }
     if (custom_vad) {
