@@ -119,6 +119,8 @@ def load_library():
         "af_vad_smoothed_energy": (C.c_float, [vp]),
         "af_vad_frame_energy": (C.c_int, [fp, sz, fp]),
         "af_pcm16_encode": (C.c_int, [fp, sz, C.POINTER(C.c_int16)]),
+        "af_pcm16_base64_len": (C.c_size_t, [sz]),
+        "af_pcm16_base64": (C.c_int, [fp, sz, C.c_char_p, sz, C.POINTER(C.c_size_t)]),
         "af_pipeline_config_default": (None, [C.POINTER(PipelineConfigC)]),
         "af_pipeline_create": (C.c_int, [C.POINTER(PipelineConfigC), C.POINTER(vp)]),
         "af_pipeline_destroy": (None, [vp]),
@@ -392,6 +394,17 @@ def pcm16_encode(samples) -> np.ndarray:
     out = np.empty(len(x), np.int16)
     _check(load_library().af_pcm16_encode(_fp(x), len(x), out.ctypes.data_as(C.POINTER(C.c_int16))))
     return out
+
+
+def pcm16_base64(samples) -> bytes:
+    """The "audio_base_64" payload of WebSocketClient::send_audio (websocket.rs:244-254): base64 of the PCM16 LE bytes."""
+    L = load_library()
+    x = _f32(samples)
+    cap = int(L.af_pcm16_base64_len(len(x)))
+    buf = C.create_string_buffer(max(cap, 1))
+    n = C.c_size_t(0)
+    _check(L.af_pcm16_base64(_fp(x), len(x), buf, cap, C.byref(n)))
+    return buf.raw[:n.value]
 
 
 # ---------------------------------------------------------------------------------------------

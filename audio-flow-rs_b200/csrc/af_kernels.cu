@@ -866,6 +866,39 @@ __global__ void af_pcm16_kernel(const float *__restrict__ in, uint64_t n, int16_
     }
 }
 
+// ---- f32 -> PCM16 LE -> base64 (websocket.rs:244-254): one thread per 3-byte group = 4 characters, one 32-bit store ----
+__device__ __forceinline__ uint32_t pcm16_of(float v)
+{
+    int r = 0;
+    if (v == v) {
+        v = v < -1.0f ? -1.0f : (v > 1.0f ? 1.0f : v);
+        r = __float2int_rz(__fmul_rn(v, 32767.0f));
+    }
+    return (uint32_t)r & 0xffffu;
+}
+__device__ __forceinline__ uint32_t b64_char(uint32_t v)      // standard alphabet
+{
+    return v < 26u ? 'A' + v : (v < 52u ? 'a' + (v - 26u) : (v < 62u ? '0' + (v - 52u) : (v == 62u ? '+' : '/')));
+}
+__global__ void af_pcm16_base64_kernel(const float *__restrict__ in, uint64_t n, uint32_t *__restrict__ out4)
+{
+    const uint64_t n_bytes = 2 * n, n_groups = (n_bytes + 2) / 3;
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n_groups; g += (uint64_t)gridDim.x * blockDim.x) {
+        // bytes 3g, 3g+1, 3g+2 of the little-endian sample stream: byte k is the low (k even) or high half of sample k / 2
+        const uint64_t k0 = 3 * g, s0 = k0 >> 1;
+        const uint32_t a = pcm16_of(in[s0]);
+        const uint32_t b = s0 + 1 < n ? pcm16_of(in[s0 + 1]) : 0u;
+        // 32 bits of the stream starting at sample s0 (little endian), shifted to byte k0
+        const uint32_t w = (a | (b << 16)) >> (8 * (uint32_t)(k0 & 1));
+        const uint32_t left = (uint32_t)(n_bytes - k0 < 3 ? n_bytes - k0 : 3);          // bytes of this group that exist
+        const uint32_t b0 = w & 0xffu, b1 = left > 1 ? (w >> 8) & 0xffu : 0u, b2 = left > 2 ? (w >> 16) & 0xffu : 0u;
+        const uint32_t t = (b0 << 16) | (b1 << 8) | b2;
+        const uint32_t c0 = b64_char(t >> 18), c1 = b64_char((t >> 12) & 63u);
+        const uint32_t c2 = left > 1 ? b64_char((t >> 6) & 63u) : '=', c3 = left > 2 ? b64_char(t & 63u) : '=';
+        out4[g] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+    }
+}
+
 // the same over the rows of a batch: in [rows][in_stride] f32 -> out [rows][out_stride] i16, `width` samples per row
 // (four at a time: one 16-byte load, one 8-byte store; both strides are multiples of 4)
 __global__ void af_pcm16_rows_kernel(const float *__restrict__ in, uint64_t in_stride, int16_t *__restrict__ out, uint64_t out_stride,
@@ -905,6 +938,15 @@ cudaError_t launch_pcm16(const float *in, uint64_t n, int16_t *out, cudaStream_t
     if (n == 0) return cudaSuccess;
     const int blocks = (int)std::min<uint64_t>((n + 255) / 256, 148 * 8);
     af_pcm16_kernel<<<blocks, 256, 0, st>>>(in, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pcm16_base64(const float *in, uint64_t n, char *out, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    const uint64_t groups = (2 * n + 2) / 3;
+    const int blocks = (int)std::min<uint64_t>((groups + 255) / 256, 148 * 8);
+    af_pcm16_base64_kernel<<<blocks, 256, 0, st>>>(in, n, reinterpret_cast<uint32_t *>(out));
     return cudaGetLastError();
 }
 

@@ -91,6 +91,7 @@ cudaError_t launch_resample_jobs(const ResampleJob *jobs_dev, uint32_t n_jobs, u
 cudaError_t launch_frame_energy(const EnergyJob &job, cudaStream_t st);
 cudaError_t launch_vad_scan(const ScanJob &job, cudaStream_t st);
 cudaError_t launch_pcm16(const float *in, uint64_t n, int16_t *out, cudaStream_t st);
+cudaError_t launch_pcm16_base64(const float *in, uint64_t n, char *out, cudaStream_t st);   // 4 * ceil(2 n / 3) characters
 cudaError_t launch_pcm16_rows(const float *in, uint64_t in_stride, int16_t *out, uint64_t out_stride, uint32_t width, uint32_t rows,
                               cudaStream_t st);
 cudaError_t launch_vad_segments(const uint8_t *states, uint64_t stride, const uint32_t *n_frames, uint32_t n_streams,

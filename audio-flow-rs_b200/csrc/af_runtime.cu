@@ -662,6 +662,30 @@ AF_API int af_pcm16_encode(const float *samples, size_t n, int16_t *out)
     return AF_OK;
 }
 
+AF_API size_t af_pcm16_base64_len(size_t n_samples) { return 4 * ((2 * n_samples + 2) / 3); }
+
+AF_API int af_pcm16_base64(const float *samples, size_t n, char *out, size_t out_cap, size_t *n_out)
+{
+    if (n_out) *n_out = 0;
+    if ((!samples || !out) && n) return fail(AF_ERR_INVALID, "null buffer");
+    const size_t need = af_pcm16_base64_len(n);
+    if (out_cap < need) return fail(AF_ERR_CAPACITY, "base64 output needs %zu characters, capacity %zu", need, out_cap);
+    int rc = require_ctx();
+    if (rc) return rc;
+    if (n == 0) return AF_OK;
+    std::lock_guard<std::mutex> lk(cur_ctx().mu);
+    cudaStream_t st = cur_ctx().stream;
+    AF_CUDA(cur_ctx().scratch_in.reserve(n * sizeof(float)));
+    AF_CUDA(cur_ctx().scratch_out.reserve(need));
+    AF_CUDA(cudaMemcpyAsync(cur_ctx().scratch_in.p, samples, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    AF_CUDA(launch_pcm16_base64((const float *)cur_ctx().scratch_in.p, n, (char *)cur_ctx().scratch_out.p, st));
+    count_launch();
+    AF_CUDA(cudaMemcpyAsync(out, cur_ctx().scratch_out.p, need, cudaMemcpyDeviceToHost, st));
+    AF_CUDA(cudaStreamSynchronize(st));
+    if (n_out) *n_out = need;
+    return AF_OK;
+}
+
 AF_API int af_vad_segments(const uint8_t *states, uint64_t vad_stride, const uint32_t *n_frames, size_t n_streams,
                            uint32_t *seg, uint32_t seg_cap, uint32_t *n_seg, void *cuda_stream)
 {

@@ -135,6 +135,11 @@ AF_API int af_vad_frame_energy(const float *frame, size_t n, float *energy);
 
 /* ---- PCM16 wire encode  (src-tauri/src/modules/network/websocket.rs:246-251) ---------- */
 AF_API int af_pcm16_encode(const float *samples, size_t n, int16_t *out);
+/* The wire payload itself: base64 (standard alphabet, '=' padding) of the little-endian PCM16 bytes -- the
+ * "audio_base_64" field of WebSocketClient::send_audio / MessageBuilder::audio_message (websocket.rs:244-254, :338-348).
+ * Writes af_pcm16_base64_len(n) = 4 * ceil(2 n / 3) characters (no terminator) into out[out_cap]. */
+AF_API size_t af_pcm16_base64_len(size_t n_samples);
+AF_API int af_pcm16_base64(const float *samples, size_t n, char *out, size_t out_cap, size_t *n_out);
 
 /* ======================================================================================= */
 /* Batched fast path: many independent streams through                                     */

@@ -330,6 +330,13 @@ def pcm16_encode(x) -> np.ndarray:
     return out
 
 
+
+def pcm16_base64(x) -> bytes:
+    """websocket.rs:244-254 / :338-348: base64 (standard alphabet) of the little-endian bytes of pcm16_encode(x)."""
+    import base64
+    return base64.b64encode(pcm16_encode(x).astype("<i2").tobytes())
+
+
 def vad_segments(states) -> np.ndarray:
     s = np.ascontiguousarray(states, dtype=np.uint8)
     cap = len(s) // 2 + 2

@@ -175,6 +175,14 @@ def test_pcm16(orc):
     assert orc.pcm16_encode(x).tolist() == [0, 32767, -32767, 32767, -32767, 16383, -16383, 0, 0, 32766]
 
 
+def test_pcm16_base64(orc):
+    # the payload of websocket.rs:244-254 for a ramp: the bytes are the little-endian i16 samples
+    import base64
+    x = np.array([0.0, 0.5, -0.5, 1.0, -1.0], np.float32)
+    b = base64.b64decode(orc.pcm16_base64(x))
+    assert np.frombuffer(b, '<i2').tolist() == [0, 16383, -16383, 32767, -32767]
+
+
 def test_segments(orc):
     st = np.array([0, 1, 1, 1, 2, 0, 0, 1, 1, 0, 1], np.uint8)
     assert orc.vad_segments(st).tolist() == [[1, 5], [7, 9], [10, 11]]

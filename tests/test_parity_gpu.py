@@ -220,6 +220,17 @@ def test_pcm16_matches_oracle(af, orc):
     assert np.array_equal(af.pcm16_encode(x), orc.pcm16_encode(x))
 
 
+def test_pcm16_base64_wire_payload(af, orc):              # websocket.rs:244-254 ("audio_base_64")
+    rng = np.random.default_rng(6)
+    special = np.array([0.0, 1.0, -1.0, np.nan, 1e-5, -1e-5, 0.99999, 2.0, -3.0, np.inf, -np.inf], np.float32)
+    for n in (0, 1, 2, 3, 4, 5, 6, 7, 320, 959, 960, 16000, 100003):
+        x = rng.uniform(-1.2, 1.2, n).astype(np.float32)
+        x[:min(n, len(special))] = special[:min(n, len(special))]
+        got = af.pcm16_base64(x)
+        assert len(got) == 4 * ((2 * n + 2) // 3)
+        assert got == orc.pcm16_base64(x), f"n = {n}"
+
+
 # =============================================================================================
 # the batched pipeline
 # =============================================================================================
