@@ -446,6 +446,51 @@ __device__ __forceinline__ void resample_quads_48k(const float *__restrict__ x0,
         if (i4 < i_hi) quad(px, yq, pq, i4);
 }
 
+// ---- the same for 48 kHz STEREO f32 (cfg4): four outputs per thread and quad from 14 stereo frames = seven LDS.128 ----
+// x0 points at the stereo frame of tap y0 of step-buffer sample 0.  For a quad (i4 = 0 mod 4) the first frame it reads,
+// 3 i4 - 1 past x0's frame, is even relative to a 16-byte boundary of the stage, so the 28 floats are seven aligned float4.
+// Downmix as AudioFrame::to_mono does ((0 + l) + r) / 2, in packed arithmetic (an addition followed by a multiplication:
+// nothing ptxas could contract), then the mono quad's test for the bit-exact frac = 0 shortcut.
+__device__ __forceinline__ void resample_quads_48k_stereo(const float *__restrict__ x0, float *__restrict__ yb, float *pq0, int lim4,
+                                                          int i_lo, int i_hi, int rtid)
+{
+    constexpr int QS = 4 * RS_THREADS;
+    int i4 = (i_lo & ~31) + 4 * rtid;
+    if (i4 < i_lo) i4 += QS;
+    const float4 *px = reinterpret_cast<const float4 *>(x0 + 6 * i4);          // 3 frames x 2 floats per output
+    float *yq = yb + ypad(i4);
+    float *pq = pq0 + i4;
+    const f2 zero = mk2(0.0f, 0.0f), half = mk2(0.5f, 0.5f);
+    for (; i4 < i_hi; i4 += QS) {
+        float m[14];                                                            // mono frames 3 i4 - 1 ... 3 i4 + 12 (the last is not used)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const float4 v = px[j];                                             // frames 2 j, 2 j + 1 of the quad: (l, r, l, r)
+            const f2 mm = mul2(add2(add2(zero, mk2(v.x, v.z)), mk2(v.y, v.w)), half);
+            m[2 * j] = mm.x; m[2 * j + 1] = mm.y;
+        }
+        uint32_t orx = 0;
+#pragma unroll
+        for (int j = 0; j < 13; ++j) orx |= __float_as_uint(m[j]);
+        float4 y = make_float4(m[1], m[4], m[7], m[10]);
+        if (!((orx & 0x40000000u) == 0u && y.x != 0.0f && y.y != 0.0f && y.z != 0.0f && y.w != 0.0f)) {
+            y.x = interp_cubic(0.0f, m[0], m[1], m[2], m[3]);
+            y.y = interp_cubic(0.0f, m[3], m[4], m[5], m[6]);
+            y.z = interp_cubic(0.0f, m[6], m[7], m[8], m[9]);
+            y.w = interp_cubic(0.0f, m[9], m[10], m[11], m[12]);
+        }
+        *reinterpret_cast<float4 *>(yq) = y;
+        if (i4 <= lim4) __stcs(reinterpret_cast<float4 *>(pq), y);
+        else {
+            const int left = lim4 + 4 - i4;
+            if (left > 0) __stcs(pq, y.x);
+            if (left > 1) __stcs(pq + 1, y.y);
+            if (left > 2) __stcs(pq + 2, y.z);
+        }
+        px += 6 * QS / 4; yq += ypad(QS); pq += QS;
+    }
+}
+
 // ---- general rational step, interior part (44.1 kHz -> 16 kHz: 441/160 with table fractions; 8 / 24 / 32 kHz: exact) ----
 // Four consecutive outputs per thread and quad: exact integer positions advanced by p / q per output, 16 unchecked taps,
 // four unfused cubics (the reference's operation order), one 16-byte store to the step buffer and one to HBM.  The table
@@ -1220,6 +1265,8 @@ __device__ __forceinline__ void role_resample_split(FusedSmem &sm, const FusedPa
         else if (s.channels == 2) kind = s.format == FMT_F32 ? K_F32_2 : K_I16_2;
         float *pcm_row = P.pcm ? P.pcm + (uint64_t)t.stream * P.pcm_stride : nullptr;
         // does this tile's fast path hand out output quads to fixed owner threads (see resample_half_fast)?
+        // 48 kHz stereo f32 (cfg4): its staged interior parts take a quad loop of their own
+        const bool hot2 = kind == K_F32_2 && s.mode != RS_PASSTHROUGH && s.q == 1 && s.p == 3;
         const bool quad_tile = s.mode != RS_PASSTHROUGH && ((kind == K_F32_1 && s.q == 1 && s.p == 3) || (kind != K_GENERIC && s.q > 1));
         bool prev_quads = false;
         // the hot case -- 48 kHz mono f32 -- bypasses the format dispatch: its interior half steps go straight to the quad loop
@@ -1247,7 +1294,7 @@ __device__ __forceinline__ void role_resample_split(FusedSmem &sm, const FusedPa
                     // the quad paths give every output quad a fixed owner thread: each thread carries the quad it wrote
                     // itself in the previous step -- no synchronisation among the resampler warps
                     constexpr int QS = 4 * RS_THREADS;
-                    int c4 = LAST_PART_LO2 + 4 * rtid;
+                    int c4 = (parts == 4u ? part_end(4, 2) : LAST_PART_LO2) + 4 * rtid;   // first quad of the step's last part
                     c4 += ((STEP_SAMPLES - c4 + QS - 1) / QS) * QS;           // first own quad at or after STEP_SAMPLES
                     if (c4 < YLEN)
                         *reinterpret_cast<float4 *>(out.yb + ypad(c4 - STEP_SAMPLES)) = *reinterpret_cast<const float4 *>(prev + ypad(c4));
@@ -1263,7 +1310,11 @@ __device__ __forceinline__ void role_resample_split(FusedSmem &sm, const FusedPa
                 const int i_lo = part_lo(g, (int)parts, k), i_hi = part_end((int)parts, k);
                 AF_WAIT(&sm.stage_full[h], (uses0 + ((uint32_t)k >> 1)) & 1u, 1);
                 AF_TIC2
-                if (HOT && sm.st_interior[h] == 1u) {
+                if (!HOT && hot2 && sm.st_interior[h] == 1u) {
+                    resample_quads_48k_stereo(reinterpret_cast<const float *>(sm.stage[h]) +
+                                                  2 * (tile_k + 3 * (int)toff - 1 - (int)((uint32_t)sm.st_lo[h] >> 1)),
+                                              out.yb, out.pcm + out.base, lim4, i_lo, i_hi, rtid);
+                } else if (HOT && sm.st_interior[h] == 1u) {
                     resample_quads_48k(reinterpret_cast<const float *>(sm.stage[h]) + (tile_k + 3 * (int)toff - 1 - (int)(uint32_t)sm.st_lo[h]),
                                        out.yb, out.pcm + out.base, lim4, i_lo, i_hi, rtid);
                 } else if (HOT) {
@@ -1278,7 +1329,8 @@ __device__ __forceinline__ void role_resample_split(FusedSmem &sm, const FusedPa
                     }
                 }
                 AF_TOC(4)
-                if (k == (int)parts - 1) prev_quads = quad_tile && parts == 2u && sm.st_interior[1] != 0u;   // (read before the stage is released)
+                if (k == (int)parts - 1)                       // (read before the stage is released)
+                    prev_quads = hot2 ? sm.st_interior[1] == 1u : (quad_tile && parts == 2u && sm.st_interior[1] != 0u);
                 warp_arrive(&sm.stage_empty[h], lane);          // this warp no longer reads stage[h] or its metadata
             }
             if (rtid == 0) {

@@ -589,7 +589,11 @@ def measure_cfg4(env: Env, steps: int, warmup: int):
         L.af_vad_gate(pcm.data_ptr(), b.pcm_stride, lm.data_ptr(), b.logmel_stride, M, nout.data_ptr(), 160, seg.data_ptr(), seg_cap,
                       nseg.data_ptr(), 1, C.byref(go), st)
 
+    if env.args.pipe_stats:
+        pipe_stats_clear()
     ms, _, _, _ = env.timed(step, steps, warmup)
+    if env.args.pipe_stats:
+        pipe_stats_print()
     msg, _, _, _ = env.timed(step_gate, steps, warmup)
     alg = (48000 * 2 * 4 + 16000 * 4 + 100 * M * 4 + 100) * sec
     peak, _ = measured_peak_gbs()
