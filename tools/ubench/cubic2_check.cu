@@ -1,8 +1,10 @@
-// Does a packed (f32x2) cubic reproduce the scalar one bit for bit?  NO (measured on B200, CUDA 12.9): ptxas contracts
-// mul.rn.f32x2 + add.rn.f32x2 into FFMA2 despite the explicit rounding modifiers -- also when the product is written as
-// fma(a, b, -0) and also with -Xptxas -fmad=false -- so 30 % of random cubics come out one ulp off.  The scalar
-// __fmul_rn/__fadd_rn path is never contracted.  This is why the general-ratio resampler (44.1 kHz) keeps scalar
-// arithmetic although it is the instruction-bound part of cfg3.
+// Does a packed (f32x2) cubic reproduce the scalar one bit for bit?  As written naively: NO (measured on B200, CUDA 12.9) --
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 despite the explicit rounding modifiers, also when the product is
+// written as fma(a, b, -0) with a literal zero and also with -Xptxas -fmad=false, so 30 % of random cubics come out one ulp
+// off (kernel `k`).  Variant Z (kernel `kz`): every product is fma(a, b, z) with z = -0.0f passed as a KERNEL ARGUMENT.  ptxas
+// cannot fold an addend it does not know, nothing is left to contract (SASS: 11 FFMA2 with a broadcast .F32 addend + 11 FADD2
+// per pair of outputs), and a * b + (-0) == RN(a * b) for every a, b: 0 mismatches in 2^20 pairs.  That variant is
+// interp_cubic2 (af_device.cuh), used by the general-ratio resampler.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -o cubic2_check cubic2_check.cu
 #include <cstdio>
 #include <cstdint>
