@@ -10,6 +10,7 @@
 //!
 //! Source only: the graft build image has no Rust toolchain.
 mod ffi;
+pub mod batch;
 
 use std::ptr;
 
