@@ -1,3 +1,6 @@
+"""Per-role wait statistics (stats build, AF_GPU_LIB=.../libaudioflow_gpu_stats.so) of cfg2 with and without the PCM write-out:
+are the resampler warps' global stores what their barrier arrives wait for?  Measured: no -- the shares are the same and the
+kernel is only 2 % faster without the stores."""
 import os, sys, ctypes as C
 sys.path.insert(0, 'audio-flow-rs_b200'); sys.path.insert(0, '.')
 import torch, numpy as np
