@@ -605,17 +605,28 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_long_a_kernel(const ScanJ
         // a second one to leave Ending -- a speech frame right after a single zero would be swallowed by Ending -> Silence
         // (vad.rs:147-151), which a fresh machine does not reproduce
         const uint32_t need = max(timeout, 1u) + 1u;
+        uint32_t next_bits = s_bits[0];
         for (uint32_t w = 0; w < n_words; ++w) {
-            const uint32_t bits = s_bits[w], m_n = min(32u, n - w * 32);
+            const uint32_t bits = next_bits, m_n = min(32u, n - w * 32);
+            if (w + 1 < n_words) next_bits = s_bits[w + 1];                 // (the load overlaps this word's walk)
             uint32_t *en = V.entry + 3 * (size_t)((b0 >> 5) + w);
             en[0] = m.st; en[1] = m.sil; en[2] = m.spk;
+            // whole words of silence in Silence, or of speech in Speech, leave the machine where it is (up to the count)
+            if (m.st == 0u && bits == 0u) { zrun += m_n; continue; }
+            if (m.st == 1u && m_n == 32u && bits == 0xffffffffu && (sync != NO_SYNC || zrun < need)) {
+                m.spk += 32u; m.sil = 0u; zrun = 0;
+                continue;
+            }
             vad_machine_word_t(m, bits, m_n, none, timeout, minsp);
             if (sync == NO_SYNC) {                              // (only until the first one is found)
-                for (uint32_t j = 0; j < m_n; ++j) {
-                    if ((bits >> j) & 1u) {
-                        if (zrun >= need) { sync = w * 32 + j; break; }
-                        zrun = 0;
-                    } else ++zrun;
+                if (bits == 0u) zrun += m_n;
+                else {
+                    for (uint32_t j = 0; j < m_n; ++j) {
+                        if ((bits >> j) & 1u) {
+                            if (zrun >= need) { sync = w * 32 + j; break; }
+                            zrun = 0;
+                        } else ++zrun;
+                    }
                 }
             }
         }
