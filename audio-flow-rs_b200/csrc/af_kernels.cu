@@ -635,10 +635,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_long_a_kernel(const ScanJ
     }
 }
 
-// phase B: one thread per stream carries the true EMA and machine state from block to block
-__global__ void af_vad_long_b_kernel(const ScanJob J)
+// phase B: one WARP per stream carries the true EMA and machine state from block to block.  The walk is sequential, so
+// every lane executes it redundantly (same registers, same control flow); what the warp buys is the loads: the per-block
+// records of 32 blocks at a time (one per lane, handed round by shuffles) and the decision bits of the words in front of a
+// block's sync point as coalesced 32-word loads, instead of a dependent global load per block and per word (33 -> ~10 us
+// for one hour of audio).
+__global__ void __launch_bounds__(32) af_vad_long_b_kernel(const ScanJob J)
 {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t s = blockIdx.x, lane = threadIdx.x;
     if (s >= J.n_streams) return;
     const uint32_t T = J.n_frames ? J.n_frames[s] : J.n_frames_all;
     const LongScanView V = long_scan_view(J.scratch, J.max_frames, s);
@@ -648,47 +652,79 @@ __global__ void af_vad_long_b_kernel(const ScanJob J)
     const bool use_smoothed = alpha > 0.0f;
     const uint32_t timeout = (uint32_t)prm.silence_timeout, minsp = (uint32_t)prm.min_speech;
     const uint32_t nb = (T + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    constexpr uint32_t FULL = 0xffffffffu;
     float carry_s = 0.0f;
     VadMachine m{0u, 0u, 0u};
     EmitNone none;
-    for (uint32_t blk = 0; blk < nb; ++blk) {
-        const uint32_t b0 = blk * SCAN_BLOCK, n = min(SCAN_BLOCK, T - b0), n_words = (n + 31) / 32;
-        bool rewalk_all = false;
-        if (blk > 0 && __float_as_uint(V.spec[blk]) != __float_as_uint(carry_s)) {
-            // (rare) the warm-up did not reproduce the true EMA: redo this block's decisions from the true value
-            float sm = carry_s;
-            for (uint32_t w = 0; w < n_words; ++w) {
-                const uint32_t mw = min(32u, n - w * 32);
-                uint32_t bits = 0;
-                for (uint32_t j = 0; j < mw; ++j) {
-                    const float ev = e[b0 + w * 32 + j];
-                    sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
-                    bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
+    for (uint32_t blk0 = 0; blk0 < nb; blk0 += 32) {
+        // the records phase A left for blocks blk0 .. blk0 + 31, one block per lane
+        const uint32_t mb = blk0 + lane;
+        float l_spec = 0.0f, l_end = 0.0f;
+        uint32_t l_sync = NO_SYNC, l_e0 = 0, l_e1 = 0, l_e2 = 0;
+        if (mb < nb) {
+            l_spec = V.spec[mb]; l_end = V.end[mb]; l_sync = V.sync[mb];
+            l_e0 = V.exit[3 * mb]; l_e1 = V.exit[3 * mb + 1]; l_e2 = V.exit[3 * mb + 2];
+        }
+        const uint32_t kn = min(32u, nb - blk0);
+        for (uint32_t k = 0; k < kn; ++k) {
+            const uint32_t blk = blk0 + k;
+            const float spec = __shfl_sync(FULL, l_spec, k);
+            float end_v = __shfl_sync(FULL, l_end, k);
+            const uint32_t sync_rec = __shfl_sync(FULL, l_sync, k);
+            const VadMachine exit_m{__shfl_sync(FULL, l_e0, k), __shfl_sync(FULL, l_e1, k), __shfl_sync(FULL, l_e2, k)};
+            const uint32_t b0 = blk * SCAN_BLOCK, n = min(SCAN_BLOCK, T - b0), n_words = (n + 31) / 32;
+            if (blk > 0 && __float_as_uint(spec) != __float_as_uint(carry_s)) {
+                // (rare) the warm-up did not reproduce the true EMA: redo this block's decisions from the true value and walk
+                // them at once from the true machine state (every lane computes the same; lane 0 stores)
+                float sm = carry_s;
+                for (uint32_t w = 0; w < n_words; ++w) {
+                    const uint32_t mw = min(32u, n - w * 32);
+                    uint32_t bits = 0;
+                    for (uint32_t j = 0; j < mw; ++j) {
+                        const float ev = e[b0 + w * 32 + j];
+                        sm = __fadd_rn(__fmul_rn(alpha, ev), __fmul_rn(beta, sm));
+                        bits |= ((use_smoothed ? sm : ev) >= e_min ? 1u : 0u) << j;
+                    }
+                    if (lane == 0) {
+                        V.bits[(b0 >> 5) + w] = bits;
+                        uint32_t *en = V.entry + 3 * (size_t)((b0 >> 5) + w);
+                        en[0] = m.st; en[1] = m.sil; en[2] = m.spk;
+                    }
+                    vad_machine_word_t(m, bits, mw, none, timeout, minsp);
                 }
-                V.bits[(b0 >> 5) + w] = bits;
+                if (lane == 0) V.end[blk] = sm;
+                carry_s = sm;
+                continue;
             }
-            V.end[blk] = sm;
-            rewalk_all = true;
+            carry_s = end_v;
+            const bool as_assumed = m.st == 0u && m.sil == 0u && m.spk == 0u;
+            if (blk == 0 || as_assumed) {                           // the speculative walk started from the true state
+                m = exit_m;
+                continue;
+            }
+            const uint32_t stop = sync_rec == NO_SYNC ? n : sync_rec;   // frames [0, stop) of the block need the true walk
+            const uint32_t words = (stop + 31) / 32;
+            for (uint32_t w0 = 0; w0 < words; w0 += 32) {
+                const uint32_t my = w0 + lane < words ? V.bits[(b0 >> 5) + w0 + lane] : 0u;   // 32 words per load
+                const uint32_t wn = min(32u, words - w0);
+                for (uint32_t j = 0; j < wn; ++j) {
+                    const uint32_t w = w0 + j, bits = __shfl_sync(FULL, my, j);
+                    if (lane == 0) {
+                        uint32_t *en = V.entry + 3 * (size_t)((b0 >> 5) + w);
+                        en[0] = m.st; en[1] = m.sil; en[2] = m.spk;
+                    }
+                    const uint32_t m_n = min(min(32u, n - w * 32), stop - w * 32);
+                    vad_machine_word_t(m, bits, m_n, none, timeout, minsp);
+                }
+            }
+            if (sync_rec != NO_SYNC) m = exit_m;                    // exact from the sync point on
         }
-        carry_s = V.end[blk];
-        const bool as_assumed = m.st == 0u && m.sil == 0u && m.spk == 0u;
-        if (!rewalk_all && (blk == 0 || as_assumed)) {          // the speculative walk started from the true state
-            m = VadMachine{V.exit[3 * blk], V.exit[3 * blk + 1], V.exit[3 * blk + 2]};
-            continue;
-        }
-        const uint32_t sync = rewalk_all ? NO_SYNC : V.sync[blk];
-        const uint32_t stop = sync == NO_SYNC ? n : sync;       // frames [0, stop) of the block need the true walk
-        for (uint32_t w = 0; w * 32 < stop; ++w) {
-            uint32_t *en = V.entry + 3 * (size_t)((b0 >> 5) + w);
-            en[0] = m.st; en[1] = m.sil; en[2] = m.spk;
-            const uint32_t m_n = min(min(32u, n - w * 32), stop - w * 32);
-            vad_machine_word_t(m, V.bits[(b0 >> 5) + w], m_n, none, timeout, minsp);
-        }
-        if (sync != NO_SYNC) m = VadMachine{V.exit[3 * blk], V.exit[3 * blk + 1], V.exit[3 * blk + 2]};   // exact from the sync point on
     }
-    VadState v;
-    v.smoothed = carry_s; v.state = (int)m.st; v.silence_frames = m.sil; v.speech_frames = m.spk;
-    if (J.final_out) J.final_out[s] = v;
+    if (lane == 0) {
+        VadState v;
+        v.smoothed = carry_s; v.state = (int)m.st; v.silence_frames = m.sil; v.speech_frames = m.spk;
+        if (J.final_out) J.final_out[s] = v;
+    }
 }
 
 // phase C: every word expands into state bytes from its (now exact) entry state
@@ -753,7 +789,7 @@ cudaError_t launch_vad_scan(const ScanJob &job, cudaStream_t st)
             // long streams: speculative block walks in parallel, a cheap sequential carry pass, parallel expansion
             const dim3 grid(long_scan_blocks(job.max_frames), job.n_streams);
             af_vad_long_a_kernel<<<grid, SCAN_THREADS, 0, st>>>(job, warm);
-            af_vad_long_b_kernel<<<(job.n_streams + 31) / 32, 32, 0, st>>>(job);
+            af_vad_long_b_kernel<<<job.n_streams, 32, 0, st>>>(job);
             af_vad_long_c_kernel<<<grid, SCAN_THREADS, 0, st>>>(job);
             return cudaGetLastError();
         }
