@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
 {
     __shared__ uint32_t s_bits[SCAN_BLOCK / 32];
     __shared__ uint32_t s_entry[SCAN_BLOCK / 32][3];
+    __shared__ uint32_t s_exit[SCAN_BLOCK / 32][4];     // per chain head: the machine after the chain, and the OR of its bits
     __shared__ float s_spec[SCAN_BLOCK / SCAN_CHUNK], s_end[SCAN_BLOCK / SCAN_CHUNK];
     __shared__ float s_e[SCAN_E_FLOATS];                // energies of [b0 - lead, b0 + n), padded (epad)
     __shared__ int s_bad;
@@ -435,19 +436,60 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_scan_par_kernel(const Sca
             __syncthreads();
         }
         AF_SCAN_T(3)
-        // ---- phase 2: one thread walks the words, recording the machine state at every word boundary ----
-        if (tid == 0) {
+        // ---- phase 2: the machine state at every word boundary ----
+        // After `need` = max(timeout, 1) + 1 non-speech frames the machine is in Silence whatever came before (Speech times
+        // out, Ending lasts one frame), so a word whose predecessor ends with that many zeros is the head of a CHAIN that can
+        // be walked on its own from a fresh Silence; the block's first word starts from the carried state.  One thread per
+        // chain (a speech burst and its hang-over: a few words), all chains at once, instead of one thread over all words.
+        // What a fresh Silence does not know is the silence_frames count Silence was entered with (it does not act on
+        // anything, but it is state): thread 0 hands it down the chains afterwards.
+        const uint32_t need = max(timeout, 1u) + 1u;
+        if (need <= 32u) {
+            for (uint32_t h = tid; h < n_words; h += SCAN_THREADS) {
+                if (h != 0u && (s_bits[h - 1] >> (32u - need)) != 0u) continue;         // not a head
+                VadMachine m = h == 0u ? carry_m : VadMachine{0u, 0u, 0u};
+                EmitNone none;
+                uint32_t w = h, seen = 0u;
+                for (;;) {
+                    const uint32_t bits = s_bits[w], m_n = min(32u, n - w * 32);
+                    s_entry[w][0] = m.st; s_entry[w][1] = m.sil; s_entry[w][2] = m.spk;
+                    seen |= bits;
+                    // whole words of silence in Silence, or of speech in Speech, leave the machine where it is (up to the count)
+                    if (m.st == 0u && bits == 0u) {}
+                    else if (m.st == 1u && m_n == 32u && bits == 0xffffffffu) { m.spk += 32u; m.sil = 0u; }
+                    else vad_machine_word_t(m, bits, m_n, none, timeout, minsp);
+                    ++w;
+                    if (w >= n_words || (bits >> (32u - need)) == 0u) break;            // the next word heads a chain of its own
+                }
+                s_exit[h][0] = m.st; s_exit[h][1] = m.sil; s_exit[h][2] = m.spk; s_exit[h][3] = seen;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                VadMachine last = carry_m;
+                uint32_t w = 0;
+                while (w < n_words) {                       // w is a head
+                    const uint32_t entry_sil = last.sil;   // true silence_frames at the head (chain 0 already started from it)
+                    const bool fresh = w != 0u;
+                    uint32_t e = w, seen = 0u;               // patch the words the chain enters in its initial Silence
+                    for (;;) {
+                        if (fresh && entry_sil != 0u && seen == 0u) s_entry[e][1] = entry_sil;
+                        const uint32_t bits = s_bits[e];
+                        seen |= bits;
+                        ++e;
+                        if (e >= n_words || (bits >> (32u - need)) == 0u) break;
+                    }
+                    last = VadMachine{s_exit[w][0], s_exit[w][1], s_exit[w][2]};
+                    if (fresh && s_exit[w][3] == 0u) last.sil = entry_sil;              // never left Silence: the count stays
+                    w = e;
+                }
+                carry_m = last;
+            }
+        } else if (tid == 0) {
             VadMachine m = carry_m;
             EmitNone none;
-            uint32_t next_bits = s_bits[0];
             for (uint32_t w = 0; w < n_words; ++w) {
-                const uint32_t bits = next_bits, m_n = min(32u, n - w * 32);
-                if (w + 1 < n_words) next_bits = s_bits[w + 1];                     // (the load overlaps this word's walk)
                 s_entry[w][0] = m.st; s_entry[w][1] = m.sil; s_entry[w][2] = m.spk;
-                // whole words of silence in Silence, or of speech in Speech, leave the machine where it is (up to the count)
-                if (m.st == 0u && bits == 0u) continue;
-                if (m.st == 1u && m_n == 32u && bits == 0xffffffffu) { m.spk += 32u; m.sil = 0u; continue; }
-                vad_machine_word_t(m, bits, m_n, none, timeout, minsp);
+                vad_machine_word_t(m, s_bits[w], min(32u, n - w * 32), none, timeout, minsp);
             }
             carry_m = m;
         }
