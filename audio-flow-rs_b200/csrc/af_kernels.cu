@@ -582,6 +582,7 @@ constexpr uint32_t NO_SYNC = 0xffffffffu;
 __global__ void __launch_bounds__(SCAN_THREADS) af_vad_long_a_kernel(const ScanJob J, uint32_t warm)
 {
     __shared__ uint32_t s_bits[SCAN_BLOCK / 32];
+    __shared__ uint32_t s_exit[SCAN_BLOCK / 32][5];     // per chain head: machine after the chain, OR of its bits, its sync candidate
     __shared__ float s_spec[SCAN_BLOCK / SCAN_CHUNK], s_end[SCAN_BLOCK / SCAN_CHUNK];
     __shared__ float s_e[SCAN_E_FLOATS];
     __shared__ int s_bad;
@@ -637,8 +638,74 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_long_a_kernel(const ScanJ
     }
     __syncthreads();
     for (uint32_t w = tid; w < n_words; w += SCAN_THREADS) V.bits[(b0 >> 5) + w] = s_bits[w];
-    if (tid == 0) {
-        V.spec[blk] = s_spec[0]; V.end[blk] = s_end[n_chunks - 1];
+    if (tid == 0) { V.spec[blk] = s_spec[0]; V.end[blk] = s_end[n_chunks - 1]; }
+    // silence_timeout == 0 behaves like 1 here: the first non-speech frame moves Speech to Ending / Silence, and it takes
+    // a second one to leave Ending -- a speech frame right after a single zero would be swallowed by Ending -> Silence
+    // (vad.rs:147-151), which a fresh machine does not reproduce
+    const uint32_t need = max(timeout, 1u) + 1u;
+    if (need <= 32u) {
+        // Speculative walk from a fresh machine, chain-parallel as in af_vad_scan_par_kernel: a word whose predecessor ends
+        // with `need` non-speech frames heads a chain that starts from a fresh Silence, one thread per chain.  The first speech
+        // frame of such a chain is a sync point of the block by construction; inside the block's first chain (which has no
+        // run of zeros in front of it) the sync point is searched bit by bit as before.
+        for (uint32_t h = tid; h < n_words; h += SCAN_THREADS) {
+            if (h != 0u && (s_bits[h - 1] >> (32u - need)) != 0u) continue;             // not a head
+            VadMachine m{0u, 0u, 0u};
+            EmitNone none;
+            uint32_t w = h, seen = 0u, first = NO_SYNC, zrun = 0u;
+            for (;;) {
+                const uint32_t bits = s_bits[w], m_n = min(32u, n - w * 32);
+                uint32_t *en = V.entry + 3 * (size_t)((b0 >> 5) + w);
+                en[0] = m.st; en[1] = m.sil; en[2] = m.spk;
+                if (h != 0u) {
+                    if (first == NO_SYNC && bits != 0u) first = w * 32 + (uint32_t)__ffs((int)bits) - 1u;
+                } else if (first == NO_SYNC) {                                      // the block's first chain: bit by bit
+                    if (bits == 0u) zrun += m_n;
+                    else {
+                        for (uint32_t j = 0; j < m_n; ++j) {
+                            if ((bits >> j) & 1u) {
+                                if (zrun >= need) { first = w * 32 + j; break; }
+                                zrun = 0;
+                            } else ++zrun;
+                        }
+                    }
+                }
+                seen |= bits;
+                // whole words of silence in Silence, or of speech in Speech, leave the machine where it is (up to the count)
+                if (m.st == 0u && bits == 0u) {}
+                else if (m.st == 1u && m_n == 32u && bits == 0xffffffffu) { m.spk += 32u; m.sil = 0u; }
+                else vad_machine_word_t(m, bits, m_n, none, timeout, minsp);
+                ++w;
+                if (w >= n_words || (bits >> (32u - need)) == 0u) break;                // the next word heads a chain of its own
+            }
+            s_exit[h][0] = m.st; s_exit[h][1] = m.sil; s_exit[h][2] = m.spk; s_exit[h][3] = seen; s_exit[h][4] = first;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // in order over the chains: the block's first sync point, the silence_frames count Silence was entered with (a
+            // fresh Silence assumed 0) handed down the chains, the machine after the last one
+            VadMachine last{0u, 0u, 0u};
+            uint32_t sync = NO_SYNC, w = 0;
+            while (w < n_words) {                                                       // w is a head
+                const uint32_t entry_sil = last.sil;
+                const bool fresh = w != 0u;
+                uint32_t e = w, seen = 0u;
+                for (;;) {
+                    if (fresh && entry_sil != 0u && seen == 0u) V.entry[3 * (size_t)((b0 >> 5) + e) + 1] = entry_sil;
+                    const uint32_t bits = s_bits[e];
+                    seen |= bits;
+                    ++e;
+                    if (e >= n_words || (bits >> (32u - need)) == 0u) break;
+                }
+                if (sync == NO_SYNC) sync = s_exit[w][4];
+                last = VadMachine{s_exit[w][0], s_exit[w][1], s_exit[w][2]};
+                if (fresh && s_exit[w][3] == 0u) last.sil = entry_sil;                  // never left Silence: the count stays
+                w = e;
+            }
+            V.sync[blk] = sync;
+            V.exit[3 * blk] = last.st; V.exit[3 * blk + 1] = last.sil; V.exit[3 * blk + 2] = last.spk;
+        }
+    } else if (tid == 0) {
         // speculative walk from a fresh machine + the first sync point
         VadMachine m{0u, 0u, 0u};
         EmitNone none;
@@ -646,7 +713,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) af_vad_long_a_kernel(const ScanJ
         // silence_timeout == 0 behaves like 1 here: the first non-speech frame moves Speech to Ending / Silence, and it takes
         // a second one to leave Ending -- a speech frame right after a single zero would be swallowed by Ending -> Silence
         // (vad.rs:147-151), which a fresh machine does not reproduce
-        const uint32_t need = max(timeout, 1u) + 1u;
         uint32_t next_bits = s_bits[0];
         for (uint32_t w = 0; w < n_words; ++w) {
             const uint32_t bits = next_bits, m_n = min(32u, n - w * 32);
