@@ -391,6 +391,8 @@ ORC_API int orc_vad_state(const orc_vad *v) { return v->state; }                
 ORC_API float orc_vad_energy_db(const orc_vad *v) { return orc_energy_to_dbfs(v->smoothed_energy); } /* :192-194 */
 ORC_API int orc_vad_is_speaking(const orc_vad *v) { return v->state == ORC_SPEECH; }       /* :197-199 */
 ORC_API uint64_t orc_vad_speech_frame_count(const orc_vad *v) { return v->speech_frames; } /* :202-204 */
+/* the private field behind the timeout (vad.rs:72): no accessor in the reference; exposed for the state-exactness tests */
+ORC_API uint64_t orc_vad_silence_frames(const orc_vad *v) { return v->silence_frames; }
 ORC_API float orc_vad_smoothed_energy(const orc_vad *v) { return v->smoothed_energy; }
 
 /* Framed VAD over a whole 16 kHz stream: frames [f*hop, f*hop+len), "valid" framing.

@@ -88,6 +88,8 @@ def lib():
     L.orc_vad_is_speaking.argtypes = [C.c_void_p]
     L.orc_vad_speech_frame_count.restype = C.c_uint64
     L.orc_vad_speech_frame_count.argtypes = [C.c_void_p]
+    L.orc_vad_silence_frames.restype = C.c_uint64
+    L.orc_vad_silence_frames.argtypes = [C.c_void_p]
     L.orc_vad_smoothed_energy.restype = C.c_float
     L.orc_vad_smoothed_energy.argtypes = [C.c_void_p]
     L.orc_vad_stream.restype = sz
@@ -249,6 +251,7 @@ class VoiceActivityDetector:
     def energy_db(self) -> float: return float(lib().orc_vad_energy_db(self._h))
     def is_speaking(self) -> bool: return bool(lib().orc_vad_is_speaking(self._h))
     def speech_frame_count(self) -> int: return int(lib().orc_vad_speech_frame_count(self._h))
+    def silence_frames(self) -> int: return int(lib().orc_vad_silence_frames(self._h))
     def smoothed_energy(self) -> float: return float(lib().orc_vad_smoothed_energy(self._h))
 
     def stream(self, y, frame_len: int, hop: int):
@@ -379,5 +382,5 @@ def pipeline_stream(samples, channels: int, in_rate: int, feat: FeatConfig | Non
         v = VoiceActivityDetector(vad)
         out["vad"], out["energy"] = v.stream(pcm, vad_len, vad_hop)
         out["vad_final"] = dict(state=v.state(), smoothed=v.smoothed_energy(),
-                                speech_frames=v.speech_frame_count())
+                                speech_frames=v.speech_frame_count(), silence_frames=v.silence_frames())
     return out

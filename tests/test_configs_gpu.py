@@ -408,3 +408,37 @@ def test_pcm16_wire_output_host_and_device(af, orc):
     for i, ref in enumerate(refs):
         n = int(b.n_out[i])
         assert np.array_equal(pcm[i, :n].cpu().numpy(), orc.pcm16_encode(ref["pcm"])), f"device pcm16 {i}"
+
+
+@pytest.mark.parametrize("seconds", [40.0, 200.0])
+def test_scan_chains_hand_down_silence_count(af, orc, seconds):
+    """The word walk of the scan kernels is chain-parallel: a word whose predecessor ends with timeout + 1 non-speech frames is
+    walked from a fresh Silence.  What a fresh Silence cannot know is the silence_frames count Silence was entered with
+    (vad.rs:136-145: Speech that times out below min_speech_frames goes straight to Silence and keeps the count; Ending ->
+    Silence resets it).  Bursts shorter than min_speech_frames, bursts long enough for Ending, long pauses between them and a
+    silent tail: the states and the WHOLE final machine (silence_frames included) must equal the sequential reference, on the
+    one-CTA scan (40 s) and on the many-CTA one (200 s, > 16384 frames)."""
+    fs = 16000
+    rng = np.random.default_rng(int(seconds))
+    n = int(seconds * fs)
+    y = (1e-4 * rng.standard_normal(n)).astype(np.float32)
+    pos = 8000
+    k = 0
+    while pos + 40000 < n - 6 * fs:                      # alternate 20 ms bursts (one or two frames) and 400 ms bursts, 0.6-2.2 s apart
+        ln, amp = (320, 0.07) if k % 3 else (6400, 0.5)   # (a 320-sample burst at 0.07 lifts one or two frames over -50 dB)
+        y[pos:pos + ln] += (amp * rng.standard_normal(ln)).astype(np.float32)
+        pos += ln + int(rng.integers(int(0.6 * fs), int(2.2 * fs)))
+        k += 1
+    y[pos:pos + 320] += (0.07 * rng.standard_normal(320)).astype(np.float32)   # the last burst is a short one: Silence keeps the count
+    vc = orc.default_vad_config()
+    vc.smoothing_factor = 0.0                            # decisions follow the bursts frame by frame
+    cfg = af.pipeline_config(n_mels=0, vad_enable=True)
+    cfg.vad.smoothing_factor = 0.0
+    got = af.Pipeline(cfg).run_host([(y, fs, 1)])[0]
+    ref = orc.pipeline_stream(y, 1, fs, None, vc, 400, 160, "f32")
+    assert_bit_equal(got["vad"], ref["vad"], "states")
+    v = ref["vad"]
+    assert (v == 2).any() and ((v[:-1] == 1) & (v[1:] == 0)).any()      # both ways out of Speech occur
+    gf, rf = got["vad_final"], ref["vad_final"]
+    assert (gf["state"], gf["speech_frames"], gf["silence_frames"]) == (rf["state"], rf["speech_frames"], rf["silence_frames"])
+    assert rf["state"] == 0 and rf["silence_frames"] == 15
